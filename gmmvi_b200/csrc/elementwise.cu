@@ -1,0 +1,585 @@
+// Parameter preparation, mixture reductions, importance weights, diagonal-covariance kernels,
+// weight updates and the counter-based normal generator.  Everything here is bandwidth- or
+// latency-bound; no tensor-core work.
+#include "common.cuh"
+#include "../../include/gmmvi_b200.h"
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace gvi {
+
+// ---- error plumbing -------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return GVI_ERR_CUDA;
+  }
+  return GVI_OK;
+}
+int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                 long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                 long long strideC, cudaStream_t st);
+int launch_stein_stats_full(const float* X, int N, int D, const float* means, const float* W,
+                            const uint8_t* active, const float* G, int K, float* M, cudaStream_t st);
+
+// =================================================================================================
+// prepare_full: one CTA per component, fp64 arithmetic, thread-per-column forward substitution.
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+prepare_full_kernel(const float* __restrict__ chol, int D, float* __restrict__ linv, float* __restrict__ prec,
+                    float* __restrict__ cst, int32_t* __restrict__ ok, double* __restrict__ ws) {
+  const int k = blockIdx.x;
+  const float* L = chol + (long long)k * D * D;
+  double* Y = ws + (long long)k * D * D;
+  __shared__ double red[33];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  // const part and diagonal check
+  double ls = 0.0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const float d = L[(long long)i * D + i];
+    if (!(d > 0.f) || !isfinite(d)) bad = 1;
+    ls += log((double)d);
+  }
+  ls = block_sum(ls, red);
+  if (threadIdx.x == 0) {
+    cst[k] = (float)(-ls - 0.5 * D * kLog2PiD);
+    if (ok) ok[k] = bad ? 0 : 1;
+  }
+  // Y = L^-1, column c per thread
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    for (int i = 0; i < c; ++i) Y[(long long)i * D + c] = 0.0;
+    Y[(long long)c * D + c] = 1.0 / (double)L[(long long)c * D + c];
+    for (int i = c + 1; i < D; ++i) {
+      const float* Li = L + (long long)i * D;
+      double s0 = 0.0, s1 = 0.0;
+      int m = c;
+      for (; m + 1 < i; m += 2) {
+        s0 = fma((double)Li[m], Y[(long long)m * D + c], s0);
+        s1 = fma((double)Li[m + 1], Y[(long long)(m + 1) * D + c], s1);
+      }
+      if (m < i) s0 = fma((double)Li[m], Y[(long long)m * D + c], s0);
+      Y[(long long)i * D + c] = -(s0 + s1) / (double)Li[i];
+    }
+  }
+  __syncthreads();
+  float* Lo = linv + (long long)k * D * D;
+  for (long long e = threadIdx.x; e < (long long)D * D; e += blockDim.x) Lo[e] = (float)Y[e];
+  if (prec == nullptr) return;
+  // P = Y^T Y, upper part per thread-column then mirrored
+  float* P = prec + (long long)k * D * D;
+  for (int b = threadIdx.x; b < D; b += blockDim.x) {
+    for (int a = 0; a <= b; ++a) {
+      double s0 = 0.0, s1 = 0.0;
+      int i = b;
+      for (; i + 1 < D; i += 2) {
+        s0 = fma(Y[(long long)i * D + a], Y[(long long)i * D + b], s0);
+        s1 = fma(Y[(long long)(i + 1) * D + a], Y[(long long)(i + 1) * D + b], s1);
+      }
+      if (i < D) s0 = fma(Y[(long long)i * D + a], Y[(long long)i * D + b], s0);
+      const float v = (float)(s0 + s1);
+      P[(long long)a * D + b] = v;
+      P[(long long)b * D + a] = v;
+    }
+  }
+}
+
+// =================================================================================================
+// mixture logsumexp over components: out[n] = LSE_k(lq[k,n] + logw[k])
+// =================================================================================================
+__global__ void mixture_lse_kernel(const float* __restrict__ lq, const float* __restrict__ logw, int K, int N,
+                                   float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float m = -INFINITY, s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float v = lq[(long long)k * N + n] + __ldg(logw + k);
+    if (v > m) {
+      s = s * expf(m - v) + 1.f;   // m == -inf -> s*0
+      m = v;
+    } else if (v > -INFINITY) {
+      s += expf(v - m);
+    }
+  }
+  out[n] = (m > -INFINITY) ? m + logf(s) : -INFINITY;
+}
+
+// =================================================================================================
+// diagonal log densities: CTA = 32 samples (lanes) x all components (warps stride over k)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+logdens_diag_kernel(const float* __restrict__ X, int N, int D, const float* __restrict__ means,
+                    const float* __restrict__ stds, int K, float* __restrict__ lq) {
+  extern __shared__ float Xs[];   // [D][32]
+  const int n0 = blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {
+    const int r = e / D, d = e % D;
+    Xs[d * 32 + r] = (n0 + r < N) ? X[(long long)(n0 + r) * D + d] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = w + blockIdx.y * nw; k < K; k += nw * gridDim.y) {
+    const float* mu = means + (long long)k * D;
+    const float* sg = stds + (long long)k * D;
+    float ls = 0.f;
+    for (int d = lane; d < D; d += 32) ls += logf(sg[d]);
+    ls = warp_sum(ls);
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float t = (1.f / __ldg(sg + d)) * (__ldg(mu + d) - Xs[d * 32 + lane]);
+      acc = fmaf(t, t, acc);
+    }
+    if (n0 + lane < N) lq[(long long)k * N + n0 + lane] = (-0.5f * D * kLog2Pi - ls) - 0.5f * acc;
+  }
+}
+
+// grad[n,d] = - sum_k r_kn (x_nd - mu_kd) / std_kd^2;  CTA = 32 samples, threads over d
+__global__ void __launch_bounds__(256)
+mixture_grad_diag_kernel(const float* __restrict__ X, int N, int D, const float* __restrict__ means,
+                         const float* __restrict__ stds, const float* __restrict__ lq,
+                         const float* __restrict__ logw, const float* __restrict__ logq, int K,
+                         float* __restrict__ grad) {
+  __shared__ float rs[64][33];
+  const int n0 = blockIdx.x * 32;
+  for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+    const int d = d0 + threadIdx.x;
+    float x[32], acc[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      x[r] = (d < D && n0 + r < N) ? X[(long long)(n0 + r) * D + d] : 0.f;
+      acc[r] = 0.f;
+    }
+    for (int k0 = 0; k0 < K; k0 += 64) {
+      __syncthreads();
+      bool any = false;
+      for (int e = threadIdx.x; e < 64 * 32; e += blockDim.x) {
+        const int kk = e >> 5, r = e & 31;
+        const int k = k0 + kk, n = n0 + r;
+        float v = 0.f;
+        if (k < K && n < N) {
+          const float a = lq[(long long)k * N + n] + logw[k] - logq[n];
+          v = a > -60.f ? expf(a) : 0.f;
+        }
+        rs[kk][r] = v;
+        any |= v > 0.f;
+      }
+      if (!__syncthreads_or(any)) continue;
+      if (d < D) {
+        for (int kk = 0; kk < 64 && k0 + kk < K; ++kk) {
+          const float mu = means[(long long)(k0 + kk) * D + d];
+          const float sg = stds[(long long)(k0 + kk) * D + d];
+          const float iv = 1.f / (sg * sg);
+#pragma unroll
+          for (int r = 0; r < 32; ++r) acc[r] = fmaf(rs[kk][r] * iv, x[r] - mu, acc[r]);
+        }
+      }
+    }
+    if (d < D) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (n0 + r < N) grad[(long long)(n0 + r) * D + d] = -acc[r];
+    }
+  }
+}
+
+// =================================================================================================
+// importance weights: one CTA per component row
+// =================================================================================================
+__global__ void __launch_bounds__(512)
+importance_weights_kernel(const float* __restrict__ lq, const float* __restrict__ bg,
+                          const int32_t* __restrict__ rel_map, int K, int N, int self_normalized,
+                          const float* __restrict__ rho, float* __restrict__ W, float* __restrict__ dot,
+                          float* __restrict__ ess, uint8_t* __restrict__ active) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float* row = lq + (long long)k * N;
+  const int nblk = ceil_div(N, 128);
+  if (rel_map != nullptr) {   // only_use_own_samples: uniform weights over the component's own samples
+    float cnt = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) cnt += (rel_map[n] == k) ? 1.f : 0.f;
+    cnt = block_sum(cnt, red);
+    const float w1 = cnt > 0.f ? 1.f / cnt : 0.f;
+    float d = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const bool own = rel_map[n] == k;
+      if (W) W[(long long)k * N + n] = own ? w1 : 0.f;
+      if (own && rho) d += w1 * rho[n];
+      if (own && active) active[(long long)k * nblk + (n >> 7)] = 1;
+    }
+    if (dot) {
+      d = block_sum(d, red);
+      if (threadIdx.x == 0) dot[k] = d;
+    }
+    if (ess && threadIdx.x == 0) ess[k] = cnt;
+    return;
+  }
+  // pass 1: max and sum exp
+  float m = -INFINITY;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, row[n] - bg[n]);
+  m = block_max(m, red);
+  if (!(m > -INFINITY) || !isfinite(m)) m = 0.f;   // tf.reduce_logsumexp: non-finite max -> 0
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) s += expf(row[n] - bg[n] - m);
+  s = block_sum(s, red);
+  const float lse = m + logf(s);
+  // pass 2: second normaliser and sum of squares of the singly-normalised weights
+  float s2 = 0.f, sq = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float w = expf(row[n] - bg[n] - lse);
+    s2 += w;
+    sq = fmaf(w, w, sq);
+  }
+  s2 = block_sum(s2, red);
+  sq = block_sum(sq, red);
+  if (ess && threadIdx.x == 0) ess[k] = 1.f / sq;
+  if (W == nullptr && dot == nullptr && active == nullptr) return;
+  const float inv_s2 = 1.f / s2;
+  const float logN = logf((float)N);
+  float d = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float lw = row[n] - bg[n];
+    const float w = self_normalized ? expf(lw - lse) * inv_s2 : expf(lw - logN);
+    if (W) W[(long long)k * N + n] = w;
+    if (rho) d = fmaf(w, rho[n], d);
+    if (active && (lw - m) > -60.f) active[(long long)k * nblk + (n >> 7)] = 1;
+  }
+  if (dot) {
+    d = block_sum(d, red);
+    if (threadIdx.x == 0) dot[k] = d;
+  }
+}
+
+// =================================================================================================
+// Stein finalisation and diagonal Stein
+// =================================================================================================
+__global__ void stein_finalize_kernel(const float* __restrict__ T, int D, int symmetrize, float* __restrict__ H) {
+  const int k = blockIdx.y;
+  const float* Tk = T + (long long)k * D * D;
+  float* Hk = H + (long long)k * D * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)D * D;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(e / D), b = (int)(e % D);
+    const float tab = Tk[(long long)a * D + b], tba = Tk[(long long)b * D + a];
+    Hk[e] = symmetrize ? -0.5f * (tab + tba) : -tba;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+stein_diag_kernel(const float* __restrict__ X, int N, int D, const float* __restrict__ means,
+                  const float* __restrict__ stds, const float* __restrict__ W, const float* __restrict__ G,
+                  float* __restrict__ Hneg, float* __restrict__ gneg) {
+  const int k = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Wk = W + (long long)k * N;
+  const float mu = d < D ? means[(long long)k * D + d] : 0.f;
+  const float sg = d < D ? stds[(long long)k * D + d] : 1.f;
+  const float iv = 1.f / (sg * sg);
+  float h = 0.f, g = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float w = __ldg(Wk + n);
+    if (w == 0.f) continue;
+    if (d < D) {
+      const float wg = w * G[(long long)n * D + d];
+      g += wg;
+      h = fmaf(iv * (X[(long long)n * D + d] - mu), wg, h);
+    }
+  }
+  if (d < D) {
+    Hneg[(long long)k * D + d] = -h;
+    gneg[(long long)k * D + d] = -g;
+  }
+}
+
+// =================================================================================================
+// weight updates (single CTA; fp32 like the reference so that the bisection takes the same branches)
+// =================================================================================================
+__device__ float block_lse(const float* v, int K, float* red) {
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmaxf(m, v[k]);
+  m = block_max(m, red);
+  if (!isfinite(m)) m = 0.f;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s += expf(v[k] - m);
+  s = block_sum(s, red);
+  return m + logf(s);
+}
+
+// new_lw <- normalise(floor(normalise(v)));  returns KL(new || old)
+__device__ float weight_kl_eval(float eta, float T, const float* logw, const float* elr, int K, float* nl,
+                                float* red) {
+  const float a = (eta + 1.f) / (T + eta), b = 1.f / (T + eta);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) nl[k] = a * logw[k] + b * elr[k];
+  __syncthreads();
+  float l = block_lse(nl, K, red);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) nl[k] = fmaxf(nl[k] - l, -69.07f);
+  __syncthreads();
+  l = block_lse(nl, K, red);
+  float kl = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = nl[k] - l;
+    nl[k] = v;
+    kl += expf(v) * (v - logw[k]);
+  }
+  kl = block_sum(kl, red);
+  return kl;
+}
+
+__global__ void __launch_bounds__(1024)
+weight_update_kernel(int trust_region, const float* __restrict__ logw, const float* __restrict__ elr, int K,
+                     const float* __restrict__ stepsize, float T, float* __restrict__ out, float* __restrict__ info) {
+  __shared__ float red[33];
+  const float step = stepsize[0];
+  if (K <= 1) {   // weight_updater.py:136,275: nothing happens for a single component
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] = logw[k];
+    if (info && threadIdx.x == 0) { info[0] = -1.f; info[1] = -1.f; }
+    return;
+  }
+  if (!trust_region) {   // weight_updater.py:136-141
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] = logw[k] + step / T * elr[k];
+    __syncthreads();
+    float l = block_lse(out, K, red);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] = fmaxf(out[k] - l, -69.07f);
+    __syncthreads();
+    l = block_lse(out, K, red);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] -= l;
+    if (info && threadIdx.x == 0) { info[0] = -1.f; info[1] = -1.f; }
+    return;
+  }
+  // trust region, weight_updater.py:193-279
+  const float kl_bound = step;
+  float lower = -45.f, upper = 45.f;
+  float log_eta = 0.5f * (upper + lower);
+  bool feasible = false;
+  float kl = -1.f, eta = -1.f;
+  bool evaluated = false;
+  for (int it = 0; it < 50; ++it) {
+    eta = expf(log_eta);
+    const float diff = fabsf(expf(upper) - expf(lower));
+    if (diff < 1e-1f) break;
+    kl = weight_kl_eval(eta, T, logw, elr, K, out, red);
+    evaluated = true;
+    if (fabsf(kl_bound - kl) < 1e-1f * kl_bound) {
+      lower = upper;
+      break;
+    }
+    if (kl_bound > kl) {
+      upper = log_eta;
+      feasible = true;
+    } else {
+      lower = log_eta;
+    }
+    log_eta = 0.5f * (upper + lower);
+  }
+  if (lower == upper && evaluated) {
+    // keep the weights of the last evaluation
+  } else if (feasible) {
+    eta = expf(upper);
+    kl = weight_kl_eval(eta, T, logw, elr, K, out, red);
+  } else {
+    kl = -1.f;
+    eta = -1.f;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) out[k] = logw[k];
+  }
+  if (info && threadIdx.x == 0) { info[0] = kl; info[1] = eta; }
+}
+
+// =================================================================================================
+// Philox4x32-10 + Box-Muller
+// =================================================================================================
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void fill_normal_kernel(float* __restrict__ out, long long rows, int D, unsigned long long seed,
+                                   unsigned long long subseq, long long row_offset) {
+  const int groups = ceil_div(D, 4);
+  const long long total = rows * groups;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / groups;
+    const int g = (int)(e % groups);
+    const unsigned long long grow = (unsigned long long)(r + row_offset);
+    uint32_t c[4] = {(uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)g, (uint32_t)subseq};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(subseq >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    float z[4];
+    {
+      const float r0 = sqrtf(-2.f * logf(u01(c[0])));
+      float s, co;
+      sincospif(2.f * u01(c[1]), &s, &co);
+      z[0] = r0 * co; z[1] = r0 * s;
+      const float r1 = sqrtf(-2.f * logf(u01(c[2])));
+      sincospif(2.f * u01(c[3]), &s, &co);
+      z[2] = r1 * co; z[3] = r1 * s;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = g * 4 + q;
+      if (d < D) out[r * D + d] = z[q];
+    }
+  }
+}
+
+}  // namespace gvi
+
+using namespace gvi;
+
+extern "C" int gvi_version(void) { return 100; }
+extern "C" const char* gvi_last_error(void) { return g_last_error; }
+
+extern "C" size_t gvi_prepare_full_workspace(int K, int D) {
+  return (size_t)(K > 0 ? K : 0) * D * D * sizeof(double);
+}
+extern "C" int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv, float* prec, float* cst,
+                                    int32_t* ok, void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_prepare_full_f32: bad sizes K=%d D=%d", K, D);
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(chol && linv && cst && ws, "gvi_prepare_full_f32: null pointer");
+  if (ws_bytes < gvi_prepare_full_workspace(K, D)) {
+    set_last_error("gvi_prepare_full_f32: workspace %zu < %zu", ws_bytes, gvi_prepare_full_workspace(K, D));
+    return GVI_ERR_WORKSPACE;
+  }
+  prepare_full_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(chol, D, linv, prec, cst, ok, (double*)ws);
+  return check_launch("prepare_full_kernel");
+}
+
+extern "C" int gvi_mixture_lse_f32(const float* lq, const float* logw, int K, int N, float* out, void* stream) {
+  GVI_REQUIRE(K >= 0 && N >= 0, "gvi_mixture_lse_f32: bad sizes");
+  if (N == 0) return GVI_OK;
+  GVI_REQUIRE(lq && logw && out, "gvi_mixture_lse_f32: null pointer");
+  mixture_lse_kernel<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(lq, logw, K, N, out);
+  return check_launch("mixture_lse_kernel");
+}
+
+extern "C" int gvi_logdens_diag_f32(const float* X, int N, int D, const float* means, const float* stds, int K,
+                                    float* lq, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_logdens_diag_f32: bad sizes");
+  if (N == 0 || K == 0) return GVI_OK;
+  GVI_REQUIRE(X && means && stds && lq, "gvi_logdens_diag_f32: null pointer");
+  const size_t smem = (size_t)32 * D * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_last_error("gvi_logdens_diag_f32: D=%d too large for the sample tile", D);
+    return GVI_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(logdens_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(N, 32), min(ceil_div(K, 8), 8));
+  logdens_diag_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(X, N, D, means, stds, K, lq);
+  return check_launch("logdens_diag_kernel");
+}
+
+extern "C" int gvi_mixture_grad_diag_f32(const float* X, int N, int D, const float* means, const float* stds,
+                                         const float* lq, const float* logw, const float* logq, int K, float* grad,
+                                         void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_mixture_grad_diag_f32: bad sizes");
+  if (N == 0) return GVI_OK;
+  GVI_REQUIRE(X && means && stds && lq && logw && logq && grad, "gvi_mixture_grad_diag_f32: null pointer");
+  mixture_grad_diag_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(X, N, D, means, stds, lq, logw, logq,
+                                                                             K, grad);
+  return check_launch("mixture_grad_diag_kernel");
+}
+
+extern "C" int gvi_importance_weights_f32(const float* lq, const float* bg, const int32_t* rel_map, int K, int N,
+                                          int self_normalized, const float* rho, float* W, float* dot, float* ess,
+                                          uint8_t* active, void* stream) {
+  GVI_REQUIRE(K >= 0 && N >= 0, "gvi_importance_weights_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(lq && (bg || rel_map), "gvi_importance_weights_f32: null pointer");
+  GVI_REQUIRE(!dot || rho, "gvi_importance_weights_f32: dot requested without rho");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (active) {
+    cudaError_t e = cudaMemsetAsync(active, 0, (size_t)K * ceil_div(N, 128), st);
+    if (e != cudaSuccess) {
+      set_last_error("gvi_importance_weights_f32: memset: %s", cudaGetErrorString(e));
+      return GVI_ERR_CUDA;
+    }
+  }
+  importance_weights_kernel<<<K, 512, 0, st>>>(lq, bg, rel_map, K, N, self_normalized, rho, W, dot, ess, active);
+  return check_launch("importance_weights_kernel");
+}
+
+extern "C" size_t gvi_stein_full_workspace(int K, int D) {
+  return (size_t)2 * (K > 0 ? K : 0) * D * D * sizeof(float);
+}
+extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec,
+                                  const float* W, const uint8_t* active, const float* G, int K, int symmetrize,
+                                  float* Hneg, float* gneg, void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_stein_full_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(X && means && prec && W && G && Hneg && gneg && ws, "gvi_stein_full_f32: null pointer");
+  GVI_REQUIRE(K <= 65535, "gvi_stein_full_f32: K=%d exceeds 65535", K);
+  if (ws_bytes < gvi_stein_full_workspace(K, D)) {
+    set_last_error("gvi_stein_full_f32: workspace %zu < %zu", ws_bytes, gvi_stein_full_workspace(K, D));
+    return GVI_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* M = (float*)ws;
+  float* T = M + (size_t)K * D * D;
+  int rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
+  if (rc) return rc;
+  // gneg = -W G   ([K x N] [N x D])
+  rc = launch_bgemm(0, 0, 1, K, D, N, -1.f, W, N, 0, G, D, 0, gneg, D, 0, st);
+  if (rc) return rc;
+  // T_k = P_k M_k
+  rc = launch_bgemm(0, 0, K, D, D, D, 1.f, prec, D, (long long)D * D, M, D, (long long)D * D, T, D,
+                    (long long)D * D, st);
+  if (rc) return rc;
+  dim3 grid(min(ceil_div(D * D, 256), 1024), K);
+  stein_finalize_kernel<<<grid, 256, 0, st>>>(T, D, symmetrize, Hneg);
+  return check_launch("stein_finalize_kernel");
+}
+
+extern "C" int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds,
+                                  const float* W, const float* G, int K, float* Hneg, float* gneg, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_stein_diag_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(X && means && stds && W && G && Hneg && gneg, "gvi_stein_diag_f32: null pointer");
+  dim3 grid(ceil_div(D, 256), K);
+  stein_diag_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, means, stds, W, G, Hneg, gneg);
+  return check_launch("stein_diag_kernel");
+}
+
+extern "C" int gvi_weight_update_f32(int trust_region, const float* logw, const float* elr, int K,
+                                     const float* stepsize, float temperature, float* out_logw, float* info,
+                                     void* stream) {
+  GVI_REQUIRE(K >= 0, "gvi_weight_update_f32: bad K");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(logw && elr && stepsize && out_logw, "gvi_weight_update_f32: null pointer");
+  GVI_REQUIRE(out_logw != logw, "gvi_weight_update_f32: in-place update not supported");
+  weight_update_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(trust_region, logw, elr, K, stepsize, temperature,
+                                                            out_logw, info);
+  return check_launch("weight_update_kernel");
+}
+
+extern "C" int gvi_fill_normal_f32(float* out, long long rows, int D, unsigned long long seed,
+                                   unsigned long long subsequence, long long row_offset, void* stream) {
+  GVI_REQUIRE(rows >= 0 && D > 0, "gvi_fill_normal_f32: bad sizes");
+  if (rows == 0) return GVI_OK;
+  GVI_REQUIRE(out, "gvi_fill_normal_f32: null pointer");
+  const long long total = rows * ceil_div(D, 4);
+  const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  fill_normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, D, seed, subsequence, row_offset);
+  return check_launch("fill_normal_kernel");
+}

@@ -1,0 +1,495 @@
+// Component updates: KL-constrained (trust region), direct and iBLR -- full and diagonal covariance.
+//
+// Reference: optimization/gmmvi_modules/ng_based_component_updater.py (:97-141 direct, :160-223 iBLR,
+// :244-333 kl(), :335-429 bracketing_search, :431-524 KL-constrained apply_NG_update).
+//
+// B200-first restatement (see DESIGN.md "component update"): all three full-covariance updaters are
+// evaluated in the WHITENED frame of the old component.  With B = L^T R L, h = L^T g (L = old Cholesky
+// factor, R = -E[H], g = -E[grad]) the new precision is  P' = L^-T M L^-1  with
+//     M = I + B/eta            (KL-constrained, eta found by the reference's log-space bisection)
+//     M = I + s B              (direct)
+//     M = I + s B + s^2/2 B^2  (iBLR)
+// and  KL(new || old) = 1/2 [ logdet M - D + tr(M^-1) + |M^-1 h|^2 / eta^2 ].
+// One CTA per component keeps the packed lower triangle of (index-reversed) M in shared memory, factors
+// it in place, and -- because a reversed Cholesky gives M = U U^T with U upper triangular -- produces the
+// new Cholesky factor directly as L' = L U^-T (no explicit covariance, no second factorisation).
+// The diagonal of M is carried as (diag - 1) so that logdet and tr(M^-1) - D keep full relative accuracy
+// when eta is large (small steps), where the reference's fp32 formula cancels catastrophically.
+#include "common.cuh"
+#include "../../include/gmmvi_b200.h"
+
+namespace gvi {
+
+int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                 long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                 long long strideC, cudaStream_t st);
+
+constexpr int UPD_THREADS = 256;
+
+__device__ __forceinline__ long long tri(int i) { return (long long)i * (i + 1) / 2; }
+
+// Rlow[a][b] = R[max(a,b)][min(a,b)]  (tf.linalg.cholesky only reads the lower triangle)
+__global__ void mirror_lower_kernel(const float* __restrict__ R, int D, float* __restrict__ out) {
+  const int k = blockIdx.y;
+  const float* Rk = R + (long long)k * D * D;
+  float* Ok = out + (long long)k * D * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)D * D;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(e / D), b = (int)(e % D);
+    Ok[e] = a >= b ? Rk[(long long)a * D + b] : Rk[(long long)b * D + a];
+  }
+}
+
+// geff = g + (Rlow - R) mu  (zero for symmetric R);  h = L^T geff
+__global__ void __launch_bounds__(256)
+update_vectors_kernel(const float* __restrict__ means, const float* __restrict__ chols,
+                      const float* __restrict__ R, const float* __restrict__ gneg, int D, int use_geff,
+                      float* __restrict__ hvec) {
+  extern __shared__ float gs[];   // [D]
+  const int k = blockIdx.x;
+  const float* Rk = R + (long long)k * D * D;
+  const float* L = chols + (long long)k * D * D;
+  const float* mu = means + (long long)k * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float g = gneg[(long long)k * D + i];
+    if (use_geff) {
+      float s = 0.f;
+      for (int j = i + 1; j < D; ++j) s = fmaf(Rk[(long long)j * D + i] - Rk[(long long)i * D + j], mu[j], s);
+      g += s;
+    }
+    gs[i] = g;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float s = 0.f;
+    for (int i = j; i < D; ++i) s = fmaf(L[(long long)i * D + j], gs[i], s);
+    hvec[(long long)k * D + j] = s;
+  }
+}
+
+// ---- packed lower-triangular linear algebra on a CTA ---------------------------------------------
+// A: packed lower triangle (row i at tri(i)); dm1: diagonal of the SPD input minus one (in), delta of
+// the pivots (out).  Returns false (uniformly) on a non-positive pivot.
+__device__ bool chol_packed(float* A, float* dm1, int D) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = 0; j < D; ++j) {
+    const float* rj = A + tri(j);
+    for (int i = j + tid; i < D; i += nt) {
+      const float* ri = A + tri(i);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int m = 0;
+      for (; m + 3 < j; m += 4) {
+        s0 = fmaf(ri[m], rj[m], s0);
+        s1 = fmaf(ri[m + 1], rj[m + 1], s1);
+        s2 = fmaf(ri[m + 2], rj[m + 2], s2);
+        s3 = fmaf(ri[m + 3], rj[m + 3], s3);
+      }
+      for (; m < j; ++m) s0 = fmaf(ri[m], rj[m], s0);
+      const float s = (s0 + s1) + (s2 + s3);
+      if (i == j) {
+        const float d = dm1[j] - s;
+        dm1[j] = d;
+        A[tri(j) + j] = sqrtf(1.f + d);
+      } else {
+        A[tri(i) + j] = ri[j] - s;
+      }
+    }
+    __syncthreads();
+    const float c = A[tri(j) + j];
+    if (!(c > 0.f) || !isfinite(c)) return false;
+    const float ic = 1.f / c;
+    for (int i = j + 1 + tid; i < D; i += nt) A[tri(i) + j] *= ic;
+    __syncthreads();
+  }
+  return true;
+}
+
+// In-place inverse of the packed lower-triangular factor.
+__device__ void inv_packed(float* A, int D) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = D - 1; j >= 0; --j) {
+    const float xjj = 1.f / A[tri(j) + j];
+    float sreg[4];   // supports D <= 4 * blockDim
+    int cnt = 0;
+    for (int i = j + 1 + tid; i < D; i += nt, ++cnt) {
+      const float* ri = A + tri(i);
+      float s0 = 0.f, s1 = 0.f;
+      int m = j + 1;
+      for (; m + 1 <= i; m += 2) {
+        s0 = fmaf(ri[m], A[tri(m) + j], s0);
+        s1 = fmaf(ri[m + 1], A[tri(m + 1) + j], s1);
+      }
+      if (m <= i) s0 = fmaf(ri[m], A[tri(m) + j], s0);
+      sreg[cnt] = -(s0 + s1) * xjj;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int i = j + 1 + tid; i < D; i += nt, ++cnt) A[tri(i) + j] = sreg[cnt];
+    if (tid == 0) A[tri(j) + j] = xjj;
+    __syncthreads();
+  }
+}
+
+struct KlTerms {
+  float kl;
+  bool ok;
+};
+
+// Assemble reversed M = I + a1*B + a2*B2 (packed, diag-1 separately), factor, invert, evaluate KL terms.
+// On return (ok): A holds X = chol(M~)^-1 and u (smem) holds M~^-1 h~.
+__device__ KlTerms eval_whitened(float* A, float* dm1, const float* __restrict__ B, const float* __restrict__ B2,
+                                 float a1, float a2, const float* hrev, float* v, float* u, int D,
+                                 float inv_eta, float* red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+  for (int a = w; a < D; a += nw) {
+    const float* Br = B + (long long)(D - 1 - a) * D;
+    const float* B2r = B2 ? B2 + (long long)(D - 1 - a) * D : nullptr;
+    for (int b = lane; b <= a; b += 32) {
+      float val = a1 * Br[D - 1 - b];
+      if (B2r) val = fmaf(a2, B2r[D - 1 - b], val);
+      if (a == b) dm1[a] = val;
+      else A[tri(a) + b] = val;
+    }
+  }
+  __syncthreads();
+  KlTerms out;
+  out.ok = chol_packed(A, dm1, D);
+  if (!out.ok) {
+    out.kl = FLT_MAX;
+    return out;
+  }
+  float ld = 0.f;
+  for (int j = tid; j < D; j += nt) ld += log1pf(dm1[j]);
+  ld = block_sum(ld, red);
+  inv_packed(A, D);
+  // tr(M^-1) - D = sum_j (-delta_j / (1 + delta_j)) + sum_{i>j} X_ij^2
+  float tr = 0.f;
+  for (int i = tid; i < D; i += nt) {
+    const float* ri = A + tri(i);
+    float s = 0.f;
+    for (int m = 0; m < i; ++m) s = fmaf(ri[m], ri[m], s);
+    tr += s - dm1[i] / (1.f + dm1[i]);
+  }
+  tr = block_sum(tr, red);
+  // v = X h~ ; u = X^T v
+  for (int i = tid; i < D; i += nt) {
+    const float* ri = A + tri(i);
+    float s = 0.f;
+    for (int m = 0; m <= i; ++m) s = fmaf(ri[m], hrev[m], s);
+    v[i] = s;
+  }
+  __syncthreads();
+  float mh = 0.f;
+  for (int m = tid; m < D; m += nt) {
+    float s = 0.f;
+    for (int i = m; i < D; ++i) s = fmaf(A[tri(i) + m], v[i], s);
+    u[m] = s;
+    mh = fmaf(s, s, mh);
+  }
+  mh = block_sum(mh, red);
+  out.kl = 0.5f * (ld + tr + mh * inv_eta * inv_eta);
+  return out;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS)
+update_full_kernel(int mode, const float* __restrict__ means, const float* __restrict__ chols,
+                   const float* __restrict__ Bmat, const float* __restrict__ B2mat, const float* __restrict__ hvec,
+                   const float* __restrict__ stepsizes, const float* __restrict__ last_etas,
+                   const float* __restrict__ num_updates, int D, float temperature, float* __restrict__ out_means,
+                   float* __restrict__ out_chols, int32_t* __restrict__ success, float* __restrict__ etas,
+                   float* __restrict__ kls, float* __restrict__ gscratch, int use_global) {
+  extern __shared__ float smem[];
+  __shared__ float red[33];
+  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const long long npk = tri(D);
+  float* hrev = smem;            // [D]
+  float* v = smem + D;           // [D]
+  float* u = smem + 2 * D;       // [D]
+  float* dm1 = smem + 3 * D;     // [D]
+  float* A = use_global ? gscratch + (long long)k * npk : smem + 4 * D;
+  const float* B = Bmat + (long long)k * D * D;
+  const float* B2 = (mode == 2) ? B2mat + (long long)k * D * D : nullptr;
+  const float* L = chols + (long long)k * D * D;
+  const float* mu = means + (long long)k * D;
+  for (int i = tid; i < D; i += nt) hrev[i] = hvec[(long long)k * D + (D - 1 - i)];
+  __syncthreads();
+
+  const float step = stepsizes[k];
+  bool ok = true;
+  float eta = -1.f, kl = -1.f;
+  if (mode == 0) {
+    // ---- bracketing search in log space (:335-429), cold / warm bracket (:462-471) ----
+    const float last = last_etas[k];
+    float lower, upper;
+    if (last < 0.f) { lower = -20.f; upper = 80.f; }
+    else { lower = fmaxf(0.f, logf(last) - 3.f); upper = logf(last) + 3.f; }
+    float leta = 0.5f * (upper + lower);
+    bool feasible = false;
+    for (int it = 0; it < 1000; ++it) {
+      const float diff = fminf(expf(upper) - expf(leta), expf(leta) - expf(lower));
+      if (diff < 1e-1f) break;
+      const float e = expf(leta);
+      const KlTerms t = eval_whitened(A, dm1, B, nullptr, 1.f / e, 0.f, hrev, v, u, D, 1.f / e, red);
+      if (fabsf(step - t.kl) < 1e-1f * step) { lower = upper = leta; break; }
+      if (step > t.kl) { upper = leta; feasible = true; }
+      else lower = leta;
+      leta = 0.5f * (upper + lower);
+    }
+    if (feasible) lower = upper;
+    const float new_lower = expf(lower), new_upper = expf(upper);
+    eta = fmaxf(new_lower, temperature);
+    ok = (new_lower == new_upper);
+    if (ok) {
+      const KlTerms t = eval_whitened(A, dm1, B, nullptr, 1.f / eta, 0.f, hrev, v, u, D, 1.f / eta, red);
+      ok = t.ok && (t.kl < FLT_MAX) && isfinite(t.kl);
+      kl = t.kl;
+    }
+  } else if (mode == 1) {
+    eta = 1.f / step;
+    const KlTerms t = eval_whitened(A, dm1, B, nullptr, step, 0.f, hrev, v, u, D, step, red);
+    ok = t.ok && isfinite(t.kl);
+    kl = t.kl;
+  } else {
+    const KlTerms t = eval_whitened(A, dm1, B, B2, step, 0.5f * step * step, hrev, v, u, D, step, red);
+    ok = t.ok && isfinite(t.kl);
+    kl = t.kl;
+  }
+
+  float* om = out_means + (long long)k * D;
+  float* oc = out_chols + (long long)k * D * D;
+  if (ok) {
+    // new mean
+    const bool first = (mode == 2) && (num_updates[k] == 0.f);
+    const float scale = (mode == 0) ? 1.f / eta : step;
+    for (int i = tid; i < D; i += nt) {
+      float s = 0.f;
+      if (!first) {
+        const float* Li = L + (long long)i * D;
+        if (mode == 2) { for (int j = 0; j <= i; ++j) s = fmaf(Li[j], hrev[D - 1 - j], s); }
+        else           { for (int j = 0; j <= i; ++j) s = fmaf(Li[j], u[D - 1 - j], s); }
+      }
+      om[i] = mu[i] - scale * s;
+    }
+    // new Cholesky factor L' = L U^-T,  U^-T[m][j] = X[D-1-j][D-1-m]
+    bool finite = true;
+    for (int j = tid; j < D; j += nt) {
+      const float* xr = A + tri(D - 1 - j);
+      for (int i = 0; i < j; ++i) oc[(long long)i * D + j] = 0.f;
+      for (int i = j; i < D; ++i) {
+        const float* Li = L + (long long)i * D;
+        float s0 = 0.f, s1 = 0.f;
+        int m = j;
+        for (; m + 1 <= i; m += 2) {
+          s0 = fmaf(Li[m], xr[D - 1 - m], s0);
+          s1 = fmaf(Li[m + 1], xr[D - 2 - m], s1);
+        }
+        if (m <= i) s0 = fmaf(Li[m], xr[D - 1 - m], s0);
+        const float val = s0 + s1;
+        finite &= isfinite(val);
+        oc[(long long)i * D + j] = val;
+      }
+    }
+    ok = !__syncthreads_or(!finite);
+  }
+  if (!ok) {
+    __syncthreads();
+    for (int i = tid; i < D; i += nt) om[i] = mu[i];
+    for (long long e = tid; e < (long long)D * D; e += nt) oc[e] = L[e];
+    eta = -1.f;
+    kl = -1.f;
+  }
+  if (tid == 0) {
+    success[k] = ok ? 1 : 0;
+    if (etas) etas[k] = eta;
+    if (kls) kls[k] = kl;
+  }
+}
+
+// ---- diagonal covariance -------------------------------------------------------------------------
+__device__ float diag_kl_eval(float eta, const float* mu, const float* sg, const float* R, const float* g,
+                              int D, float* red) {
+  // ng_based_component_updater.py:299-317 with log(new/old) + old/new - 1 = log1p(t) - t/(1+t), t = R sg^2 / eta
+  float a = 0.f, b = 0.f;
+  bool bad = false;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float var = sg[d] * sg[d];
+    const float t = R[d] * var / eta;
+    if (!(1.f + t > 0.f)) bad = true;
+    a += log1pf(t) - t / (1.f + t);
+    // mu - mu' = g / (eta * new_prec);  old_inv_chol * diff
+    const float np = (1.f + t) / var;
+    const float diff = g[d] / (eta * np);
+    const float z = diff / sg[d];
+    b = fmaf(z, z, b);
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (__syncthreads_or(bad)) return NAN;
+  return 0.5f * (fmaxf(0.f, a) + b);
+}
+
+__global__ void __launch_bounds__(128)
+update_diag_kernel(int mode, const float* __restrict__ means, const float* __restrict__ stds,
+                   const float* __restrict__ Hneg, const float* __restrict__ gneg,
+                   const float* __restrict__ stepsizes, const float* __restrict__ last_etas,
+                   const float* __restrict__ num_updates, int D, float temperature, float* __restrict__ out_means,
+                   float* __restrict__ out_stds, int32_t* __restrict__ success, float* __restrict__ etas,
+                   float* __restrict__ kls) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float* mu = means + (long long)k * D;
+  const float* sg = stds + (long long)k * D;
+  const float* R = Hneg + (long long)k * D;
+  const float* g = gneg + (long long)k * D;
+  float* om = out_means + (long long)k * D;
+  float* os = out_stds + (long long)k * D;
+  const float step = stepsizes[k];
+  bool ok = true;
+  float eta = -1.f, kl = -1.f;
+  if (mode == 0) {
+    const float last = last_etas[k];
+    float lower, upper;
+    if (last < 0.f) { lower = -20.f; upper = 80.f; }
+    else { lower = fmaxf(0.f, logf(last) - 3.f); upper = logf(last) + 3.f; }
+    float leta = 0.5f * (upper + lower);
+    bool feasible = false;
+    for (int it = 0; it < 1000; ++it) {
+      const float diff = fminf(expf(upper) - expf(leta), expf(leta) - expf(lower));
+      if (diff < 1e-1f) break;
+      const float klv = diag_kl_eval(expf(leta), mu, sg, R, g, D, red);
+      if (fabsf(step - klv) < 1e-1f * step) { lower = upper = leta; break; }
+      if (step > klv) { upper = leta; feasible = true; }
+      else lower = leta;
+      leta = 0.5f * (upper + lower);
+    }
+    if (feasible) lower = upper;
+    const float new_lower = expf(lower), new_upper = expf(upper);
+    eta = fmaxf(new_lower, temperature);
+    ok = (new_lower == new_upper);
+    if (ok) {
+      kl = diag_kl_eval(eta, mu, sg, R, g, D, red);
+      ok = (kl < FLT_MAX);   // NaN fails the comparison, like the reference (:487)
+    }
+    if (ok) {
+      for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float var = sg[d] * sg[d];
+        const float np = (eta / var + R[d]) / eta;
+        om[d] = mu[d] - g[d] / (eta * np);
+        os[d] = sqrtf(1.f / np);
+      }
+    }
+  } else {   // iBLR, :160-223 (diagonal branch)
+    bool bad = false;
+    const bool first = num_updates[k] == 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float var = sg[d] * sg[d];
+      const float corr = step / 2.f * R[d] * var * R[d];
+      const float np = 1.f / var + step * (R[d] + corr);
+      const float ns = sqrtf(1.f / np);
+      if (isnan(ns)) bad = true;
+      os[d] = ns;
+      om[d] = first ? mu[d] : mu[d] + step * var * (-g[d]);
+    }
+    ok = !__syncthreads_or(bad);
+  }
+  if (!ok) {
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) { om[d] = mu[d]; os[d] = sg[d]; }
+    eta = -1.f;
+    kl = -1.f;
+  }
+  if (threadIdx.x == 0) {
+    success[k] = ok ? 1 : 0;
+    if (etas) etas[k] = eta;
+    if (kls) kls[k] = kl;
+  }
+}
+
+static size_t upd_smem_bytes(int D) { return (size_t)(4 * D + (size_t)D * (D + 1) / 2) * sizeof(float); }
+constexpr size_t kMaxDynSmem = 220 * 1024;
+
+}  // namespace gvi
+
+using namespace gvi;
+
+extern "C" size_t gvi_update_full_workspace(int K, int D) {
+  if (K <= 0) return 0;
+  size_t f = (size_t)4 * K * D * D + (size_t)K * D;
+  if (upd_smem_bytes(D) > kMaxDynSmem) f += (size_t)K * D * (D + 1) / 2;
+  return f * sizeof(float);
+}
+
+extern "C" int gvi_update_full_f32(int mode, const float* means, const float* chols, const float* Hneg,
+                                   const float* gneg, const float* stepsizes, const float* last_etas,
+                                   const float* num_updates, int K, int D, float temperature, float* out_means,
+                                   float* out_chols, int32_t* success, float* etas, float* kls, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(mode >= 0 && mode <= 2, "gvi_update_full_f32: unknown mode %d", mode);
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_update_full_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(means && chols && Hneg && gneg && stepsizes && out_means && out_chols && success && ws,
+              "gvi_update_full_f32: null pointer");
+  GVI_REQUIRE(mode != 0 || last_etas, "gvi_update_full_f32: last_etas required for the KL-constrained update");
+  GVI_REQUIRE(mode != 2 || num_updates, "gvi_update_full_f32: num_updates required for iBLR");
+  GVI_REQUIRE(K <= 65535 && D <= 4 * UPD_THREADS, "gvi_update_full_f32: K or D too large");
+  if (ws_bytes < gvi_update_full_workspace(K, D)) {
+    set_last_error("gvi_update_full_f32: workspace %zu < %zu", ws_bytes, gvi_update_full_workspace(K, D));
+    return GVI_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long DD = (long long)D * D;
+  float* Rlow = (float*)ws;
+  float* T = Rlow + (size_t)K * DD;
+  float* Bm = T + (size_t)K * DD;
+  float* B2 = Bm + (size_t)K * DD;
+  float* hv = B2 + (size_t)K * DD;
+  float* gscr = hv + (size_t)K * D;
+  dim3 g1(min(ceil_div(D * D, 256), 1024), K);
+  mirror_lower_kernel<<<g1, 256, 0, st>>>(Hneg, D, Rlow);
+  int rc = check_launch("mirror_lower_kernel");
+  if (rc) return rc;
+  // T = Rlow L ;  B = L^T T
+  rc = launch_bgemm(0, 0, K, D, D, D, 1.f, Rlow, D, DD, chols, D, DD, T, D, DD, st);
+  if (rc) return rc;
+  rc = launch_bgemm(1, 0, K, D, D, D, 1.f, chols, D, DD, T, D, DD, Bm, D, DD, st);
+  if (rc) return rc;
+  if (mode == 2) {
+    rc = launch_bgemm(0, 0, K, D, D, D, 1.f, Bm, D, DD, Bm, D, DD, B2, D, DD, st);
+    if (rc) return rc;
+  }
+  update_vectors_kernel<<<K, 256, D * sizeof(float), st>>>(means, chols, Hneg, gneg, D, mode != 2, hv);
+  rc = check_launch("update_vectors_kernel");
+  if (rc) return rc;
+  const size_t full = upd_smem_bytes(D);
+  const int use_global = full > kMaxDynSmem;
+  const size_t smem = use_global ? (size_t)4 * D * sizeof(float) : full;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(update_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
+    if (e != cudaSuccess) {
+      set_last_error("gvi_update_full_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return GVI_ERR_CUDA;
+    }
+  }
+  update_full_kernel<<<K, UPD_THREADS, smem, st>>>(mode, means, chols, Bm, B2, hv, stepsizes, last_etas, num_updates,
+                                                   D, temperature, out_means, out_chols, success, etas, kls, gscr,
+                                                   use_global);
+  return check_launch("update_full_kernel");
+}
+
+extern "C" int gvi_update_diag_f32(int mode, const float* means, const float* stds, const float* Hneg,
+                                   const float* gneg, const float* stepsizes, const float* last_etas,
+                                   const float* num_updates, int K, int D, float temperature, float* out_means,
+                                   float* out_stds, int32_t* success, float* etas, float* kls, void* stream) {
+  GVI_REQUIRE(mode == 0 || mode == 2, "gvi_update_diag_f32: mode %d has no diagonal variant in the reference", mode);
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_update_diag_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(means && stds && Hneg && gneg && stepsizes && out_means && out_stds && success,
+              "gvi_update_diag_f32: null pointer");
+  GVI_REQUIRE(mode != 0 || last_etas, "gvi_update_diag_f32: last_etas required");
+  GVI_REQUIRE(mode != 2 || num_updates, "gvi_update_diag_f32: num_updates required");
+  update_diag_kernel<<<K, 128, 0, (cudaStream_t)stream>>>(mode, means, stds, Hneg, gneg, stepsizes, last_etas,
+                                                         num_updates, D, temperature, out_means, out_stds, success,
+                                                         etas, kls);
+  return check_launch("update_diag_kernel");
+}

@@ -1,0 +1,231 @@
+"""Thin torch-tensor wrappers over the C ABI (include/gmmvi_b200.h).
+
+torch owns every buffer (CUDA, contiguous, fp32 / int32); the kernels run on torch's current stream.
+No op here has a CPU or PyTorch fallback: a non-CUDA tensor is an error.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+LAUNCHES = 0   # number of C-ABI calls issued (bench.py reports kernel launches from this family)
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise _lib.GmmviLibraryError(f"{name}: gmmvi_b200 kernels need CUDA tensors (got {t.device}); there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------------
+def prepare_full(chol: torch.Tensor, want_prec: bool = True):
+    """chol[K,D,D] -> (linv[K,D,D], prec[K,D,D] | None, cst[K], ok[K] int32)."""
+    chol = _chk(chol, "chol")
+    K, D, _ = chol.shape
+    linv = torch.empty_like(chol)
+    prec = torch.empty_like(chol) if want_prec else None
+    cst = torch.empty(K, device=chol.device, dtype=torch.float32)
+    ok = torch.empty(K, device=chol.device, dtype=torch.int32)
+    nbytes = _lib.lib().gvi_prepare_full_workspace(K, D)
+    ws = torch.empty(max(nbytes, 8) // 8, device=chol.device, dtype=torch.float64)
+    _call("gvi_prepare_full_f32", chol.data_ptr(), K, D, linv.data_ptr(), _ptr(prec), cst.data_ptr(), ok.data_ptr(),
+          ws.data_ptr(), nbytes, _stream())
+    return linv, prec, cst, ok
+
+
+def logdens_full(X, means, linv, cst, out=None):
+    X, means, linv, cst = _chk(X, "X"), _chk(means, "means"), _chk(linv, "linv"), _chk(cst, "cst")
+    N, D = X.shape
+    K = means.shape[0]
+    lq = out if out is not None else torch.empty((K, N), device=X.device, dtype=torch.float32)
+    _call("gvi_logdens_full_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), cst.data_ptr(), K,
+          lq.data_ptr(), _stream())
+    return lq
+
+
+def logdens_diag(X, means, stds):
+    X, means, stds = _chk(X, "X"), _chk(means, "means"), _chk(stds, "stds")
+    N, D = X.shape
+    K = means.shape[0]
+    lq = torch.empty((K, N), device=X.device, dtype=torch.float32)
+    _call("gvi_logdens_diag_f32", X.data_ptr(), N, D, means.data_ptr(), stds.data_ptr(), K, lq.data_ptr(), _stream())
+    return lq
+
+
+def mixture_lse(lq, logw):
+    lq, logw = _chk(lq, "lq"), _chk(logw, "logw")
+    K, N = lq.shape
+    out = torch.empty(N, device=lq.device, dtype=torch.float32)
+    _call("gvi_mixture_lse_f32", lq.data_ptr(), logw.data_ptr(), K, N, out.data_ptr(), _stream())
+    return out
+
+
+def mixture_grad_full(X, means, prec, lq, logw, logq):
+    X, means, prec = _chk(X, "X"), _chk(means, "means"), _chk(prec, "prec")
+    lq, logw, logq = _chk(lq, "lq"), _chk(logw, "logw"), _chk(logq, "logq")
+    N, D = X.shape
+    K = means.shape[0]
+    grad = torch.empty_like(X)
+    _call("gvi_mixture_grad_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), lq.data_ptr(),
+          logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), _stream())
+    return grad
+
+
+def mixture_grad_diag(X, means, stds, lq, logw, logq):
+    X, means, stds = _chk(X, "X"), _chk(means, "means"), _chk(stds, "stds")
+    lq, logw, logq = _chk(lq, "lq"), _chk(logw, "logw"), _chk(logq, "logq")
+    N, D = X.shape
+    K = means.shape[0]
+    grad = torch.empty_like(X)
+    _call("gvi_mixture_grad_diag_f32", X.data_ptr(), N, D, means.data_ptr(), stds.data_ptr(), lq.data_ptr(),
+          logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), _stream())
+    return grad
+
+
+def importance_weights(lq, bg, rel_map=None, self_normalized=True, rho=None, want_W=False, want_dot=False,
+                       want_ess=False, want_active=False):
+    """Returns dict with the requested of W[K,N], dot[K], ess[K], active[K, ceil(N/128)] (uint8)."""
+    lq = _chk(lq, "lq")
+    K, N = lq.shape
+    bg = _chk(bg, "bg") if bg is not None else None
+    rel_map = _chk(rel_map, "rel_map", torch.int32) if rel_map is not None else None
+    rho = _chk(rho, "rho") if rho is not None else None
+    dev = lq.device
+    W = torch.empty((K, N), device=dev, dtype=torch.float32) if want_W else None
+    dot = torch.empty(K, device=dev, dtype=torch.float32) if want_dot else None
+    ess = torch.empty(K, device=dev, dtype=torch.float32) if want_ess else None
+    active = torch.empty((K, (N + 127) // 128), device=dev, dtype=torch.uint8) if want_active else None
+    _call("gvi_importance_weights_f32", lq.data_ptr(), _ptr(bg), _ptr(rel_map), K, N, int(bool(self_normalized)),
+          _ptr(rho), _ptr(W), _ptr(dot), _ptr(ess), _ptr(active), _stream())
+    return dict(W=W, dot=dot, ess=ess, active=active)
+
+
+def stein_full(X, means, prec, W, active, G, symmetrize=True):
+    X, means, prec, W, G = _chk(X, "X"), _chk(means, "means"), _chk(prec, "prec"), _chk(W, "W"), _chk(G, "G")
+    if active is not None:
+        active = _chk(active, "active", torch.uint8)
+    N, D = X.shape
+    K = means.shape[0]
+    Hneg = torch.empty((K, D, D), device=X.device, dtype=torch.float32)
+    gneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
+    nbytes = _lib.lib().gvi_stein_full_workspace(K, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.float32)
+    _call("gvi_stein_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), W.data_ptr(), _ptr(active),
+          G.data_ptr(), K, int(bool(symmetrize)), Hneg.data_ptr(), gneg.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return Hneg, gneg
+
+
+def stein_diag(X, means, stds, W, G):
+    X, means, stds, W, G = _chk(X, "X"), _chk(means, "means"), _chk(stds, "stds"), _chk(W, "W"), _chk(G, "G")
+    N, D = X.shape
+    K = means.shape[0]
+    Hneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
+    gneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
+    _call("gvi_stein_diag_f32", X.data_ptr(), N, D, means.data_ptr(), stds.data_ptr(), W.data_ptr(), G.data_ptr(), K,
+          Hneg.data_ptr(), gneg.data_ptr(), _stream())
+    return Hneg, gneg
+
+
+UPDATE_MODES = {"trust-region": 0, "direct": 1, "iBLR": 2}
+
+
+def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, stepsizes, last_etas=None,
+                      num_updates=None, temperature: float = 1.0):
+    """-> (new_means, new_chols, success[K] int32, etas[K], kls[K])."""
+    m = UPDATE_MODES[mode]
+    means, chols, Hneg, gneg = _chk(means, "means"), _chk(chols, "chols"), _chk(Hneg, "Hneg"), _chk(gneg, "gneg")
+    stepsizes = _chk(stepsizes, "stepsizes")
+    last_etas = _chk(last_etas, "last_etas") if last_etas is not None else None
+    num_updates = _chk(num_updates, "num_updates") if num_updates is not None else None
+    K, D = means.shape
+    dev = means.device
+    om, oc = torch.empty_like(means), torch.empty_like(chols)
+    succ = torch.empty(K, device=dev, dtype=torch.int32)
+    etas = torch.empty(K, device=dev, dtype=torch.float32)
+    kls = torch.empty(K, device=dev, dtype=torch.float32)
+    if diagonal:
+        _call("gvi_update_diag_f32", m, means.data_ptr(), chols.data_ptr(), Hneg.data_ptr(), gneg.data_ptr(),
+              stepsizes.data_ptr(), _ptr(last_etas), _ptr(num_updates), K, D, float(temperature), om.data_ptr(),
+              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), _stream())
+    else:
+        nbytes = _lib.lib().gvi_update_full_workspace(K, D)
+        ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
+        _call("gvi_update_full_f32", m, means.data_ptr(), chols.data_ptr(), Hneg.data_ptr(), gneg.data_ptr(),
+              stepsizes.data_ptr(), _ptr(last_etas), _ptr(num_updates), K, D, float(temperature), om.data_ptr(),
+              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return om, oc, succ, etas, kls
+
+
+def weight_update(trust_region: bool, logw, elr, stepsize, temperature: float = 1.0):
+    """stepsize: device scalar tensor (or python float).  -> (new_log_weights (un-normalised result of the
+    reference's search), info[2] = (kl, eta))."""
+    logw, elr = _chk(logw, "logw"), _chk(elr, "elr")
+    if not isinstance(stepsize, torch.Tensor):
+        stepsize = torch.tensor([float(stepsize)], device=logw.device, dtype=torch.float32)
+    stepsize = _chk(stepsize.reshape(1), "stepsize")
+    K = logw.shape[0]
+    out = torch.empty_like(logw)
+    info = torch.empty(2, device=logw.device, dtype=torch.float32)
+    _call("gvi_weight_update_f32", int(bool(trust_region)), logw.data_ptr(), elr.data_ptr(), K, stepsize.data_ptr(),
+          float(temperature), out.data_ptr(), info.data_ptr(), _stream())
+    return out, info
+
+
+def fill_normal(rows: int, D: int, seed: int, subsequence: int = 0, row_offset: int = 0, device="cuda"):
+    out = torch.empty((rows, D), device=device, dtype=torch.float32)
+    if not out.is_cuda:
+        raise _lib.GmmviLibraryError("fill_normal: needs a CUDA device")
+    with torch.cuda.device(out.device):
+        _call("gvi_fill_normal_f32", out.data_ptr(), rows, D, seed & (2 ** 64 - 1), subsequence & (2 ** 64 - 1),
+              row_offset, _stream())
+    return out
+
+
+def sample_components(diagonal: bool, eps, offsets, means, chols, max_rows_per_component: int):
+    """eps[N,D] noise, offsets[K+1] int32 device prefix sums -> (X[N,D], mapping[N] int32)."""
+    eps, means, chols = _chk(eps, "eps"), _chk(means, "means"), _chk(chols, "chols")
+    offsets = _chk(offsets, "offsets", torch.int32)
+    N, D = eps.shape
+    K = means.shape[0]
+    X = torch.empty_like(eps)
+    mapping = torch.empty(N, device=eps.device, dtype=torch.int32)
+    _call("gvi_sample_f32", int(bool(diagonal)), eps.data_ptr(), offsets.data_ptr(), means.data_ptr(),
+          chols.data_ptr(), K, D, int(max_rows_per_component), X.data_ptr(), mapping.data_ptr(), _stream())
+    return X, mapping
+
+
+def bgemm(A, B, transA=False, transB=False, alpha=1.0):
+    """Batched C[b] = alpha * op(A[b]) op(B[b]) for 3-D tensors (or 2-D, batch 1)."""
+    A, B = _chk(A, "A"), _chk(B, "B")
+    squeeze = A.dim() == 2
+    if squeeze:
+        A, B = A.unsqueeze(0), B.unsqueeze(0)
+    batch = A.shape[0]
+    M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
+    N = B.shape[1] if transB else B.shape[2]
+    Cc = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
+    _call("gvi_bgemm_f32", int(transA), int(transB), batch, M, N, Kd, float(alpha), A.data_ptr(), A.shape[2],
+          A.shape[1] * A.shape[2], B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], Cc.data_ptr(), N, M * N,
+          _stream())
+    return Cc[0] if squeeze else Cc

@@ -1,0 +1,129 @@
+/* gmmvi_b200 -- C ABI of the B200-native GMMVI hot path.
+ *
+ * The reference (OlegArenz/gmmvi) has no FFI: its "plugin API" is a set of Python classes whose
+ * numerical work is TensorFlow library calls.  Each entry point below replaces the TF/TFP call
+ * sequence of one reference method (cited as file:line relative to /root/reference/src/gmmvi/) and is
+ * what the Python mirror in gmmvi_b200/ binds through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 / int32, contiguous row-major) unless marked "host";
+ *   - kernels never allocate: scratch is passed in (`ws`, size from the matching *_workspace());
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and keeps no
+ *     global mutable state;
+ *   - return value: 0 ok, <0 error (GVI_ERR_*); the message is in gvi_last_error() (thread local);
+ *     nothing throws across the boundary;
+ *   - numerical failure is DATA, not an error: updaters report it per component in `success[K]`
+ *     (non-positive pivot => reject, keep old parameters), mirroring the reference's NaN-Cholesky test
+ *     (optimization/gmmvi_modules/ng_based_component_updater.py:120-138, 320-324, 488-511).
+ */
+#ifndef GMMVI_B200_H
+#define GMMVI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVI_OK 0
+#define GVI_ERR_INVALID (-1)
+#define GVI_ERR_WORKSPACE (-2)
+#define GVI_ERR_CUDA (-3)
+#define GVI_ERR_UNSUPPORTED (-4)
+
+int gvi_version(void);
+const char* gvi_last_error(void);
+
+/* ---- parameter preparation ---------------------------------------------------------------------
+ * chol[K,D,D] (lower) -> linv = chol^-1 (lower), prec = linv^T linv (nullable), cst[k] = -sum_i log
+ * chol[k,i,i] - D/2 log(2 pi).  Replaces tf.linalg.inv(chols) (optimization/sample_db.py:121,132;
+ * ng_based_component_updater.py:106,178,457) and the const_parts of models/full_cov_gmm.py:60-61.
+ * Computed in fp64 internally, stored fp32.  ok[k]=0 (nullable) flags a non-positive diagonal. */
+size_t gvi_prepare_full_workspace(int K, int D);
+int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv, float* prec, float* cst, int32_t* ok,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---- log densities ----------------------------------------------------------------------------
+ * lq[k,n] = cst[k] - 1/2 || linv_k (x_n - mu_k) ||^2          models/full_cov_gmm.py:56-62,
+ * and with linv = SampleDB.inv_chols                           optimization/sample_db.py:154-162. */
+int gvi_logdens_full_f32(const float* X, int N, int D, const float* means, const float* linv, const float* cst,
+                         int K, float* lq, void* stream);
+/* lq[k,n] = -D/2 log 2pi - sum log std_k - 1/2 sum_d ((mu_kd - x_nd)/std_kd)^2   models/diagonal_gmm.py:31-34,47-53 */
+int gvi_logdens_diag_f32(const float* X, int N, int D, const float* means, const float* stds, int K, float* lq,
+                         void* stream);
+/* out[n] = logsumexp_k(lq[k,n] + logw[k])   models/gmm.py:199-201,214-216; sample_db.py:184-192 */
+int gvi_mixture_lse_f32(const float* lq, const float* logw, int K, int N, float* out, void* stream);
+/* grad[n,:] = -sum_k r_kn Sigma_k^-1 (x_n - mu_k), r = exp(lq + logw - logq): the analytic form of the
+ * GradientTape in models/gmm.py:294-300.  prec = linv^T linv from gvi_prepare_full_f32. */
+int gvi_mixture_grad_full_f32(const float* X, int N, int D, const float* means, const float* prec, const float* lq,
+                              const float* logw, const float* logq, int K, float* grad, void* stream);
+int gvi_mixture_grad_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* lq,
+                              const float* logw, const float* logq, int K, float* grad, void* stream);
+
+/* ---- importance weights -----------------------------------------------------------------------
+ * Row-wise over lq[K,N] with background bg[N]:
+ *   self_normalized=1: w = softmax_n(lq-bg) renormalised once more (quirk: ng_estimator.py:173-176,
+ *                      weight_updater.py:60-63);   self_normalized=0: w = exp(lq-bg)/N (ng_estimator.py:147-152);
+ *   rel_map != NULL ("only_use_own_samples", ng_estimator.py:113-118): w[k,n] = [rel_map[n]==k] / n_k.
+ * Outputs (each nullable): W[K,N]; dot[k] = sum_n w[k,n] rho[n] (weight_updater.py:64,70);
+ * ess[k] = 1 / sum_n softmax_n(lq-bg)^2 (sample_selector.py:154-158);
+ * active[k, ceil(N/128)] = 1 when a 128-sample block carries weight above 1e-30 of the row maximum. */
+int gvi_importance_weights_f32(const float* lq, const float* bg, const int32_t* rel_map, int K, int N,
+                               int self_normalized, const float* rho, float* W, float* dot, float* ess,
+                               uint8_t* active, void* stream);
+
+/* ---- Stein natural-gradient statistics ---------------------------------------------------------
+ * M[k] = sum_n W[k,n] (x_n-mu_k) G[n,:]^T  (D x D),  gneg[k] = -sum_n W[k,n] G[n,:]
+ * then Hneg[k] = -sym(prec_k M[k]) (symmetrize=1, ng_estimator.py:183-187) or -(prec_k M[k])^T
+ * (symmetrize=0, :164-168).  `active` (nullable) is the block mask from gvi_importance_weights_f32. */
+size_t gvi_stein_full_workspace(int K, int D);
+int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec, const float* W,
+                       const uint8_t* active, const float* G, int K, int symmetrize, float* Hneg, float* gneg,
+                       void* ws, size_t ws_bytes, void* stream);
+/* diagonal: Hneg[k,d] = -sum_n W (x-mu)_d / std_d^2 * G[n,d]   (ng_estimator.py:177-180) */
+int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* W,
+                       const float* G, int K, float* Hneg, float* gneg, void* stream);
+
+/* ---- component updates -------------------------------------------------------------------------
+ * mode 0: KL-constrained (ng_based_component_updater.py:431-524; bisection :335-429, kl :244-333)
+ * mode 1: direct NG step  (:97-141)        mode 2: iBLR (:160-223)
+ * stepsizes[K] = eps (mode 0) or s (modes 1,2); last_etas[K] (mode 0, <0 => cold bracket);
+ * num_updates[K] (mode 2: no mean step on a component's first update).
+ * Outputs: new means/chols (old ones when success[k]==0), etas[k] / kls[k] (mode 0; -1 on failure). */
+size_t gvi_update_full_workspace(int K, int D);
+int gvi_update_full_f32(int mode, const float* means, const float* chols, const float* Hneg, const float* gneg,
+                        const float* stepsizes, const float* last_etas, const float* num_updates, int K, int D,
+                        float temperature, float* out_means, float* out_chols, int32_t* success, float* etas,
+                        float* kls, void* ws, size_t ws_bytes, void* stream);
+int gvi_update_diag_f32(int mode, const float* means, const float* stds, const float* Hneg, const float* gneg,
+                        const float* stepsizes, const float* last_etas, const float* num_updates, int K, int D,
+                        float temperature, float* out_means, float* out_stds, int32_t* success, float* etas,
+                        float* kls, void* stream);
+
+/* ---- weight updates ----------------------------------------------------------------------------
+ * direct (weight_updater.py:136-141) / trust region (:164-279).  `stepsize` is a DEVICE scalar
+ * (the weight stepsize, i.e. the KL bound for the trust-region variant).  info[0]=kl, info[1]=eta. */
+int gvi_weight_update_f32(int trust_region, const float* logw, const float* elr, int K, const float* stepsize,
+                          float temperature, float* out_logw, float* info, void* stream);
+
+/* ---- sampling -----------------------------------------------------------------------------------
+ * Counter-based N(0,1) noise: element (row, d) depends only on (seed, subsequence, row_offset+row, d),
+ * so a shard draws exactly the rows it owns regardless of the number of GPUs. */
+int gvi_fill_normal_f32(float* out, long long rows, int D, unsigned long long seed,
+                        unsigned long long subsequence, long long row_offset, void* stream);
+/* x = mu_k + L_k eps for the rows [offsets[k], offsets[k+1]) of eps/X[N,D]; mapping[n]=k
+ * (models/gmm.py:361-386, full_cov_gmm.py:36-39, diagonal_gmm.py:43-45).  offsets[K+1] is a device
+ * prefix sum; max_rows_per_component (host) bounds the grid. */
+int gvi_sample_f32(int diagonal, const float* eps, const int32_t* offsets, const float* means, const float* chols,
+                   int K, int D, int max_rows_per_component, float* X, int32_t* mapping, void* stream);
+
+/* ---- batched GEMM used by the estimators / updaters (also exported for tests) --------------------
+ * C[b] = alpha * opA(A[b]) * opB(B[b])  with A[b] (M x Kd, transA=0) or (Kd x M, transA=1), likewise B. */
+int gvi_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                  long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                  long long strideC, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMMVI_B200_H */
