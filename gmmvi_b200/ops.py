@@ -54,14 +54,36 @@ def prepare_full(chol: torch.Tensor, want_prec: bool = True):
     return linv, prec, cst, ok
 
 
-def logdens_full(X, means, linv, cst, out=None):
+_LOGDENS_MEMO = []      # [(key, keep_alive_tensors, lq)] newest first, at most 2 entries
+
+
+def _memo_key(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+
+
+def logdens_full(X, means, linv, cst, out=None, memo=True):
+    """lq[K,N].  Results are memoised on (buffer address, torch version counter, shape) of the four operands:
+    inside one iteration the background density of the sample database and the Stein estimator evaluate the same
+    components on the same samples (no-reuse configuration), and the second request is served from the first."""
     X, means, linv, cst = _chk(X, "X"), _chk(means, "means"), _chk(linv, "linv"), _chk(cst, "cst")
     N, D = X.shape
     K = means.shape[0]
+    key = _memo_key(X, means, linv, cst) if (memo and out is None) else None
+    if key is not None:
+        for k_, _, lq_ in _LOGDENS_MEMO:
+            if k_ == key:
+                return lq_
     lq = out if out is not None else torch.empty((K, N), device=X.device, dtype=torch.float32)
     _call("gvi_logdens_full_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), cst.data_ptr(), K,
           lq.data_ptr(), _stream())
+    if key is not None:
+        _LOGDENS_MEMO.insert(0, (key, (X, means, linv, cst), lq))
+        del _LOGDENS_MEMO[2:]
     return lq
+
+
+def clear_memo():
+    del _LOGDENS_MEMO[:]
 
 
 def logdens_diag(X, means, stds):

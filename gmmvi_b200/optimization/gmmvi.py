@@ -1,0 +1,68 @@
+"""GMMVI orchestrator (mirror of optimization/gmmvi.py:15-175): builds the seven modules from one config dict
+and runs `select samples -> component update -> weight update -> adapt #components`."""
+from __future__ import annotations
+
+import torch
+
+from .gmmvi_modules.component_adaptation import ComponentAdaptation
+from .gmmvi_modules.component_stepsize_adaptation import ComponentStepsizeAdaptation
+from .gmmvi_modules.ng_based_component_updater import NgBasedComponentUpdater
+from .gmmvi_modules.ng_estimator import NgEstimator
+from .gmmvi_modules.sample_selector import SampleSelector
+from .gmmvi_modules.weight_stepsize_adaptation import WeightStepsizeAdaptation
+from .gmmvi_modules.weight_updater import WeightUpdater
+from .sample_db import SampleDB
+
+
+class GMMVI:
+    def __init__(self, model, sample_db, temperature, sample_selector, num_component_adapter,
+                 component_stepsize_adapter, ng_estimator, ng_based_updater, weight_stepsize_adapter, weight_updater):
+        """optimization/gmmvi.py:63-103 (no tf.function: the kernels are launched asynchronously on one stream)."""
+        self.temperature = temperature
+        self.model = model
+        self.num_dimensions = model.num_dimensions
+        self.sample_db = sample_db
+        self.sample_selector = sample_selector
+        self.num_component_adapter = num_component_adapter
+        self.component_stepsize_adapter = component_stepsize_adapter
+        self.ng_estimator = ng_estimator
+        self.ng_based_updater = ng_based_updater
+        self.weight_stepsize_adapter = weight_stepsize_adapter
+        self.weight_updater = weight_updater
+        self.num_updates = 0
+
+    @staticmethod
+    def build_from_config(config: dict, target_distribution, model):
+        """optimization/gmmvi.py:105-144."""
+        sample_db = SampleDB.build_from_config(config, model.num_dimensions, device=model.device)
+        ng_estimator = NgEstimator.build_from_config(config, config["temperature"], model)
+        ng_based_updater = NgBasedComponentUpdater.build_from_config(config, model)
+        num_component_adapter = ComponentAdaptation.build_from_config(
+            config, model, sample_db, target_distribution=target_distribution,
+            prior_mean=config["model_initialization"]["prior_mean"],
+            initial_cov=config["model_initialization"]["initial_cov"])
+        component_stepsize_adapter = ComponentStepsizeAdaptation.build_from_config(config, model)
+        sample_selector = SampleSelector.build_from_config(config, model, sample_db, target_distribution)
+        weight_updater = WeightUpdater.build_from_config(config, model)
+        weight_stepsize_adapter = WeightStepsizeAdaptation.build_from_config(config, model)
+        return GMMVI(model, sample_db, config["temperature"], sample_selector, num_component_adapter,
+                     component_stepsize_adapter, ng_estimator, ng_based_updater, weight_stepsize_adapter,
+                     weight_updater)
+
+    def train_iter(self):
+        """optimization/gmmvi.py:146-161."""
+        samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
+            self.sample_selector.select_samples()
+        self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
+        self.num_component_adapter.adapt_number_of_components(self.num_updates)
+
+    def _run_updates(self, samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads):
+        """optimization/gmmvi.py:163-174."""
+        new_component_stepsizes = self.component_stepsize_adapter.update_stepsize(self.model.stepsizes)
+        self.model.update_stepsizes(new_component_stepsizes)
+        expected_hessian_neg, expected_grad_neg = self.ng_estimator.get_expected_hessian_and_grad(
+            samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
+        self.ng_based_updater.apply_NG_update(expected_hessian_neg, expected_grad_neg, self.model.stepsizes)
+        weight_stepsize = self.weight_stepsize_adapter.update_stepsize()
+        self.weight_updater.update_weights(samples, sample_dist_densities, target_lnpdfs, weight_stepsize)
+        self.num_updates += 1

@@ -1,0 +1,82 @@
+"""Natural-gradient estimators (mirror of optimization/gmmvi_modules/ng_estimator.py:10-376)."""
+from __future__ import annotations
+
+import torch
+
+from ... import ops
+
+
+class NgEstimator:
+    def __init__(self, temperature, model, requires_gradient, only_use_own_samples, use_self_normalized_importance_weights):
+        self._model = model
+        self._temperature = temperature
+        self._requires_gradients = requires_gradient
+        self._only_use_own_samples = only_use_own_samples
+        self._use_self_normalized_importance_weights = use_self_normalized_importance_weights
+
+    @staticmethod
+    def build_from_config(config, temperature, gmm_wrapper):
+        """ng_estimator.py:47-65."""
+        if config["ng_estimator_type"] == "Stein":
+            return SteinNgEstimator(temperature=temperature, model=gmm_wrapper, **config["ng_estimator_config"])
+        elif config["ng_estimator_type"] == "MORE":
+            return MoreNgEstimator(temperature=temperature, model=gmm_wrapper, **config["ng_estimator_config"])
+        raise ValueError(f"config['ng_estimator_type'] is '{config['ng_estimator_type']}' which is an unknown type")
+
+    @property
+    def requires_gradients(self) -> bool:
+        return self._requires_gradients
+
+    def get_expected_hessian_and_grad(self, samples, mapping, background_densities, target_lnpdfs, target_lnpdfs_grads):
+        raise NotImplementedError
+
+    def _relative_mapping(self, mapping):
+        """ng_estimator.py:244,343 (quirk 3)."""
+        return (mapping - torch.max(mapping) + self._model.num_components - 1).to(torch.int32).contiguous()
+
+    def _importance_weights(self, lq, mapping, background_densities, **want):
+        """ng_estimator.py:107-120 + :173-176 / :155: W[K,N] per component, all on device."""
+        if self._only_use_own_samples:
+            return ops.importance_weights(lq, None, self._relative_mapping(mapping), True, **want)
+        return ops.importance_weights(lq, background_densities, None, self._use_self_normalized_importance_weights, **want)
+
+
+class SteinNgEstimator(NgEstimator):
+    def __init__(self, temperature, model, only_use_own_samples, use_self_normalized_importance_weights):
+        super().__init__(temperature, model, True, only_use_own_samples, use_self_normalized_importance_weights)
+
+    def get_expected_hessian_and_grad(self, samples, mapping, background_densities, target_lnpdfs, target_lnpdfs_grads):
+        """ng_estimator.py:204-263 -> (expected_hessian_neg [K,D,D] | [K,D], expected_gradient_neg [K,D]).
+        The reference loops over components with a cholesky_solve and an [N,D,D] outer product each; here the
+        per-component sums are two batched contractions  M_k = sum_n w_kn (x_n-mu_k) g_n^T,  H_k = P_k M_k."""
+        model = self._model
+        samples = samples.contiguous()
+        _, model_densities_grad, lq = model.log_density_and_grad(samples)
+        G = (target_lnpdfs_grads - model_densities_grad).contiguous()
+        iw = self._importance_weights(lq, mapping, background_densities, want_W=True, want_active=True)
+        if model.diagonal_covs:
+            return ops.stein_diag(samples, model.means, model.chol_cov, iw["W"], G)
+        _, prec, _ = model.prepared()
+        symmetrize = self._use_self_normalized_importance_weights       # quirk 7
+        return ops.stein_full(samples, model.means, prec, iw["W"], iw["active"], G, symmetrize)
+
+
+class MoreNgEstimator(NgEstimator):
+    def __init__(self, temperature, model, only_use_own_samples, initial_l2_regularizer, use_self_normalized_importance_weights):
+        super().__init__(temperature, model, True, only_use_own_samples, use_self_normalized_importance_weights)
+        if not torch.all(model.l2_regularizers == float(initial_l2_regularizer) * torch.ones_like(model.l2_regularizers)):
+            raise AssertionError("model.l2_regularizers != initial_l2_regularizer")      # ng_estimator.py:293
+        from ..least_squares import QuadFunc
+        self.least_square_fitter = QuadFunc(model.num_dimensions)
+
+    def get_expected_hessian_and_grad(self, samples, mapping, background_densities, target_lnpdfs, target_lnpdfs_grads):
+        """ng_estimator.py:296-376."""
+        model = self._model
+        samples = samples.contiguous()
+        model_densities, lq = model.log_densities_also_individual(samples)
+        log_ratios = (target_lnpdfs - model_densities).contiguous()
+        iw = self._importance_weights(lq, mapping, background_densities, want_W=True)
+        quad, lin = self.least_square_fitter.fit_quadratic_batched(model.l2_regularizers, samples, log_ratios,
+                                                                   iw["W"], model.means, model.chol_cov)
+        g = torch.bmm(quad, model.means.unsqueeze(2)).squeeze(2) - lin
+        return quad.contiguous(), g.contiguous()

@@ -1,0 +1,123 @@
+"""Sample selection (mirror of optimization/gmmvi_modules/sample_selector.py:6-340)."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ... import ops
+
+
+class SampleSelector:
+    def __init__(self, target_distribution, model, sample_db):
+        self.target_distribution = target_distribution
+        self.model = model
+        self.sample_db = sample_db
+
+    @staticmethod
+    def build_from_config(config, gmm_wrapper, sample_db, target_distribution):
+        """sample_selector.py:39-64."""
+        if config["sample_selector_type"] == "component-based":
+            return VipsSampleSelector(target_distribution, gmm_wrapper, sample_db, **config["sample_selector_config"])
+        elif config["sample_selector_type"] == "mixture-based":
+            return LinSampleSelector(target_distribution, gmm_wrapper, sample_db, **config["sample_selector_config"])
+        raise ValueError(f"config['sample_selector_type'] is '{config['sample_selector_type']}' which is an unknown type")
+
+    def target_uld(self, samples):
+        return self.target_distribution.log_density(samples)
+
+    def get_target_grads(self, samples):
+        """sample_selector.py:69-78 -> (gradient, target)."""
+        if self.target_distribution.use_log_density_and_grad:
+            target, gradient = self.target_distribution.log_density_and_grad(samples)
+        else:
+            x = samples.detach().clone().requires_grad_(True)
+            with torch.enable_grad():
+                target = self.target_distribution.log_density(x)
+                gradient, = torch.autograd.grad(target.sum(), x)
+            target = target.detach()
+        return gradient.contiguous(), target.contiguous()
+
+    def select_samples(self):
+        raise NotImplementedError
+
+    def _prepared(self):
+        return None if self.model.diagonal_covs else self.model.prepared()
+
+
+class VipsSampleSelector(SampleSelector):
+    def __init__(self, target_distribution, model, sample_db, desired_samples_per_component, ratio_reused_samples_to_desired):
+        super().__init__(target_distribution, model, sample_db)
+        self.desired_samples_per_component = int(desired_samples_per_component)
+        self.reused_samples_per_component = int(math.floor(ratio_reused_samples_to_desired * desired_samples_per_component))
+
+    def get_effective_samples(self, model_densities, oldsamples_pdf):
+        """sample_selector.py:140-158 -> ess[K] (float)."""
+        return ops.importance_weights(model_densities, oldsamples_pdf, want_ess=True)["ess"]
+
+    def sample_where_needed(self, samples, oldsamples_pdf, num_desired_samples=None, noise=None):
+        """sample_selector.py:160-202 -> (new_samples, new_target_lnpdfs, new_target_grads, mapping)."""
+        if num_desired_samples is None:
+            num_desired_samples = self.desired_samples_per_component
+        K = self.model.num_components
+        if samples.shape[0] == 0:
+            n_add = torch.full((K,), max(1, int(num_desired_samples)), device=self.model.device, dtype=torch.int32)
+            total, mx = K * max(1, int(num_desired_samples)), max(1, int(num_desired_samples))
+        else:
+            model_logpdfs = self.model.component_log_densities(samples)
+            n_eff = torch.floor(self.get_effective_samples(model_logpdfs, oldsamples_pdf)).to(torch.int32)
+            n_add = torch.clamp(num_desired_samples - n_eff, min=1).to(torch.int32)
+            total, mx = None, None
+        new_samples, mapping = self.model.sample_from_components_no_shuffle(n_add, noise=noise, total=total,
+                                                                            max_per_component=mx)
+        new_target_grads, new_target_lnpdfs = self.get_target_grads(new_samples)
+        return new_samples, new_target_lnpdfs, new_target_grads, mapping
+
+    def select_samples(self, noise=None):
+        """sample_selector.py:204-219 -> (samples, mapping, bg, target_lnpdfs, target_grads)  (quirk 2)."""
+        num_samples_to_reuse = self.reused_samples_per_component * self.model.num_components
+        oldsamples_pdf, samples, _, _, _ = self.sample_db.get_newest_samples(num_samples_to_reuse)
+        num_reused_samples = samples.shape[0]
+        new_samples, new_target_lnpdfs, new_target_grads, mapping = self.sample_where_needed(samples, oldsamples_pdf,
+                                                                                             noise=noise)
+        self.sample_db.add_samples(new_samples, self.model.means, self.model.chol_cov, new_target_lnpdfs,
+                                   new_target_grads, mapping, prepared=self._prepared())
+        num_new_samples = new_samples.shape[0]
+        oldsamples_pdf, samples, mapping, target_lnpdfs, target_grads = self.sample_db.get_newest_samples(
+            num_reused_samples + num_new_samples)
+        return samples, mapping, oldsamples_pdf, target_lnpdfs, target_grads
+
+
+class LinSampleSelector(SampleSelector):
+    def __init__(self, target_distribution, model, sample_db, desired_samples_per_component, ratio_reused_samples_to_desired):
+        super().__init__(target_distribution, model, sample_db)
+        self.desired_samples_per_component = int(desired_samples_per_component)
+        self.reused_samples_per_component = int(math.floor(ratio_reused_samples_to_desired * desired_samples_per_component))
+
+    def get_effective_samples(self, model_densities, oldsamples_pdf):
+        """sample_selector.py:258-278 (one row: the mixture density)."""
+        return ops.importance_weights(model_densities.reshape(1, -1).contiguous(), oldsamples_pdf, want_ess=True)["ess"]
+
+    def sample_where_needed(self):
+        """sample_selector.py:280-325 -> (new_samples, mapping, num_reused_samples)."""
+        num_samples_to_reuse = self.reused_samples_per_component * self.model.num_components
+        oldsamples_pdf, old_samples, _, _, _ = self.sample_db.get_newest_samples(num_samples_to_reuse)
+        num_reused_samples = old_samples.shape[0]
+        if old_samples.shape[0] == 0:
+            n_eff = 0
+        else:
+            model_logpdfs = self.model.log_density(old_samples)
+            n_eff = int(torch.floor(self.get_effective_samples(model_logpdfs, oldsamples_pdf))[0].item())
+        n_add = max(1, self.desired_samples_per_component - n_eff)
+        new_samples, mapping = self.model.sample(n_add)
+        return new_samples, mapping, num_reused_samples
+
+    def select_samples(self):
+        """sample_selector.py:327-339."""
+        new_samples, mapping, num_reused_samples = self.sample_where_needed()
+        new_target_grads, new_target_lnpdfs = self.get_target_grads(new_samples)
+        self.sample_db.add_samples(new_samples, self.model.means, self.model.chol_cov, new_target_lnpdfs,
+                                   new_target_grads, mapping, prepared=self._prepared())
+        samples_this_iter = num_reused_samples + new_samples.shape[0]
+        oldsamples_pdf, samples, mapping, target_lnpdfs, target_grads = self.sample_db.get_newest_samples(samples_this_iter)
+        return samples, mapping, oldsamples_pdf, target_lnpdfs, target_grads

@@ -1,0 +1,134 @@
+"""SampleDB on device (mirror of optimization/sample_db.py:4-228)."""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+class SampleDB:
+    def __init__(self, dim, diagonal_covariances, keep_samples, max_samples=None, device="cuda"):
+        """optimization/sample_db.py:30-46."""
+        self._dim = dim
+        self.diagonal_covariances = diagonal_covariances
+        self.keep_samples = keep_samples
+        self.max_samples = max_samples
+        self.device = torch.device(device)
+        z = lambda *s: torch.zeros(s, device=self.device)
+        cshape = (0, dim) if diagonal_covariances else (0, dim, dim)
+        self.samples = z(0, dim)
+        self.means = z(0, dim)
+        self.chols = z(*cshape)
+        self.inv_chols = z(*cshape)
+        self.consts = z(0)                       # log-normalisers of the stored Gaussians (full cov)
+        self.target_lnpdfs = z(0)
+        self.target_grads = z(0, dim)
+        self.mapping = torch.zeros(0, device=self.device, dtype=torch.int32)
+        self.num_samples_written = 0
+        self._shared_lq = None                   # (key, lq[K,N]) of the newest evaluation, see gmmvi.py
+
+    @staticmethod
+    def build_from_config(config, num_dimensions, device="cuda"):
+        """optimization/sample_db.py:48-62."""
+        return SampleDB(num_dimensions, config["model_initialization"]["use_diagonal_covs"],
+                        config["use_sample_database"], config["max_database_size"], device=device)
+
+    def remove_every_nth_sample(self, N: int):
+        """optimization/sample_db.py:64-79."""
+        self.samples = self.samples[::N].contiguous()
+        self.target_lnpdfs = self.target_lnpdfs[::N].contiguous()
+        self.target_grads = self.target_grads[::N].contiguous()
+        mapping = self.mapping[::N]
+        # tf.unique: first-occurrence order; mapping is non-decreasing so sorted order is the same
+        used, reduced = torch.unique(mapping, sorted=True, return_inverse=True)
+        self.mapping = reduced.to(torch.int32).contiguous()
+        used = used.long()
+        self.means = self.means[used].contiguous()
+        self.chols = self.chols[used].contiguous()
+        self.inv_chols = self.inv_chols[used].contiguous()
+        if not self.diagonal_covariances:
+            self.consts = self.consts[used].contiguous()
+
+    def _invert(self, chols, prepared=None):
+        if self.diagonal_covariances:
+            return 1.0 / chols, None
+        if prepared is not None:
+            return prepared[0], prepared[2]
+        linv, _, cst, _ = ops.prepare_full(chols, want_prec=False)
+        return linv, cst
+
+    def add_samples(self, samples, means, chols, target_lnpdfs, target_grads, mapping, prepared=None):
+        """optimization/sample_db.py:82-135.  `prepared` = model.prepared() lets the caller share the already
+        inverted Cholesky factors (tf.linalg.inv(chols), :121,132) instead of recomputing them."""
+        if self.max_samples is not None and samples.shape[0] + self.samples.shape[0] > self.max_samples:
+            self.remove_every_nth_sample(2)
+        self.num_samples_written += int(samples.shape[0])
+        inv, cst = self._invert(chols, prepared)
+        mapping = mapping.to(torch.int32)
+        if self.keep_samples:
+            self.mapping = torch.cat((self.mapping, mapping + self.chols.shape[0]))
+            self.means = torch.cat((self.means, means), 0)
+            self.chols = torch.cat((self.chols, chols), 0)
+            self.inv_chols = torch.cat((self.inv_chols, inv), 0)
+            if cst is not None:
+                self.consts = torch.cat((self.consts, cst), 0)
+            self.samples = torch.cat((self.samples, samples), 0)
+            self.target_lnpdfs = torch.cat((self.target_lnpdfs, target_lnpdfs), 0)
+            self.target_grads = torch.cat((self.target_grads, target_grads), 0)
+        else:
+            self.mapping, self.means, self.chols, self.inv_chols = mapping, means, chols, inv
+            self.consts = cst if cst is not None else self.consts
+            self.samples, self.target_lnpdfs, self.target_grads = samples, target_lnpdfs, target_grads
+
+    def get_random_sample(self, N: int):
+        """optimization/sample_db.py:137-152."""
+        idx = torch.randperm(self.samples.shape[0], device=self.device)[:N]
+        return self.samples[idx], self.target_lnpdfs[idx]
+
+    def gaussian_log_pdf(self, mean, chol, inv_chol, x):
+        """optimization/sample_db.py:154-162 (single stored Gaussian)."""
+        if self.diagonal_covariances:
+            return ops.logdens_diag(x, mean.reshape(1, -1).contiguous(), chol.reshape(1, -1).contiguous())[0]
+        D = self._dim
+        cst = (-0.5 * D * 1.8378770664093453 - torch.sum(torch.log(torch.diagonal(chol)))).reshape(1)
+        return ops.logdens_full(x, mean.reshape(1, -1).contiguous(), inv_chol.reshape(1, D, D).contiguous(), cst)[0]
+
+    def evaluate_background(self, weights, means, chols, inv_chols, samples, consts=None):
+        """optimization/sample_db.py:164-192: log of the mixture the samples were drawn from.  The reference
+        accumulates the components sequentially with pairwise logsumexp; here one batched log-density pass is
+        followed by a single logsumexp over components (weights of 0 contribute -inf)."""
+        if self.diagonal_covariances:
+            lq = ops.logdens_diag(samples, means, chols)
+        else:
+            if consts is None:
+                D = self._dim
+                consts = -0.5 * D * 1.8378770664093453 - torch.sum(torch.log(torch.diagonal(chols, dim1=1, dim2=2)), 1)
+            lq = ops.logdens_full(samples, means, inv_chols, consts.contiguous())
+        return ops.mixture_lse(lq, torch.log(weights).contiguous()), lq
+
+    def get_newest_samples(self, N):
+        """optimization/sample_db.py:195-228 -> (bg[N'], samples, mapping, target_lnpdfs, target_grads)."""
+        D, dev = self._dim, self.device
+        S = int(self.samples.shape[0])
+        N = int(N)
+        self._shared_lq = None
+        if S == 0 or N == 0:
+            z = lambda *s: torch.zeros(s, device=dev)
+            return z(0), z(0, D), torch.zeros(0, device=dev, dtype=torch.int32), z(0), z(0, D)
+        start = max(0, S - N)
+        X = self.samples[start:]
+        amap = self.mapping[start:]
+        M = int(self.means.shape[0])
+        if self.keep_samples and M > 0:
+            lo, hi = int(amap.min().item()), int(amap.max().item())      # mapping is non-decreasing
+        else:
+            lo, hi = 0, M - 1
+        count = torch.zeros(hi - lo + 1, device=dev, dtype=torch.float32)
+        count.scatter_add_(0, (amap - lo).long(), torch.ones(amap.shape[0], device=dev))
+        weight = count / torch.sum(count)
+        sl = slice(lo, hi + 1)
+        consts = None if self.diagonal_covariances else self.consts[sl]
+        bg, lq = self.evaluate_background(weight, self.means[sl], self.chols[sl], self.inv_chols[sl],
+                                          X.contiguous(), consts)
+        self._shared_lq = (lo, hi, lq)
+        return bg, X, amap, self.target_lnpdfs[start:], self.target_grads[start:]

@@ -1,0 +1,199 @@
+"""API-level parity: the module mirror (GMMVI / SampleSelector / NgEstimator / updaters) against the oracle's
+`train_iter` on identical injected noise, plus runner smoke runs of the example configurations."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def base_config(updater="trust-region", weight_updater="trust-region", diag=False, desired=40, ratio=0.0,
+                use_db=False, stepsize=0.05, comp_adapter="fixed"):
+    return {
+        "temperature": 1.0, "use_sample_database": use_db, "max_database_size": 100000,
+        "model_initialization": {"use_diagonal_covs": diag, "prior_mean": 0.0, "initial_cov": 1.0},
+        "ng_estimator_type": "Stein",
+        "ng_estimator_config": {"only_use_own_samples": False, "use_self_normalized_importance_weights": True},
+        "num_component_adapter_type": "fixed", "num_component_adapter_config": {},
+        "sample_selector_type": "component-based",
+        "sample_selector_config": {"desired_samples_per_component": desired, "ratio_reused_samples_to_desired": ratio},
+        "ng_based_updater_type": updater, "ng_based_updater_config": {},
+        "component_stepsize_adapter_type": comp_adapter,
+        "component_stepsize_adapter_config": ({"initial_stepsize": stepsize} if comp_adapter == "fixed" else
+                                              {"initial_stepsize": stepsize, "min_stepsize": 0.001, "max_stepsize": 1.0,
+                                               "stepsize_inc_factor": 1.15, "stepsize_dec_factor": 0.85}),
+        "weight_updater_type": weight_updater,
+        "weight_updater_config": {"use_self_normalized_importance_weights": True},
+        "weight_stepsize_adapter_type": "fixed", "weight_stepsize_adapter_config": {"initial_stepsize": 0.1},
+    }
+
+
+def build_pair(K, D, cfg, seed=0):
+    from gmmvi_b200.models.full_cov_gmm import FullCovGMM
+    from gmmvi_b200.models.diagonal_gmm import DiagonalGMM
+    from gmmvi_b200.models.gmm_wrapper import GmmWrapper
+    from gmmvi_b200.optimization.gmmvi import GMMVI
+    from gmmvi_b200.experiments.target_distributions.gmm import GMM_LNPDF
+    rng = np.random.default_rng(seed)
+    diag = cfg["model_initialization"]["use_diagonal_covs"]
+    means = (rng.standard_normal((K, D)) * 2).astype(np.float32)
+    w = np.ones(K, np.float32) / K
+    if diag:
+        covs = rng.uniform(0.5, 2.0, (K, D)).astype(np.float32)
+        model = DiagonalGMM(w, means, covs)
+        og = O.make_diag_gmm(w, means, covs, np.float64)
+    else:
+        A = rng.standard_normal((K, D, D))
+        covs = (A @ A.transpose(0, 2, 1) / D + np.eye(D)).astype(np.float32)
+        model = FullCovGMM(w, means, covs)
+        og = O.make_full_gmm(w, means, covs, np.float64)
+    # keep the oracle on exactly the fp32 Cholesky factors the device holds
+    og.chol_cov = model.chol_cov.cpu().numpy().astype(np.float64)
+    tw = np.ones(3) / 3
+    tm = rng.standard_normal((3, D)) * 2
+    tA = rng.standard_normal((3, D, D))
+    tc = tA @ tA.transpose(0, 2, 1) / D + np.eye(D)
+    target = GMM_LNPDF(tw, tm, tc)
+    otarget = O.gmm_target(tw, tm.astype(np.float32).astype(np.float64),
+                           target.gmm.chol_cov.cpu().numpy().astype(np.float64) @
+                           target.gmm.chol_cov.cpu().numpy().astype(np.float64).transpose(0, 2, 1), np.float64)
+    wrapper = GmmWrapper.build_from_config(model, cfg)
+    og.initial_stepsize = cfg["component_stepsize_adapter_config"]["initial_stepsize"]
+    og.stepsizes = np.full(K, og.initial_stepsize)
+    og.max_reward_history_length = 2
+    gmmvi = GMMVI.build_from_config(cfg, target, wrapper)
+    return gmmvi, og, otarget
+
+
+@pytest.mark.parametrize("updater,weight_updater,diag", [("trust-region", "trust-region", False),
+                                                         ("iBLR", "direct", False),
+                                                         ("direct", "trust-region", False),
+                                                         ("trust-region", "direct", True),
+                                                         ("iBLR", "trust-region", True)])
+def test_iterations_match_oracle(updater, weight_updater, diag):
+    K, D, desired = 6, 12, 60
+    step = 0.05 if updater != "direct" else 0.002
+    cfg = base_config(updater, weight_updater, diag, desired, stepsize=step)
+    gmmvi, og, otarget = build_pair(K, D, cfg)
+    odb = O.OracleSampleDB(D, diag, False, None, np.float64)
+    ocfg = O.IterationConfig(desired_samples_per_component=desired, updater=updater, weight_updater=weight_updater,
+                             weight_stepsize=0.1)
+    rng = np.random.default_rng(99)
+    for it in range(3):
+        E = rng.standard_normal((K * desired, D)).astype(np.float32)
+        noise_fn = lambda k, D_, n: E[k * desired:(k + 1) * desired].T.astype(np.float64)
+        out = O.train_iter(og, odb, otarget, ocfg, noise_fn)
+        Ed = torch.as_tensor(E).cuda()
+        samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=Ed)
+        assert np.array_equal(mapping.cpu().numpy(), out["mapping"])               # bit exact
+        assert rel_err(samples.cpu().numpy(), out["samples"]) < 1e-5
+        assert rel_err(bg.cpu().numpy(), out["bg"]) < 1e-5
+        assert rel_err(lnpdfs.cpu().numpy(), out["lnpdfs"]) < 1e-5
+        assert rel_err(grads.cpu().numpy(), out["grads"]) < 1e-4
+        H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
+        assert rel_err(H.cpu().numpy(), out["H_neg"]) < 2e-4, it
+        assert rel_err(g.cpu().numpy(), out["g_neg"]) < 2e-4, it
+        gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
+        m = gmmvi.model
+        assert np.array_equal(gmmvi.ng_based_updater.last_success.cpu().numpy().astype(bool), out["update"]["success"])
+        assert rel_err(m.means.cpu().numpy(), og.means) < 5e-4, it
+        assert rel_err(m.chol_cov.cpu().numpy(), og.chol_cov) < 5e-4, it
+        assert np.allclose(m.weights.cpu().numpy(), og.weights, rtol=2e-3, atol=1e-6), it
+        assert np.allclose(m.l2_regularizers.cpu().numpy(), og.l2_regularizers)
+        assert np.allclose(m.num_received_updates.cpu().numpy(), og.num_received_updates)
+        if updater == "trust-region":
+            assert np.allclose(m.last_log_etas.cpu().numpy(), og.last_log_etas, rtol=1e-4)
+
+
+def test_sample_reuse_counts_are_exact():
+    """n_add = max(1, desired - floor(ess)) must be bit exact (sample_selector.py:197-199)."""
+    K, D, desired = 5, 8, 50
+    cfg = base_config(desired=desired, ratio=2.0, use_db=True)
+    gmmvi, og, otarget = build_pair(K, D, cfg, seed=3)
+    odb = O.OracleSampleDB(D, False, True, 100000, np.float64)
+    ocfg = O.IterationConfig(desired_samples_per_component=desired, ratio_reused_samples_to_desired=2.0,
+                             weight_stepsize=0.1)
+    rng = np.random.default_rng(5)
+    for it in range(3):
+        # the oracle decides how many samples are needed; both sides then consume the same noise rows
+        old_bg, old_X, _, _, _ = odb.get_newest_samples(2 * desired * K)
+        n_add = O.vips_num_additional_samples(og, old_X, old_bg, desired)
+        tot = int(n_add.sum())
+        E = rng.standard_normal((tot, D)).astype(np.float32)
+        offs = np.concatenate(([0], np.cumsum(n_add)))
+        noise_fn = lambda k, D_, n: E[offs[k]:offs[k + 1]].T.astype(np.float64)
+        out = O.train_iter(og, odb, otarget, ocfg, noise_fn)
+        samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=torch.as_tensor(E).cuda())
+        assert samples.shape[0] == out["samples"].shape[0], (it, n_add)
+        assert np.array_equal(mapping.cpu().numpy(), out["mapping"])
+        assert rel_err(bg.cpu().numpy(), out["bg"]) < 1e-5
+        gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
+        assert rel_err(gmmvi.model.means.cpu().numpy(), og.means) < 5e-4
+
+
+@pytest.mark.parametrize("experiment,codeword,overrides", [
+    ("stm20", "SAMTRON", {"num_component_adapter_config": {"del_iters": 5, "add_iters": 2},
+                          "sample_selector_config": {"desired_samples_per_component": 50, "ratio_reused_samples_to_desired": 0.0},
+                          "model_initialization": {"num_initial_components": 8}}),
+    ("planar_robot_4", "SAMTRON", {"num_component_adapter_config": {"del_iters": 5, "add_iters": 1},
+                                   "sample_selector_config": {"desired_samples_per_component": 30, "ratio_reused_samples_to_desired": 0.0},
+                                   "model_initialization": {"num_initial_components": 10}}),
+    ("gmm20", "SEPYFUX", {"sample_selector_config": {"desired_samples_per_component": 200},
+                          "component_stepsize_adapter_config": {"initial_stepsize": 0.001},
+                          "model_initialization": {"num_initial_components": 5, "use_diagonal_covs": True}}),
+    ("stm20", "SAMYROX", {"sample_selector_config": {"desired_samples_per_component": 40, "ratio_reused_samples_to_desired": 2.0},
+                          "component_stepsize_adapter_config": {"initial_stepsize": 0.01, "max_stepsize": 0.1},
+                          "model_initialization": {"num_initial_components": 6}}),
+])
+def test_runner_examples(experiment, codeword, overrides):
+    """The example scripts' flow (examples/5_samtron_20D_student-T.py:13-31, 6_samtron_planar4.py:15-51)."""
+    from gmmvi_b200.configs import get_default_algorithm_config, get_default_experiment_config, update_config
+    from gmmvi_b200.gmmvi_runner import GmmviRunner
+    algo = update_config(get_default_algorithm_config(codeword), overrides)
+    env = update_config(get_default_experiment_config(experiment), {"start_seed": 1})
+    config = update_config(env, algo)
+    config["gmmvi_runner_config"] = {"log_metrics_interval": 6}
+    runner = GmmviRunner.build_from_config(config)
+    elbos = []
+    for n in range(13):
+        metrics = runner.iterate_and_log(n)
+        assert set(["walltime", "num_samples", "num_components", "max_weight", "num_db_samples",
+                    "num_db_components"]) <= set(metrics)
+        if "-elbo" in metrics:
+            elbos.append(-metrics["-elbo"])
+    assert len(elbos) == 3 and all(np.isfinite(elbos))
+    if codeword == "SAMTRON":
+        assert elbos[-1] > elbos[0]    # the ELBO improves
+    m = runner.gmmvi.model
+    assert torch.isfinite(m.means).all() and torch.isfinite(m.chol_cov).all()
+    assert abs(float(m.weights.sum().item()) - 1.0) < 1e-4
+
+
+def test_unknown_types_raise():
+    cfg = base_config()
+    gmmvi, _, _ = build_pair(2, 3, cfg)
+    from gmmvi_b200.optimization.gmmvi_modules.ng_estimator import NgEstimator
+    from gmmvi_b200.optimization.gmmvi_modules.weight_updater import WeightUpdater
+    bad = copy.deepcopy(cfg)
+    bad["ng_estimator_type"] = "nope"
+    with pytest.raises(ValueError):
+        NgEstimator.build_from_config(bad, 1.0, gmmvi.model)
+    bad["weight_updater_type"] = "nope"
+    with pytest.raises(ValueError):
+        WeightUpdater.build_from_config(bad, gmmvi.model)
+
+
+def test_cpu_tensor_is_rejected():
+    from gmmvi_b200 import ops, _lib
+    with pytest.raises(_lib.GmmviLibraryError):
+        ops.mixture_lse(torch.zeros(2, 3), torch.zeros(2))
