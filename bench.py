@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- SAMTRON iteration throughput on the BASELINE.json stress configuration (C5).
+
+One "step" = one full SAMTRON iteration (sample -> log-density / background -> Stein NG -> KL-constrained
+component update -> trust-region weight update) of a K=512-component, D=256 full-covariance GMM on 65,536
+samples per iteration (128 per component), GMM target, no sample reuse.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = iterations/s with all inputs resident in HBM; `e2e` = the same through
+GMMVI.train_iter with the step's noise coming from pinned host memory and the updated mixture read back;
+`roofline` describes the dominant kernel (component log-density); `cpu_baseline` times the oracle (restated
+reference, NumPy/OpenBLAS fp32) on a bounded sample of the same workload on this box's host cores.
+`--impl reference` reports that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_COMP, DIM, PER_COMP = 512, 256, 128
+TARGET_COMPONENTS = 10
+PRIOR_SCALE = 31.63          # configs/experiment_configs/gmm100.yml:11 (GMM-target experiments)
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_arrays(K, D, seed=0, mean_scale=PRIOR_SCALE):
+    """w = 1/K, mu_k ~ N(0, s^2 I), L_k = chol(A A^T / D + I); GMM target with 10
+    components, means 100 (u - 0.5), covariance A^T A + I with A ~ 0.1 N(0, D) (target_distributions/gmm.py:135-145)."""
+    rng = np.random.default_rng(seed)
+    means = (rng.standard_normal((K, D)) * mean_scale).astype(np.float32)
+    chols = np.empty((K, D, D), np.float32)
+    for k in range(K):
+        A = rng.standard_normal((D, D))
+        chols[k] = np.linalg.cholesky(A @ A.T / D + np.eye(D)).astype(np.float32)
+    tmeans = (100.0 * (rng.random((TARGET_COMPONENTS, D)) - 0.5)).astype(np.float32)
+    tchols = np.empty((TARGET_COMPONENTS, D, D), np.float32)
+    for j in range(TARGET_COMPONENTS):
+        A = 0.1 * rng.normal(0.0, D, (D, D))
+        tchols[j] = np.linalg.cholesky(A.T @ A + np.eye(D)).astype(np.float32)
+    return means, chols, tmeans, tchols
+
+
+def samtron_config(per_comp):
+    return {
+        "temperature": 1.0, "use_sample_database": False, "max_database_size": 10000000,
+        "model_initialization": {"use_diagonal_covs": False, "prior_mean": 0.0, "initial_cov": 1.0},
+        "ng_estimator_type": "Stein",
+        "ng_estimator_config": {"only_use_own_samples": False, "use_self_normalized_importance_weights": True},
+        "num_component_adapter_type": "fixed", "num_component_adapter_config": {},
+        "sample_selector_type": "component-based",
+        "sample_selector_config": {"desired_samples_per_component": per_comp, "ratio_reused_samples_to_desired": 0.0},
+        "ng_based_updater_type": "trust-region", "ng_based_updater_config": {},
+        "component_stepsize_adapter_type": "improvement-based",
+        "component_stepsize_adapter_config": {"initial_stepsize": 0.1, "min_stepsize": 0.001, "max_stepsize": 1.0,
+                                              "stepsize_inc_factor": 1.15, "stepsize_dec_factor": 0.85},
+        "weight_updater_type": "trust-region", "weight_updater_config": {"use_self_normalized_importance_weights": True},
+        "weight_stepsize_adapter_type": "improvement_based",
+        "weight_stepsize_adapter_config": {"initial_stepsize": 1.0, "min_stepsize": 0.0001, "max_stepsize": 1.0,
+                                           "stepsize_inc_factor": 1.15, "stepsize_dec_factor": 0.85},
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (restated reference) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(K, D, per_comp, sample_per_comp=4, seed=0):
+    import oracle as O
+    means, chols, tmeans, tchols = workload_arrays(K, D, seed)
+    dt = np.float32
+    g = O.OracleGMM(np.log(np.ones(K, dt) / K), means, chols, False, initial_stepsize=0.1)
+    tgt = O.OracleGMM(np.log(np.ones(TARGET_COMPONENTS, dt) / TARGET_COMPONENTS), tmeans, tchols, False)
+
+    def target(X):
+        lq, gr, _ = O.log_density_and_grad(tgt, X)
+        return lq, gr
+    db = O.OracleSampleDB(D, False, False, None, dt)
+    rng = np.random.default_rng(1)
+    noise = lambda k, D_, n: rng.standard_normal((D_, n)).astype(dt)
+    t0 = time.perf_counter()
+    db._inv(chols)
+    t_inv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    X, mapping, bg, lnpdfs, grads = O.vips_select_samples(g, db, target, sample_per_comp, 0.0, noise)
+    t_sel = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    H, gn = O.stein_ng(g, X, mapping, bg, lnpdfs, grads)
+    t_stein = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.kl_constrained_update(g, H, gn, g.stepsizes, 1.0)
+    t_upd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    elr = O.expected_log_ratios(g, X, bg, lnpdfs, 1.0, True)
+    t_elr = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.trust_region_weight_update(g, elr, 1.0, 1.0)
+    t_w = time.perf_counter() - t0
+    scale = per_comp / sample_per_comp
+    t_iter = (max(t_sel - t_inv, 0.0) + t_stein + t_elr) * scale + t_inv + t_upd + t_w
+    n_s = K * sample_per_comp
+    # log-density pairs/s of the reference-structured CPU path: one component_log_densities pass
+    t0 = time.perf_counter()
+    O.component_log_densities(g, X)
+    t_ld = time.perf_counter() - t0
+    return {
+        "iters_per_sec": 1.0 / t_iter, "sec_per_iter": t_iter, "pairs_per_sec": n_s * K / t_ld,
+        "stages_s": {"select+background": t_sel - t_inv, "stein": t_stein, "expected_log_ratios": t_elr,
+                     "chol_inverse": t_inv, "kl_update": t_upd, "weight_update": t_w, "n_scale": scale},
+        "sample": (f"oracle (restated reference, NumPy/OpenBLAS fp32) timed on N={n_s} of {K * per_comp} samples "
+                   f"({sample_per_comp} of {per_comp} per component), full K={K} and D={D}; sample-proportional stages "
+                   f"scaled x{scale:g}, Cholesky inverses and the KL/weight updates timed at full K"),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gmmvi_b200 import ops, rng
+    from gmmvi_b200.distributed import ShardContext
+    from gmmvi_b200.experiments.target_distributions.gmm import GMM_LNPDF
+    from gmmvi_b200.models.full_cov_gmm import FullCovGMM
+    from gmmvi_b200.models.gmm_wrapper import GmmWrapper
+    from gmmvi_b200.optimization.gmmvi import GMMVI
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    K, D, per = args.components, args.dim, args.per_comp
+    N_total = K * per                            # samples per iteration (strong scaling: fixed, sharded over ranks)
+    lo_hi = ShardContext(rank, world).row_range(N_total)
+    N = lo_hi[1] - lo_hi[0]                      # rows this rank draws and evaluates
+
+    def build(mean_scale):
+        means, chols, tmeans, tchols = workload_arrays(K, D, 0, mean_scale)
+        model = FullCovGMM.from_cholesky(np.ones(K, np.float32) / K, means, chols, device=dev)
+        tgt = GMM_LNPDF.from_cholesky(np.ones(TARGET_COMPONENTS) / TARGET_COMPONENTS, tmeans, tchols, device=dev)
+        cfg = samtron_config(per)
+        wrapper = GmmWrapper.build_from_config(model, cfg)
+        g = GMMVI.build_from_config(cfg, tgt, wrapper)
+        if world > 1:
+            g.enable_sharding(ShardContext(rank, world))
+        return g
+
+    rng.set_seed(1234)
+    gmmvi = build(PRIOR_SCALE)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- HBM-resident timing --------------------------------------------------------------------
+    for _ in range(args.warmup):
+        gmmvi.train_iter()
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        gmmvi.train_iter()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = ops.kernel_launches() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    finite = bool(torch.isfinite(gmmvi.model.means).all() and torch.isfinite(gmmvi.model.chol_cov).all())
+
+    # ---- end to end: host noise in, updated mixture out -------------------------------------------
+    hostE = torch.empty((N, D), dtype=torch.float32).pin_memory()
+    hostE.normal_()
+    out_w = torch.empty(K, dtype=torch.float32).pin_memory()
+    out_m = torch.empty((K, D), dtype=torch.float32).pin_memory()
+    out_c = torch.empty((K, D, D), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        E = hostE.to(dev, non_blocking=True)
+        gmmvi.train_iter(noise=E)
+        out_w.copy_(gmmvi.model.log_weights, non_blocking=True)
+        out_m.copy_(gmmvi.model.means, non_blocking=True)
+        out_c.copy_(gmmvi.model.chol_cov, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    # ---- dominant kernel: component log-density, timed alone with CUDA events -------------------------
+    linv, prec, cst = gmmvi.model.prepared()
+    X = gmmvi.sample_db.samples.contiguous()
+    reps = 5
+    ops.logdens_full(X, gmmvi.model.means, linv, cst, memo=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.logdens_full(X, gmmvi.model.means, linv, cst, memo=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ld_ms = e0.elapsed_time(e1) / reps
+    pairs = float(X.shape[0]) * K
+    flop_alg = pairs * (D * D + 4 * D)
+    hbm, bf16, bf16_sus, how = measured_peaks()
+    tf32_peak = bf16 / 2.0
+    achieved = flop_alg / (ld_ms * 1e-3) / 1e12
+
+    # ---- dense variant: overlapping components (nothing can be skipped) -------------------------------
+    dense = None
+    if rank == 0 and world == 1 and not args.no_dense:
+        g2 = build(0.05)
+        for _ in range(2):
+            g2.train_iter()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(max(2, args.steps // 2)):
+            g2.train_iter()
+        e1.record()
+        torch.cuda.synchronize()
+        dense = max(2, args.steps // 2) / (e0.elapsed_time(e1) * 1e-3)
+        del g2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline(K, D, per, args.cpu_sample_per_comp) if (world == 1 and not args.no_cpu) else None
+    line = {
+        "metric": "samtron_iterations_per_sec", "value": args.steps / (ms_total * 1e-3),
+        "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5 stress: SAMTRON (Stein NG + KL-constrained update + trust-region weights), "
+                               f"K={K} full-cov components, D={D}, {per} samples/component "
+                               f"({N_total} samples/iteration sharded over {world} GPU), GMM target "
+                               f"({TARGET_COMPONENTS} comps)",
+                   "samples_per_iteration": N_total, "components": K, "dim": D,
+                   "parallelism": f"samples sharded over {world} rank(s), NCCL all-reduce of per-component statistics, "
+                                  f"component update sharded + all-gather",
+                   "l2": "working set per step (~1.2 GB: [K,N] densities, [K,D,D] factors) exceeds the 126 MB L2",
+                   "pairs_per_sec_full_iteration": N_total * K / (ms_per_step * 1e-3),
+                   "dense_variant_iterations_per_sec": dense, "finite": finite},
+        "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / tf32_peak, "traffic": None,
+                     "kernel": ops.logdens_kernel_name(), "launch_ms": ld_ms,
+                     "algorithmic_flop_per_pair": D * D + 4 * D,
+                     "peak_source": f"{how} bf16 burst {bf16} TFLOP/s / 2 (TF32 dense rate is half the bf16 rate)"},
+        "e2e": {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": N_total * D * 4,
+                "d2h_bytes_per_step": (K + K * D + K * D * D) * 4 * world},
+        "gpu_launches": launches, "clocks": clk,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["iters_per_sec"], "unit": "iterations/s", "cores": os.cpu_count(),
+                                "kind": "port", "sample": cpu["sample"], "pairs_per_sec": cpu["pairs_per_sec"],
+                                "stages_s": cpu["stages_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, D, per = args.components, args.dim, args.per_comp
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    vals = []
+    for _ in range(max(1, min(args.steps, 2))):
+        vals.append(cpu_baseline(K, D, per, args.cpu_sample_per_comp))
+    best = max(vals, key=lambda c: c["iters_per_sec"])
+    # strong scaling: the iteration's total work does not depend on the number of GPUs of the other arm
+    sec = best["sec_per_iter"]
+    value = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": "samtron_iterations_per_sec", "value": value, "unit": "iterations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C5 stress on host CPU: K={K}, D={D}, {per * K} samples/iteration",
+                   "samples_per_iteration": per * K, "components": K, "dim": D},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": best["sample"]},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--components", type=int, default=K_COMP)
+    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--per-comp", type=int, default=PER_COMP)
+    ap.add_argument("--cpu-sample-per-comp", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

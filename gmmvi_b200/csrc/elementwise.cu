@@ -258,6 +258,57 @@ importance_weights_kernel(const float* __restrict__ lq, const float* __restrict_
   }
 }
 
+// ---- pieces of the same computation for sample-sharded (multi-GPU) runs: the row statistics are reduced
+// across ranks between the calls (gmmvi_b200/distributed.py) ----------------------------------------------
+__global__ void __launch_bounds__(512)
+row_max_kernel(const float* __restrict__ lq, const float* __restrict__ bg, int N, float* __restrict__ out) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float* row = lq + (long long)k * N;
+  float m = -INFINITY;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, row[n] - bg[n]);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) out[k] = m;
+}
+
+__global__ void __launch_bounds__(512)
+row_sumexp_kernel(const float* __restrict__ lq, const float* __restrict__ bg, int N,
+                  const float* __restrict__ shift, float* __restrict__ out) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float* row = lq + (long long)k * N;
+  const float sh = shift[k];
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) s += expf(row[n] - bg[n] - sh);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[k] = s;
+}
+
+// w = exp(lw - lse[k]) * scale[k]; dot[k] = sum_n w rho[n] (local partial sum)
+__global__ void __launch_bounds__(512)
+importance_weights_ext_kernel(const float* __restrict__ lq, const float* __restrict__ bg, int N,
+                              const float* __restrict__ lse, const float* __restrict__ scale,
+                              const float* __restrict__ rowmax, const float* __restrict__ rho,
+                              float* __restrict__ W, float* __restrict__ dot, uint8_t* __restrict__ active) {
+  __shared__ float red[33];
+  const int k = blockIdx.x;
+  const float* row = lq + (long long)k * N;
+  const int nblk = ceil_div(N, 128);
+  const float l = lse[k], sc = scale ? scale[k] : 1.f, m = rowmax ? rowmax[k] : l;
+  float d = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float lw = row[n] - bg[n];
+    const float w = expf(lw - l) * sc;
+    if (W) W[(long long)k * N + n] = w;
+    if (rho) d = fmaf(w, rho[n], d);
+    if (active && (lw - m) > -60.f) active[(long long)k * nblk + (n >> 7)] = 1;
+  }
+  if (dot) {
+    d = block_sum(d, red);
+    if (threadIdx.x == 0) dot[k] = d;
+  }
+}
+
 // =================================================================================================
 // Stein finalisation and diagonal Stein
 // =================================================================================================
@@ -518,6 +569,42 @@ extern "C" int gvi_importance_weights_f32(const float* lq, const float* bg, cons
   }
   importance_weights_kernel<<<K, 512, 0, st>>>(lq, bg, rel_map, K, N, self_normalized, rho, W, dot, ess, active);
   return check_launch("importance_weights_kernel");
+}
+
+extern "C" int gvi_row_max_f32(const float* lq, const float* bg, int K, int N, float* out, void* stream) {
+  GVI_REQUIRE(K >= 0 && N >= 0, "gvi_row_max_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(lq && bg && out, "gvi_row_max_f32: null pointer");
+  row_max_kernel<<<K, 512, 0, (cudaStream_t)stream>>>(lq, bg, N, out);
+  return check_launch("row_max_kernel");
+}
+
+extern "C" int gvi_row_sumexp_f32(const float* lq, const float* bg, int K, int N, const float* shift, float* out,
+                                  void* stream) {
+  GVI_REQUIRE(K >= 0 && N >= 0, "gvi_row_sumexp_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(lq && bg && shift && out, "gvi_row_sumexp_f32: null pointer");
+  row_sumexp_kernel<<<K, 512, 0, (cudaStream_t)stream>>>(lq, bg, N, shift, out);
+  return check_launch("row_sumexp_kernel");
+}
+
+extern "C" int gvi_importance_weights_ext_f32(const float* lq, const float* bg, int K, int N, const float* lse,
+                                              const float* scale, const float* rowmax, const float* rho, float* W,
+                                              float* dot, uint8_t* active, void* stream) {
+  GVI_REQUIRE(K >= 0 && N >= 0, "gvi_importance_weights_ext_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(lq && bg && lse, "gvi_importance_weights_ext_f32: null pointer");
+  GVI_REQUIRE(!dot || rho, "gvi_importance_weights_ext_f32: dot requested without rho");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (active) {
+    cudaError_t e = cudaMemsetAsync(active, 0, (size_t)K * ceil_div(N, 128), st);
+    if (e != cudaSuccess) {
+      set_last_error("gvi_importance_weights_ext_f32: memset: %s", cudaGetErrorString(e));
+      return GVI_ERR_CUDA;
+    }
+  }
+  importance_weights_ext_kernel<<<K, 512, 0, st>>>(lq, bg, N, lse, scale, rowmax, rho, W, dot, active);
+  return check_launch("importance_weights_ext_kernel");
 }
 
 extern "C" size_t gvi_stein_full_workspace(int K, int D) {

@@ -1,0 +1,67 @@
+"""Sample / component sharding over one process per GPU (torch.distributed, NCCL over NVLink; gloo in CPU tests).
+
+Partitioning: the iteration's global sample index space [0, N) in the reference's order
+(component-major, models/gmm.py:378-386) is cut into `world` contiguous ranges; rank r draws the noise of ITS rows
+from the counter-based generator (value depends only on the global row), evaluates log-densities / target /
+gradients for them, and contributes partial per-component sums.  Exchange steps:
+  * importance-weight normalisers: all-reduce MAX [K] + 2 x all-reduce SUM [K]
+  * Stein statistics: all-reduce SUM of (-E[H]) [K,D,D] and (-E[g]) [K,D]
+  * expected log-ratios for the weight update: all-reduce SUM [K]
+  * component update: components are sharded K/world per rank, the new (mean, Cholesky) are all-gathered.
+Model parameters and all O(K) learner state are replicated and stay bit-identical on every rank because every
+collective returns the same bits to all ranks."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class ShardContext:
+    def __init__(self, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = int(rank), int(world), group
+
+    # ---- collectives -----------------------------------------------------------------------------
+    def all_reduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather_rows(self, local: torch.Tensor, total_rows: int) -> torch.Tensor:
+        """Concatenate equally sized row blocks of all ranks (rank order) -> [total_rows, ...]."""
+        if self.world == 1:
+            return local
+        out = torch.empty((total_rows,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    # ---- index arithmetic (pure host logic; covered by the gloo tests) ----------------------------------
+    def row_range(self, n_total: int) -> Tuple[int, int]:
+        """Contiguous global row range owned by this rank (the first n_total % world ranks get one more)."""
+        base, rem = divmod(int(n_total), self.world)
+        lo = self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
+
+    def local_counts(self, counts_per_component):
+        """Global per-component sample counts -> (local counts per component, first global row)."""
+        counts = [int(c) for c in counts_per_component]
+        lo, hi = self.row_range(sum(counts))
+        out, start = [], 0
+        for c in counts:
+            end = start + c
+            out.append(max(0, min(hi, end) - max(lo, start)))
+            start = end
+        return out, lo
+
+    def component_range(self, K: int) -> Optional[Tuple[int, int]]:
+        """Equal component slice for the update step, or None when K is not divisible by world."""
+        if K % self.world != 0:
+            return None
+        c = K // self.world
+        return self.rank * c, (self.rank + 1) * c

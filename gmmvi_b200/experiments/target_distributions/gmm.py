@@ -18,6 +18,17 @@ class GMM_LNPDF(LNPDF):
         self.target_covs = torch.as_tensor(np.asarray(target_covs), dtype=torch.float32)
         self.gmm = FullCovGMM(self.target_weights, self.target_means, self.target_covs, device=device)
 
+    @classmethod
+    def from_cholesky(cls, target_weights, target_means, target_chols, device="cuda"):
+        """Same target, given the Cholesky factors of the component covariances."""
+        self = cls.__new__(cls)
+        LNPDF.__init__(self, use_log_density_and_grad=True, safe_for_tf_graph=True)
+        self.target_weights = torch.as_tensor(np.asarray(target_weights), dtype=torch.float32)
+        self.target_means = torch.as_tensor(np.asarray(target_means), dtype=torch.float32)
+        self.gmm = FullCovGMM.from_cholesky(self.target_weights, self.target_means, target_chols, device=device)
+        self.target_covs = None
+        return self
+
     def log_density(self, x):
         return self.gmm.log_density(x.to(torch.float32).contiguous())
 

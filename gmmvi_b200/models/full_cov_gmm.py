@@ -25,6 +25,14 @@ class FullCovGMM(GMM):
         log_weights = torch.log(_as_param(weights, device))
         super().__init__(log_weights, means, chol)
 
+    @classmethod
+    def from_cholesky(cls, weights, means, chols, device="cuda"):
+        """Build the mixture directly from lower-triangular Cholesky factors [K,D,D] (no host factorisation)."""
+        self = cls.__new__(cls)
+        self.diagonal_covs = False
+        GMM.__init__(self, torch.log(_as_param(weights, device)), _as_param(means, device), _as_param(chols, device))
+        return self
+
     @property
     def covs(self) -> torch.Tensor:
         """models/full_cov_gmm.py:29-31."""

@@ -25,6 +25,7 @@ class GMM:
         self.num_dimensions = int(means.shape[1])
         self._const_log_det = 0.5 * self.num_dimensions * torch.log(torch.tensor(2 * pi)).item()
         self._version = 0
+        self.shard = None              # gmmvi_b200.distributed.ShardContext when samples are sharded over GPUs
         self._prepared = None          # (version, linv, prec, cst) for full covariances
         self.log_weights = log_weights
         self._means = means

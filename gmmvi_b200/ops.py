@@ -11,7 +11,21 @@ import torch
 
 from . import _lib
 
-LAUNCHES = 0   # number of C-ABI calls issued (bench.py reports kernel launches from this family)
+LAUNCHES = 0   # number of C-ABI calls issued
+KERNELS = 0    # number of CUDA kernels those calls launched (bench.py's "gpu_launches")
+
+# kernels launched per C-ABI call (memsets are not counted)
+_KERNELS_PER_CALL = {
+    "gvi_stein_full_f32": 4,          # stein_stats + bgemm(gneg) + bgemm(P M) + finalize
+}
+
+
+def kernel_launches() -> int:
+    return KERNELS
+
+
+def logdens_kernel_name() -> str:
+    return "gvi::logdens_full_kernel (SIMT fp32 tile engine)"
 
 
 def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
@@ -32,9 +46,10 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name, *args):
-    global LAUNCHES
+def _call(name, *args, kernels=None):
+    global LAUNCHES, KERNELS
     LAUNCHES += 1
+    KERNELS += kernels if kernels is not None else _KERNELS_PER_CALL.get(name, 1)
     _lib.check(getattr(_lib.lib(), name)(*args), name)
 
 
@@ -143,6 +158,43 @@ def importance_weights(lq, bg, rel_map=None, self_normalized=True, rho=None, wan
     return dict(W=W, dot=dot, ess=ess, active=active)
 
 
+def importance_weights_sharded(lq, bg, shard, self_normalized=True, rho=None, want_W=False, want_dot=False,
+                               want_active=False, n_total=None):
+    """Sample-sharded version of `importance_weights`: lq[K, N_local], bg[N_local]; the row maxima and sums of
+    exponentials are all-reduced over `shard` (gmmvi_b200.distributed.ShardContext) so that the weights are
+    normalised over ALL samples of the iteration.  `dot` is the global sum."""
+    lq, bg = _chk(lq, "lq"), _chk(bg, "bg")
+    K, N = lq.shape
+    dev = lq.device
+    rho = _chk(rho, "rho") if rho is not None else None
+    f = lambda: torch.empty(K, device=dev, dtype=torch.float32)
+    m = f()
+    _call("gvi_row_max_f32", lq.data_ptr(), bg.data_ptr(), K, N, m.data_ptr(), _stream())
+    shard.all_reduce_max_(m)
+    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    if self_normalized:
+        s = f()
+        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, m.data_ptr(), s.data_ptr(), _stream())
+        shard.all_reduce_sum_(s)
+        lse = (m + torch.log(s)).contiguous()
+        s2 = f()
+        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), s2.data_ptr(), _stream())
+        shard.all_reduce_sum_(s2)
+        scale = (1.0 / s2).contiguous()
+    else:
+        import math
+        lse = torch.full((K,), math.log(float(n_total)), device=dev, dtype=torch.float32)
+        scale = None
+    W = torch.empty((K, N), device=dev, dtype=torch.float32) if want_W else None
+    dot = f() if want_dot else None
+    active = torch.empty((K, (N + 127) // 128), device=dev, dtype=torch.uint8) if want_active else None
+    _call("gvi_importance_weights_ext_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), _ptr(scale),
+          m.data_ptr(), _ptr(rho), _ptr(W), _ptr(dot), _ptr(active), _stream())
+    if dot is not None:
+        shard.all_reduce_sum_(dot)
+    return dict(W=W, dot=dot, ess=None, active=active)
+
+
 def stein_full(X, means, prec, W, active, G, symmetrize=True):
     X, means, prec, W, G = _chk(X, "X"), _chk(means, "means"), _chk(prec, "prec"), _chk(W, "W"), _chk(G, "G")
     if active is not None:
@@ -195,7 +247,8 @@ def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, steps
         ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
         _call("gvi_update_full_f32", m, means.data_ptr(), chols.data_ptr(), Hneg.data_ptr(), gneg.data_ptr(),
               stepsizes.data_ptr(), _ptr(last_etas), _ptr(num_updates), K, D, float(temperature), om.data_ptr(),
-              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), ws.data_ptr(), nbytes, _stream())
+              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), ws.data_ptr(), nbytes, _stream(),
+              kernels=6 if m == 2 else 5)     # mirror + 2 (3) bgemm + vectors + update
     return om, oc, succ, etas, kls
 
 

@@ -49,10 +49,25 @@ class GMMVI:
                      component_stepsize_adapter, ng_estimator, ng_based_updater, weight_stepsize_adapter,
                      weight_updater)
 
-    def train_iter(self):
-        """optimization/gmmvi.py:146-161."""
+    def enable_sharding(self, shard):
+        """Shard every iteration's samples (and the component update) over the ranks of `shard`
+        (gmmvi_b200.distributed.ShardContext).  Supported for a fixed number of components without sample reuse."""
+        from .gmmvi_modules.component_adaptation import FixedComponentAdaptation
+        from .gmmvi_modules.sample_selector import VipsSampleSelector
+        if not isinstance(self.num_component_adapter, FixedComponentAdaptation):
+            raise NotImplementedError("multi-GPU sharding needs num_component_adapter_type='fixed'")
+        if not isinstance(self.sample_selector, VipsSampleSelector) or self.sample_selector.reused_samples_per_component:
+            raise NotImplementedError("multi-GPU sharding needs the component-based selector without sample reuse")
+        if self.sample_db.keep_samples:
+            raise NotImplementedError("multi-GPU sharding needs use_sample_database=False")
+        gmm = self.model.model if hasattr(self.model, "model") else self.model
+        gmm.shard = shard
+
+    def train_iter(self, noise=None):
+        """optimization/gmmvi.py:146-161.  `noise` ([N,D] standard-normal draws, optional) replaces the device
+        generator for this iteration's samples (used by the parity tests and the end-to-end benchmark)."""
         samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
-            self.sample_selector.select_samples()
+            self.sample_selector.select_samples(**({} if noise is None else {"noise": noise}))
         self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
         self.num_component_adapter.adapt_number_of_components(self.num_updates)
 

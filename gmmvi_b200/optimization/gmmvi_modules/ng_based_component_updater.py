@@ -33,9 +33,22 @@ class NgBasedComponentUpdater:
         if self._mode == "direct" and m.diagonal_covs:
             raise NotImplementedError("the reference's direct updater has no diagonal-covariance branch "
                                       "(ng_based_component_updater.py:106 inverts a rank-1 tensor)")
-        means, chols, succ, etas, kls = ops.update_components(
-            self._mode, m.diagonal_covs, m.means, m.chol_cov, expected_hessians_neg, expected_gradients_neg,
-            stepsizes, m.last_log_etas, m.num_received_updates, self.temperature)
+        shard = m.shard
+        rng_ = shard.component_range(m.num_components) if shard is not None else None
+        if rng_ is None:
+            means, chols, succ, etas, kls = ops.update_components(
+                self._mode, m.diagonal_covs, m.means, m.chol_cov, expected_hessians_neg, expected_gradients_neg,
+                stepsizes, m.last_log_etas, m.num_received_updates, self.temperature)
+        else:
+            # components sharded K/world per rank; the updated parameters are all-gathered
+            a, b = rng_
+            K = m.num_components
+            sl = lambda t: t[a:b].contiguous()
+            parts = ops.update_components(
+                self._mode, m.diagonal_covs, sl(m.means), sl(m.chol_cov), sl(expected_hessians_neg),
+                sl(expected_gradients_neg), sl(stepsizes), sl(m.last_log_etas), sl(m.num_received_updates),
+                self.temperature)
+            means, chols, succ, etas, kls = (shard.all_gather_rows(p, K) for p in parts)
         self.last_success, self.last_kls, self.last_etas = succ, kls, etas
         m.replace_components(means, chols)
         m.num_received_updates = m.num_received_updates + 1.0

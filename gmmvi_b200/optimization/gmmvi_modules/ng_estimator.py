@@ -36,6 +36,14 @@ class NgEstimator:
 
     def _importance_weights(self, lq, mapping, background_densities, **want):
         """ng_estimator.py:107-120 + :173-176 / :155: W[K,N] per component, all on device."""
+        shard = self._model.shard
+        if shard is not None:
+            if self._only_use_own_samples:
+                raise NotImplementedError("only_use_own_samples is not supported together with multi-GPU sharding")
+            n_total = shard.all_reduce_sum_(torch.tensor([float(lq.shape[1])], device=lq.device)).item() \
+                if not self._use_self_normalized_importance_weights else None
+            return ops.importance_weights_sharded(lq, background_densities, shard,
+                                                  self._use_self_normalized_importance_weights, n_total=n_total, **want)
         if self._only_use_own_samples:
             return ops.importance_weights(lq, None, self._relative_mapping(mapping), True, **want)
         return ops.importance_weights(lq, background_densities, None, self._use_self_normalized_importance_weights, **want)
@@ -55,10 +63,15 @@ class SteinNgEstimator(NgEstimator):
         G = (target_lnpdfs_grads - model_densities_grad).contiguous()
         iw = self._importance_weights(lq, mapping, background_densities, want_W=True, want_active=True)
         if model.diagonal_covs:
-            return ops.stein_diag(samples, model.means, model.chol_cov, iw["W"], G)
-        _, prec, _ = model.prepared()
-        symmetrize = self._use_self_normalized_importance_weights       # quirk 7
-        return ops.stein_full(samples, model.means, prec, iw["W"], iw["active"], G, symmetrize)
+            H, g = ops.stein_diag(samples, model.means, model.chol_cov, iw["W"], G)
+        else:
+            _, prec, _ = model.prepared()
+            symmetrize = self._use_self_normalized_importance_weights       # quirk 7
+            H, g = ops.stein_full(samples, model.means, prec, iw["W"], iw["active"], G, symmetrize)
+        if model.shard is not None:     # partial sums over this rank's samples -> sums over the whole iteration
+            model.shard.all_reduce_sum_(H)
+            model.shard.all_reduce_sum_(g)
+        return H, g
 
 
 class MoreNgEstimator(NgEstimator):

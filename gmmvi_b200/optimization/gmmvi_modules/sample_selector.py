@@ -60,7 +60,18 @@ class VipsSampleSelector(SampleSelector):
         if num_desired_samples is None:
             num_desired_samples = self.desired_samples_per_component
         K = self.model.num_components
-        if samples.shape[0] == 0:
+        shard = self.model.shard
+        row_offset = 0
+        if shard is not None:
+            # sample-sharded iteration (no reuse): this rank draws only its contiguous range of the global rows
+            if samples.shape[0] != 0:
+                raise NotImplementedError("sample reuse is not supported together with multi-GPU sharding")
+            per = max(1, int(num_desired_samples))
+            local, row_offset = shard.local_counts([per] * K)
+            n_add = torch.tensor(local, device=self.model.device, dtype=torch.int32)
+            total, mx = sum(local), max(local)
+            self.sample_db.count_override = torch.full((K,), float(per), device=self.model.device)
+        elif samples.shape[0] == 0:
             n_add = torch.full((K,), max(1, int(num_desired_samples)), device=self.model.device, dtype=torch.int32)
             total, mx = K * max(1, int(num_desired_samples)), max(1, int(num_desired_samples))
         else:
@@ -69,7 +80,7 @@ class VipsSampleSelector(SampleSelector):
             n_add = torch.clamp(num_desired_samples - n_eff, min=1).to(torch.int32)
             total, mx = None, None
         new_samples, mapping = self.model.sample_from_components_no_shuffle(n_add, noise=noise, total=total,
-                                                                            max_per_component=mx)
+                                                                            max_per_component=mx, row_offset=row_offset)
         new_target_grads, new_target_lnpdfs = self.get_target_grads(new_samples)
         return new_samples, new_target_lnpdfs, new_target_grads, mapping
 

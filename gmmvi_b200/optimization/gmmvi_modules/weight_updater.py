@@ -28,8 +28,17 @@ class WeightUpdater:
         """weight_updater.py:56-75 (evaluated on the already-updated components, quirk 15)."""
         model_densities, lq = self.model.log_densities_also_individual(samples.contiguous())
         log_ratios = (target_lnpdfs - self.temperature * model_densities).contiguous()
-        elr = ops.importance_weights(lq, background_mixture_densities, None, self.use_self_normalized_importance_weights,
-                                     rho=log_ratios, want_dot=True)["dot"]
+        shard = self.model.shard
+        if shard is not None:
+            n_total = shard.all_reduce_sum_(torch.tensor([float(lq.shape[1])], device=lq.device)).item() \
+                if not self.use_self_normalized_importance_weights else None
+            elr = ops.importance_weights_sharded(lq, background_mixture_densities, shard,
+                                                 self.use_self_normalized_importance_weights, rho=log_ratios,
+                                                 want_dot=True, n_total=n_total)["dot"]
+        else:
+            elr = ops.importance_weights(lq, background_mixture_densities, None,
+                                         self.use_self_normalized_importance_weights, rho=log_ratios,
+                                         want_dot=True)["dot"]
         self.model.store_rewards(self.temperature * self.model.log_weights + elr)
         return elr
 

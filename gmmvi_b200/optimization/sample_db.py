@@ -25,7 +25,7 @@ class SampleDB:
         self.target_grads = z(0, dim)
         self.mapping = torch.zeros(0, device=self.device, dtype=torch.int32)
         self.num_samples_written = 0
-        self._shared_lq = None                   # (key, lq[K,N]) of the newest evaluation, see gmmvi.py
+        self.count_override = None               # global per-component counts when samples are sharded over GPUs
 
     @staticmethod
     def build_from_config(config, num_dimensions, device="cuda"):
@@ -111,7 +111,6 @@ class SampleDB:
         D, dev = self._dim, self.device
         S = int(self.samples.shape[0])
         N = int(N)
-        self._shared_lq = None
         if S == 0 or N == 0:
             z = lambda *s: torch.zeros(s, device=dev)
             return z(0), z(0, D), torch.zeros(0, device=dev, dtype=torch.int32), z(0), z(0, D)
@@ -123,12 +122,14 @@ class SampleDB:
             lo, hi = int(amap.min().item()), int(amap.max().item())      # mapping is non-decreasing
         else:
             lo, hi = 0, M - 1
-        count = torch.zeros(hi - lo + 1, device=dev, dtype=torch.float32)
-        count.scatter_add_(0, (amap - lo).long(), torch.ones(amap.shape[0], device=dev))
+        if self.count_override is not None:      # sharded: this rank only holds a slice of the iteration's samples
+            count = self.count_override.to(torch.float32)
+        else:
+            count = torch.zeros(hi - lo + 1, device=dev, dtype=torch.float32)
+            count.scatter_add_(0, (amap - lo).long(), torch.ones(amap.shape[0], device=dev))
         weight = count / torch.sum(count)
         sl = slice(lo, hi + 1)
         consts = None if self.diagonal_covariances else self.consts[sl]
         bg, lq = self.evaluate_background(weight, self.means[sl], self.chols[sl], self.inv_chols[sl],
                                           X.contiguous(), consts)
-        self._shared_lq = (lo, hi, lq)
         return bg, X, amap, self.target_lnpdfs[start:], self.target_grads[start:]

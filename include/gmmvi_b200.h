@@ -72,6 +72,15 @@ int gvi_importance_weights_f32(const float* lq, const float* bg, const int32_t* 
                                int self_normalized, const float* rho, float* W, float* dot, float* ess,
                                uint8_t* active, void* stream);
 
+/* The same computation split for sample-sharded (multi-GPU) runs: every rank holds a slice of the N samples,
+ * the per-row maximum / sum of exponentials are all-reduced between the calls, and the weights are then formed
+ * from the global normalisers:  w[k,n] = exp(lq[k,n] - bg[n] - lse[k]) * scale[k]  (scale nullable = 1). */
+int gvi_row_max_f32(const float* lq, const float* bg, int K, int N, float* out, void* stream);
+int gvi_row_sumexp_f32(const float* lq, const float* bg, int K, int N, const float* shift, float* out, void* stream);
+int gvi_importance_weights_ext_f32(const float* lq, const float* bg, int K, int N, const float* lse,
+                                   const float* scale, const float* rowmax, const float* rho, float* W, float* dot,
+                                   uint8_t* active, void* stream);
+
 /* ---- Stein natural-gradient statistics ---------------------------------------------------------
  * M[k] = sum_n W[k,n] (x_n-mu_k) G[n,:]^T  (D x D),  gneg[k] = -sum_n W[k,n] G[n,:]
  * then Hneg[k] = -sym(prec_k M[k]) (symmetrize=1, ng_estimator.py:183-187) or -(prec_k M[k])^T
