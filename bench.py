@@ -324,7 +324,7 @@ def run_ours(args):
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf32_peak, "traffic": None,
-                     "kernel": ops.logdens_kernel_name(), "launch_ms": ld_ms,
+                     "kernel": ops.logdens_kernel_name(D), "launch_ms": ld_ms,
                      "algorithmic_flop_per_pair": D * D + 4 * D,
                      "peak_source": f"{how} bf16 burst {bf16} TFLOP/s / 2 (TF32 dense rate is half the bf16 rate)"},
         "e2e": {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": N_total * D * 4,

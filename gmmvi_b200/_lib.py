@@ -23,6 +23,9 @@ _SIGNATURES = {
     "gvi_prepare_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "gvi_prepare_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_i, c_vp, C.c_size_t, c_vp]),
     "gvi_logdens_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, c_f, c_vp]),
+    "gvi_split_tf32_f32": (C.c_int, [c_f, C.c_longlong, c_f, c_f, c_vp]),
+    "gvi_logdens_full_tc_supported": (C.c_int, [C.c_int]),
+    "gvi_logdens_full_tc_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),
     "gvi_logdens_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, C.c_int, c_f, c_vp]),
     "gvi_mixture_lse_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_vp]),
     "gvi_mixture_grad_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -24,8 +26,27 @@ def kernel_launches() -> int:
     return KERNELS
 
 
-def logdens_kernel_name() -> str:
+USE_TENSOR_CORES = os.environ.get("GMMVI_B200_TC", "1") != "0"
+_SPLIT_CACHE = []       # [(key, linv, hi, lo)]
+
+
+def logdens_kernel_name(D: int = 256) -> str:
+    if USE_TENSOR_CORES and _lib.lib().gvi_logdens_full_tc_supported(int(D)):
+        return "gvi::tc::tc_logdens_kernel (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM)"
     return "gvi::logdens_full_kernel (SIMT fp32 tile engine)"
+
+
+def split_tf32(linv):
+    """(hi, lo) TF32 split of the inverse Cholesky factors, cached per buffer."""
+    key = (linv.data_ptr(), linv._version, tuple(linv.shape))
+    for k_, _, hi, lo in _SPLIT_CACHE:
+        if k_ == key:
+            return hi, lo
+    hi, lo = torch.empty_like(linv), torch.empty_like(linv)
+    _call("gvi_split_tf32_f32", linv.data_ptr(), linv.numel(), hi.data_ptr(), lo.data_ptr(), _stream())
+    _SPLIT_CACHE.insert(0, (key, linv, hi, lo))
+    del _SPLIT_CACHE[3:]
+    return hi, lo
 
 
 def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
@@ -76,7 +97,7 @@ def _memo_key(*tensors):
     return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
 
 
-def logdens_full(X, means, linv, cst, out=None, memo=True):
+def logdens_full(X, means, linv, cst, out=None, memo=True, tensor_cores=None):
     """lq[K,N].  Results are memoised on (buffer address, torch version counter, shape) of the four operands:
     inside one iteration the background density of the sample database and the Stein estimator evaluate the same
     components on the same samples (no-reuse configuration), and the second request is served from the first."""
@@ -89,8 +110,14 @@ def logdens_full(X, means, linv, cst, out=None, memo=True):
             if k_ == key:
                 return lq_
     lq = out if out is not None else torch.empty((K, N), device=X.device, dtype=torch.float32)
-    _call("gvi_logdens_full_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), cst.data_ptr(), K,
-          lq.data_ptr(), _stream())
+    use_tc = USE_TENSOR_CORES if tensor_cores is None else tensor_cores
+    if use_tc and N > 0 and K > 0 and _lib.lib().gvi_logdens_full_tc_supported(D):
+        hi, lo = split_tf32(linv)
+        _call("gvi_logdens_full_tc_f32", X.data_ptr(), N, D, means.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+              cst.data_ptr(), K, lq.data_ptr(), _stream())
+    else:
+        _call("gvi_logdens_full_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), cst.data_ptr(), K,
+              lq.data_ptr(), _stream())
     if key is not None:
         _LOGDENS_MEMO.insert(0, (key, (X, means, linv, cst), lq))
         del _LOGDENS_MEMO[2:]

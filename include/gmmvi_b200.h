@@ -48,6 +48,12 @@ int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv, float* pr
  * and with linv = SampleDB.inv_chols                           optimization/sample_db.py:154-162. */
 int gvi_logdens_full_f32(const float* X, int N, int D, const float* means, const float* linv, const float* cst,
                          int K, float* lq, void* stream);
+/* Same result on the tcgen05 tensor cores (3xTF32 split precision, fp32 accumulation in TMEM, TMA-staged
+ * Linv).  linv_hi / linv_lo = gvi_split_tf32_f32(linv).  Supported when gvi_logdens_full_tc_supported(D). */
+int gvi_split_tf32_f32(const float* in, long long n, float* hi, float* lo, void* stream);
+int gvi_logdens_full_tc_supported(int D);
+int gvi_logdens_full_tc_f32(const float* X, int N, int D, const float* means, const float* linv_hi,
+                            const float* linv_lo, const float* cst, int K, float* lq, void* stream);
 /* lq[k,n] = -D/2 log 2pi - sum log std_k - 1/2 sum_d ((mu_kd - x_nd)/std_kd)^2   models/diagonal_gmm.py:31-34,47-53 */
 int gvi_logdens_diag_f32(const float* X, int N, int D, const float* means, const float* stds, int K, float* lq,
                          void* stream);
