@@ -240,6 +240,9 @@ def run_ours(args):
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     finite = bool(torch.isfinite(gmmvi.model.means).all() and torch.isfinite(gmmvi.model.chol_cov).all())
+    kl_evals = ops.last_update_evals.float() if ops.last_update_evals is not None else None
+    kl_evals_stats = None if kl_evals is None else {"mean": float(kl_evals.mean()), "max": float(kl_evals.max()),
+                                                    "success": float(gmmvi.ng_based_updater.last_success.float().mean())}
 
     # ---- end to end: host noise in, updated mixture out -------------------------------------------
     hostE = torch.empty((N, D), dtype=torch.float32).pin_memory()
@@ -320,7 +323,8 @@ def run_ours(args):
                                   f"component update sharded + all-gather",
                    "l2": "working set per step (~1.2 GB: [K,N] densities, [K,D,D] factors) exceeds the 126 MB L2",
                    "pairs_per_sec_full_iteration": N_total * K / (ms_per_step * 1e-3),
-                   "dense_variant_iterations_per_sec": dense, "finite": finite},
+                   "dense_variant_iterations_per_sec": dense, "finite": finite,
+                   "kl_evaluations_per_component": kl_evals_stats},
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf32_peak, "traffic": None,

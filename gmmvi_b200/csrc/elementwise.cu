@@ -55,20 +55,48 @@ prepare_full_kernel(const float* __restrict__ chol, int D, float* __restrict__ l
     cst[k] = (float)(-ls - 0.5 * D * kLog2PiD);
     if (ok) ok[k] = bad ? 0 : 1;
   }
-  // Y = L^-1, column c per thread
+  // Y = L^-1, column c per thread.  Rows are produced four at a time so that every Y[m][c] fetched from L2 feeds
+  // four accumulators (the column-oriented substitution is bound by the re-reads of Y, not by the flops).
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    for (int i = 0; i < c; ++i) Y[(long long)i * D + c] = 0.0;
-    Y[(long long)c * D + c] = 1.0 / (double)L[(long long)c * D + c];
-    for (int i = c + 1; i < D; ++i) {
-      const float* Li = L + (long long)i * D;
-      double s0 = 0.0, s1 = 0.0;
+    double* Yc = Y + c;
+    for (int i = 0; i < c; ++i) Yc[(long long)i * D] = 0.0;
+    Yc[(long long)c * D] = 1.0 / (double)L[(long long)c * D + c];
+    for (int i0 = c + 1; i0 < D; i0 += 4) {
+      const int nb = min(4, D - i0);
+      const float* L0 = L + (long long)i0 * D;
+      const float* L1 = L + (long long)min(i0 + 1, D - 1) * D;
+      const float* L2 = L + (long long)min(i0 + 2, D - 1) * D;
+      const float* L3 = L + (long long)min(i0 + 3, D - 1) * D;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int m = c;
-      for (; m + 1 < i; m += 2) {
-        s0 = fma((double)Li[m], Y[(long long)m * D + c], s0);
-        s1 = fma((double)Li[m + 1], Y[(long long)(m + 1) * D + c], s1);
+      for (; m + 1 < i0; m += 2) {
+        const double ya = Yc[(long long)m * D], yb = Yc[(long long)(m + 1) * D];
+        s0 = fma((double)L0[m], ya, s0); s1 = fma((double)L1[m], ya, s1);
+        s2 = fma((double)L2[m], ya, s2); s3 = fma((double)L3[m], ya, s3);
+        s0 = fma((double)L0[m + 1], yb, s0); s1 = fma((double)L1[m + 1], yb, s1);
+        s2 = fma((double)L2[m + 1], yb, s2); s3 = fma((double)L3[m + 1], yb, s3);
       }
-      if (m < i) s0 = fma((double)Li[m], Y[(long long)m * D + c], s0);
-      Y[(long long)i * D + c] = -(s0 + s1) / (double)Li[i];
+      if (m < i0) {
+        const double ya = Yc[(long long)m * D];
+        s0 = fma((double)L0[m], ya, s0); s1 = fma((double)L1[m], ya, s1);
+        s2 = fma((double)L2[m], ya, s2); s3 = fma((double)L3[m], ya, s3);
+      }
+      const double y0 = -s0 / (double)L0[i0];
+      Yc[(long long)i0 * D] = y0;
+      if (nb > 1) {
+        s1 = fma((double)L1[i0], y0, s1);
+        const double y1 = -s1 / (double)L1[i0 + 1];
+        Yc[(long long)(i0 + 1) * D] = y1;
+        if (nb > 2) {
+          s2 = fma((double)L2[i0], y0, s2); s2 = fma((double)L2[i0 + 1], y1, s2);
+          const double y2 = -s2 / (double)L2[i0 + 2];
+          Yc[(long long)(i0 + 2) * D] = y2;
+          if (nb > 3) {
+            s3 = fma((double)L3[i0], y0, s3); s3 = fma((double)L3[i0 + 1], y1, s3); s3 = fma((double)L3[i0 + 2], y2, s3);
+            Yc[(long long)(i0 + 3) * D] = -s3 / (double)L3[i0 + 3];
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -78,17 +106,21 @@ prepare_full_kernel(const float* __restrict__ chol, int D, float* __restrict__ l
   // P = Y^T Y, upper part per thread-column then mirrored
   float* P = prec + (long long)k * D * D;
   for (int b = threadIdx.x; b < D; b += blockDim.x) {
-    for (int a = 0; a <= b; ++a) {
-      double s0 = 0.0, s1 = 0.0;
-      int i = b;
-      for (; i + 1 < D; i += 2) {
-        s0 = fma(Y[(long long)i * D + a], Y[(long long)i * D + b], s0);
-        s1 = fma(Y[(long long)(i + 1) * D + a], Y[(long long)(i + 1) * D + b], s1);
+    for (int a0 = 0; a0 <= b; a0 += 4) {       // four columns a per pass over column b
+      const int a1 = min(a0 + 1, D - 1), a2 = min(a0 + 2, D - 1), a3 = min(a0 + 3, D - 1);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int i = b; i < D; ++i) {
+        const double* yr = Y + (long long)i * D;
+        const double yb = yr[b];
+        s0 = fma(yr[a0], yb, s0); s1 = fma(yr[a1], yb, s1);
+        s2 = fma(yr[a2], yb, s2); s3 = fma(yr[a3], yb, s3);
       }
-      if (i < D) s0 = fma(Y[(long long)i * D + a], Y[(long long)i * D + b], s0);
-      const float v = (float)(s0 + s1);
-      P[(long long)a * D + b] = v;
-      P[(long long)b * D + a] = v;
+      const double sv[4] = {s0, s1, s2, s3};
+      for (int r = 0; r < 4 && a0 + r <= b; ++r) {
+        const float v = (float)sv[r];
+        P[(long long)(a0 + r) * D + b] = v;
+        P[(long long)b * D + a0 + r] = v;
+      }
     }
   }
 }

@@ -24,7 +24,7 @@ int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float 
                  long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                  long long strideC, cudaStream_t st);
 
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_THREADS = 1024;
 
 __device__ __forceinline__ long long tri(int i) { return (long long)i * (i + 1) / 2; }
 
@@ -70,28 +70,41 @@ update_vectors_kernel(const float* __restrict__ means, const float* __restrict__
 // ---- packed lower-triangular linear algebra on a CTA ---------------------------------------------
 // A: packed lower triangle (row i at tri(i)); dm1: diagonal of the SPD input minus one (in), delta of
 // the pivots (out).  Returns false (uniformly) on a non-positive pivot.
+// Rows are processed by quads: the 4 lanes of a quad split the dot product of one row, so that a 1024-thread
+// CTA keeps 32 warps of independent shared-memory loads in flight (the loops are latency bound).
+constexpr int QUAD = 4;
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
 __device__ bool chol_packed(float* A, float* dm1, int D) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int sub = tid & (QUAD - 1), slot = tid / QUAD, nslots = nt / QUAD;
   for (int j = 0; j < D; ++j) {
     const float* rj = A + tri(j);
-    for (int i = j + tid; i < D; i += nt) {
-      const float* ri = A + tri(i);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int m = 0;
-      for (; m + 3 < j; m += 4) {
-        s0 = fmaf(ri[m], rj[m], s0);
-        s1 = fmaf(ri[m + 1], rj[m + 1], s1);
-        s2 = fmaf(ri[m + 2], rj[m + 2], s2);
-        s3 = fmaf(ri[m + 3], rj[m + 3], s3);
+    for (int i0 = j; i0 < D; i0 += nslots) {
+      const int i = i0 + slot;
+      float s0 = 0.f, s1 = 0.f;
+      const float* ri = A + tri(i < D ? i : j);
+      if (i < D) {
+        int m = sub;
+        for (; m + QUAD < j; m += 2 * QUAD) {
+          s0 = fmaf(ri[m], rj[m], s0);
+          s1 = fmaf(ri[m + QUAD], rj[m + QUAD], s1);
+        }
+        if (m < j) s0 = fmaf(ri[m], rj[m], s0);
       }
-      for (; m < j; ++m) s0 = fmaf(ri[m], rj[m], s0);
-      const float s = (s0 + s1) + (s2 + s3);
-      if (i == j) {
-        const float d = dm1[j] - s;
-        dm1[j] = d;
-        A[tri(j) + j] = sqrtf(1.f + d);
-      } else {
-        A[tri(i) + j] = ri[j] - s;
+      const float s = quad_sum(s0 + s1);
+      if (i < D && sub == 0) {
+        if (i == j) {
+          const float d = dm1[j] - s;
+          dm1[j] = d;
+          A[tri(j) + j] = sqrtf(1.f + d);
+        } else {
+          A[tri(i) + j] = ri[j] - s;
+        }
       }
     }
     __syncthreads();
@@ -107,24 +120,31 @@ __device__ bool chol_packed(float* A, float* dm1, int D) {
 // In-place inverse of the packed lower-triangular factor.
 __device__ void inv_packed(float* A, int D) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int sub = tid & (QUAD - 1), slot = tid / QUAD, nslots = nt / QUAD;
   for (int j = D - 1; j >= 0; --j) {
     const float xjj = 1.f / A[tri(j) + j];
-    float sreg[4];   // supports D <= 4 * blockDim
+    float sreg[4];   // supports D <= 4 * nslots
     int cnt = 0;
-    for (int i = j + 1 + tid; i < D; i += nt, ++cnt) {
-      const float* ri = A + tri(i);
+    for (int i0 = j + 1; i0 < D; i0 += nslots, ++cnt) {
+      const int i = i0 + slot;
       float s0 = 0.f, s1 = 0.f;
-      int m = j + 1;
-      for (; m + 1 <= i; m += 2) {
-        s0 = fmaf(ri[m], A[tri(m) + j], s0);
-        s1 = fmaf(ri[m + 1], A[tri(m + 1) + j], s1);
+      if (i < D) {
+        const float* ri = A + tri(i);
+        int m = j + 1 + sub;
+        for (; m + QUAD <= i; m += 2 * QUAD) {
+          s0 = fmaf(ri[m], A[tri(m) + j], s0);
+          s1 = fmaf(ri[m + QUAD], A[tri(m + QUAD) + j], s1);
+        }
+        if (m <= i) s0 = fmaf(ri[m], A[tri(m) + j], s0);
       }
-      if (m <= i) s0 = fmaf(ri[m], A[tri(m) + j], s0);
-      sreg[cnt] = -(s0 + s1) * xjj;
+      sreg[cnt] = -quad_sum(s0 + s1) * xjj;
     }
     __syncthreads();
     cnt = 0;
-    for (int i = j + 1 + tid; i < D; i += nt, ++cnt) A[tri(i) + j] = sreg[cnt];
+    for (int i0 = j + 1; i0 < D; i0 += nslots, ++cnt) {
+      const int i = i0 + slot;
+      if (i < D && sub == 0) A[tri(i) + j] = sreg[cnt];
+    }
     if (tid == 0) A[tri(j) + j] = xjj;
     __syncthreads();
   }
@@ -192,13 +212,14 @@ __device__ KlTerms eval_whitened(float* A, float* dm1, const float* __restrict__
   return out;
 }
 
-__global__ void __launch_bounds__(UPD_THREADS)
+__global__ void __launch_bounds__(UPD_THREADS, 1)
 update_full_kernel(int mode, const float* __restrict__ means, const float* __restrict__ chols,
                    const float* __restrict__ Bmat, const float* __restrict__ B2mat, const float* __restrict__ hvec,
                    const float* __restrict__ stepsizes, const float* __restrict__ last_etas,
                    const float* __restrict__ num_updates, int D, float temperature, float* __restrict__ out_means,
                    float* __restrict__ out_chols, int32_t* __restrict__ success, float* __restrict__ etas,
-                   float* __restrict__ kls, float* __restrict__ gscratch, int use_global) {
+                   float* __restrict__ kls, int32_t* __restrict__ evals, float* __restrict__ gscratch,
+                   int use_global) {
   extern __shared__ float smem[];
   __shared__ float red[33];
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -218,6 +239,7 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
   const float step = stepsizes[k];
   bool ok = true;
   float eta = -1.f, kl = -1.f;
+  int n_evals = 0;
   if (mode == 0) {
     // ---- bracketing search in log space (:335-429), cold / warm bracket (:462-471) ----
     const float last = last_etas[k];
@@ -231,6 +253,7 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
       if (diff < 1e-1f) break;
       const float e = expf(leta);
       const KlTerms t = eval_whitened(A, dm1, B, nullptr, 1.f / e, 0.f, hrev, v, u, D, 1.f / e, red);
+      ++n_evals;
       if (fabsf(step - t.kl) < 1e-1f * step) { lower = upper = leta; break; }
       if (step > t.kl) { upper = leta; feasible = true; }
       else lower = leta;
@@ -242,6 +265,7 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
     ok = (new_lower == new_upper);
     if (ok) {
       const KlTerms t = eval_whitened(A, dm1, B, nullptr, 1.f / eta, 0.f, hrev, v, u, D, 1.f / eta, red);
+      ++n_evals;
       ok = t.ok && (t.kl < FLT_MAX) && isfinite(t.kl);
       kl = t.kl;
     }
@@ -271,23 +295,26 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
       }
       om[i] = mu[i] - scale * s;
     }
-    // new Cholesky factor L' = L U^-T,  U^-T[m][j] = X[D-1-j][D-1-m]
+    // new Cholesky factor L' = L U^-T,  U^-T[m][j] = X[D-1-j][D-1-m]; a quad shares column j (rows i split)
     bool finite = true;
-    for (int j = tid; j < D; j += nt) {
-      const float* xr = A + tri(D - 1 - j);
-      for (int i = 0; i < j; ++i) oc[(long long)i * D + j] = 0.f;
-      for (int i = j; i < D; ++i) {
-        const float* Li = L + (long long)i * D;
-        float s0 = 0.f, s1 = 0.f;
-        int m = j;
-        for (; m + 1 <= i; m += 2) {
-          s0 = fmaf(Li[m], xr[D - 1 - m], s0);
-          s1 = fmaf(Li[m + 1], xr[D - 2 - m], s1);
+    {
+      const int sub = tid & (QUAD - 1), slot = tid / QUAD, nslots = nt / QUAD;
+      for (int j = slot; j < D; j += nslots) {
+        const float* xr = A + tri(D - 1 - j);
+        for (int i = sub; i < j; i += QUAD) oc[(long long)i * D + j] = 0.f;
+        for (int i = j + sub; i < D; i += QUAD) {
+          const float* Li = L + (long long)i * D;
+          float s0 = 0.f, s1 = 0.f;
+          int m = j;
+          for (; m + 1 <= i; m += 2) {
+            s0 = fmaf(Li[m], xr[D - 1 - m], s0);
+            s1 = fmaf(Li[m + 1], xr[D - 2 - m], s1);
+          }
+          if (m <= i) s0 = fmaf(Li[m], xr[D - 1 - m], s0);
+          const float val = s0 + s1;
+          finite &= isfinite(val);
+          oc[(long long)i * D + j] = val;
         }
-        if (m <= i) s0 = fmaf(Li[m], xr[D - 1 - m], s0);
-        const float val = s0 + s1;
-        finite &= isfinite(val);
-        oc[(long long)i * D + j] = val;
       }
     }
     ok = !__syncthreads_or(!finite);
@@ -303,6 +330,7 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
     success[k] = ok ? 1 : 0;
     if (etas) etas[k] = eta;
     if (kls) kls[k] = kl;
+    if (evals) evals[k] = n_evals;
   }
 }
 
@@ -423,8 +451,8 @@ extern "C" size_t gvi_update_full_workspace(int K, int D) {
 extern "C" int gvi_update_full_f32(int mode, const float* means, const float* chols, const float* Hneg,
                                    const float* gneg, const float* stepsizes, const float* last_etas,
                                    const float* num_updates, int K, int D, float temperature, float* out_means,
-                                   float* out_chols, int32_t* success, float* etas, float* kls, void* ws,
-                                   size_t ws_bytes, void* stream) {
+                                   float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals,
+                                   void* ws, size_t ws_bytes, void* stream) {
   GVI_REQUIRE(mode >= 0 && mode <= 2, "gvi_update_full_f32: unknown mode %d", mode);
   GVI_REQUIRE(K >= 0 && D > 0, "gvi_update_full_f32: bad sizes");
   if (K == 0) return GVI_OK;
@@ -432,7 +460,7 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
               "gvi_update_full_f32: null pointer");
   GVI_REQUIRE(mode != 0 || last_etas, "gvi_update_full_f32: last_etas required for the KL-constrained update");
   GVI_REQUIRE(mode != 2 || num_updates, "gvi_update_full_f32: num_updates required for iBLR");
-  GVI_REQUIRE(K <= 65535 && D <= 4 * UPD_THREADS, "gvi_update_full_f32: K or D too large");
+  GVI_REQUIRE(K <= 65535 && D <= UPD_THREADS, "gvi_update_full_f32: K or D too large");
   if (ws_bytes < gvi_update_full_workspace(K, D)) {
     set_last_error("gvi_update_full_f32: workspace %zu < %zu", ws_bytes, gvi_update_full_workspace(K, D));
     return GVI_ERR_WORKSPACE;
@@ -472,8 +500,8 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
     }
   }
   update_full_kernel<<<K, UPD_THREADS, smem, st>>>(mode, means, chols, Bm, B2, hv, stepsizes, last_etas, num_updates,
-                                                   D, temperature, out_means, out_chols, success, etas, kls, gscr,
-                                                   use_global);
+                                                   D, temperature, out_means, out_chols, success, etas, kls, evals,
+                                                   gscr, use_global);
   return check_launch("update_full_kernel");
 }
 

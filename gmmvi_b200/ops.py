@@ -249,6 +249,13 @@ def stein_diag(X, means, stds, W, G):
 
 
 UPDATE_MODES = {"trust-region": 0, "direct": 1, "iBLR": 2}
+last_update_evals = None      # int32[K]: KL evaluations per component of the most recent full-covariance update
+
+
+def LAST_UPDATE_EVALS_PTR(K, dev):
+    global last_update_evals
+    last_update_evals = torch.zeros(K, device=dev, dtype=torch.int32)
+    return last_update_evals.data_ptr()
 
 
 def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, stepsizes, last_etas=None,
@@ -274,7 +281,8 @@ def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, steps
         ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
         _call("gvi_update_full_f32", m, means.data_ptr(), chols.data_ptr(), Hneg.data_ptr(), gneg.data_ptr(),
               stepsizes.data_ptr(), _ptr(last_etas), _ptr(num_updates), K, D, float(temperature), om.data_ptr(),
-              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), ws.data_ptr(), nbytes, _stream(),
+              oc.data_ptr(), succ.data_ptr(), etas.data_ptr(), kls.data_ptr(), LAST_UPDATE_EVALS_PTR(K, dev),
+              ws.data_ptr(), nbytes, _stream(),
               kernels=6 if m == 2 else 5)     # mirror + 2 (3) bgemm + vectors + update
     return om, oc, succ, etas, kls
 

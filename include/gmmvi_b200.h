@@ -109,7 +109,8 @@ size_t gvi_update_full_workspace(int K, int D);
 int gvi_update_full_f32(int mode, const float* means, const float* chols, const float* Hneg, const float* gneg,
                         const float* stepsizes, const float* last_etas, const float* num_updates, int K, int D,
                         float temperature, float* out_means, float* out_chols, int32_t* success, float* etas,
-                        float* kls, void* ws, size_t ws_bytes, void* stream);
+                        float* kls, int32_t* evals /* nullable: KL evaluations spent per component */, void* ws,
+                        size_t ws_bytes, void* stream);
 int gvi_update_diag_f32(int mode, const float* means, const float* stds, const float* Hneg, const float* gneg,
                         const float* stepsizes, const float* last_etas, const float* num_updates, int K, int D,
                         float temperature, float* out_means, float* out_stds, int32_t* success, float* etas,
