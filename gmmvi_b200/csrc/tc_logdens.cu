@@ -251,39 +251,73 @@ tc_logdens_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
   } else if (warp >= 8) {
     // ---------------- A producers: diff = x - mu_k, split into TF32 hi / lo ----------------
-    const int p = threadIdx.x - 256;     // row of the tile
+    // Thread p owns the 16-byte chunk c = p % 8 of rows r0, r0 + 16, ..., r0 + 112 (r0 = p / 8): a warp-wide
+    // 128-bit load then covers 4 complete 128-byte row segments (4 L1 wavefronts instead of 32).
+    const int p = threadIdx.x - 256;
+    const int c = p & 7, r0 = p >> 3;
+    const int swz = (c ^ (r0 & 7)) << 4;     // (row & 7) == (r0 & 7) for every row this thread touches
+    // The (work item, k-block) sequence is flattened and the global loads of step j+1 are issued before step j is
+    // converted, so that the L2 latency of X overlaps the split / shared-memory stores of the previous block.
     int s = 0;
     uint32_t ph = 0;
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-      const int k = (int)(w / T), t = (int)(w % T);
-      const int n = t * TILE_M + p;
-      const bool rowok = n < N;
-      const float4* xrow = reinterpret_cast<const float4*>(X + (long long)(rowok ? n : 0) * D);
-      const float4* mu = reinterpret_cast<const float4*>(means + (long long)k * D);
-      for (int kb = 0; kb < nkb; ++kb) {
-        float4 xv[8];
+    const long long nwork = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nitems = nwork * nkb;
+    // cursors of the load stream (one step ahead) and of the store stream; divisions only once per work item
+    long long w_ld = blockIdx.x, w_st = blockIdx.x;
+    int kb_ld = 0, kb_st = 0;
+    int k_ld = (int)(w_ld / T), nb_ld = (int)(w_ld % T) * TILE_M + r0, nb_st = nb_ld;
+    auto issue = [&](float4 (&xv)[8], float4& m) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xv[c] = __ldg(xrow + kb * 8 + c);
-        mbar_wait(&bars->empty[s], ph ^ 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 m = __ldg(mu + kb * 8 + c);
-          float4 d;
-          d.x = rowok ? xv[c].x - m.x : 0.f;
-          d.y = rowok ? xv[c].y - m.y : 0.f;
-          d.z = rowok ? xv[c].z - m.z : 0.f;
-          d.w = rowok ? xv[c].w - m.w : 0.f;
-          float4 hi, lo;
-          hi.x = to_tf32(d.x); hi.y = to_tf32(d.y); hi.z = to_tf32(d.z); hi.w = to_tf32(d.w);
-          lo.x = to_tf32(d.x - hi.x); lo.y = to_tf32(d.y - hi.y); lo.z = to_tf32(d.z - hi.z); lo.w = to_tf32(d.w - hi.w);
-          const int off = p * 128 + ((c ^ (p & 7)) << 4);
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+      for (int q = 0; q < 8; ++q) {
+        const int n = nb_ld + 16 * q;
+        xv[q] = n < N ? __ldg(reinterpret_cast<const float4*>(X + (long long)n * D) + kb_ld * 8 + c)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      m = __ldg(reinterpret_cast<const float4*>(means + (long long)k_ld * D) + kb_ld * 8 + c);
+      if (++kb_ld == nkb) {
+        kb_ld = 0;
+        w_ld += gridDim.x;
+        if (w_ld < total) {
+          k_ld = (int)(w_ld / T);
+          nb_ld = (int)(w_ld % T) * TILE_M + r0;
         }
-        fence_proxy_async();
-        mbar_arrive(&bars->full[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    };
+    auto emit = [&](const float4 (&xv)[8], const float4& m) {
+      mbar_wait(&bars->empty[s], ph ^ 1);
+      uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool rowok = (nb_st + 16 * q) < N;
+        float4 d;
+        d.x = rowok ? xv[q].x - m.x : 0.f;
+        d.y = rowok ? xv[q].y - m.y : 0.f;
+        d.z = rowok ? xv[q].z - m.z : 0.f;
+        d.w = rowok ? xv[q].w - m.w : 0.f;
+        float4 hi, lo;
+        hi.x = to_tf32(d.x); hi.y = to_tf32(d.y); hi.z = to_tf32(d.z); hi.w = to_tf32(d.w);
+        lo.x = to_tf32(d.x - hi.x); lo.y = to_tf32(d.y - hi.y); lo.z = to_tf32(d.z - hi.z); lo.w = to_tf32(d.w - hi.w);
+        const int off = (r0 + 16 * q) * 128 + swz;
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + A_BYTES + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bars->full[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (++kb_st == nkb) {
+        kb_st = 0;
+        w_st += gridDim.x;
+        if (w_st < total) nb_st = (int)(w_st % T) * TILE_M + r0;
+      }
+    };
+    float4 xa[8], xb[8], ma, mb;
+    if (nitems > 0) issue(xa, ma);
+    for (long long j = 0; j < nitems; j += 2) {
+      if (j + 1 < nitems) issue(xb, mb);
+      emit(xa, ma);
+      if (j + 1 < nitems) {
+        if (j + 2 < nitems) issue(xa, ma);
+        emit(xb, mb);
       }
     }
   }
