@@ -323,22 +323,44 @@ __global__ void sample_diag_kernel(const float* __restrict__ eps, const int32_t*
 // =================================================================================================
 // Batched GEMM  C[b] = alpha * opA(A[b]) opB(B[b])
 // =================================================================================================
+// C[b] = alpha * opA(A[b]) diag(scaleK[b]) opB(B[b]) + beta * C[b];  lower_only skips tiles strictly above the diagonal
 __global__ void __launch_bounds__(NTHREADS)
 bgemm_kernel(int transA, int transB, int M, int Nn, int Kd, float alpha, const float* __restrict__ A, int lda,
              long long strideA, const float* __restrict__ B, int ldb, long long strideB, float* __restrict__ C,
-             int ldc, long long strideC, bool vecA, bool vecB) {
+             int ldc, long long strideC, bool vecA, bool vecB, const float* __restrict__ scaleK,
+             long long strideScale, float beta, int lower_only) {
   __shared__ SmemTiles sm;
   const int b = blockIdx.y;
   const int ntn = ceil_div(Nn, BN);
   const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
+  if (lower_only && n0 > m0 + BM - 1) return;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const float* Ab = A + b * strideA;
   const float* Bb = B + b * strideB;
+  const float* sc = scaleK ? scaleK + b * strideScale : nullptr;
   float acc[TM][TN];
   zero_acc(acc);
   auto fA = [&](int c, float (&r)[8]) {
-    if (transA) fetchA_rcontig(Ab, lda, M, Kd, m0, c * BK, vecA, r);
-    else        fetchA_kcontig(Ab, lda, M, Kd, m0, c * BK, vecA, r);
+    if (transA) {
+      fetchA_rcontig(Ab, lda, M, Kd, m0, c * BK, vecA, r);
+      if (sc) {
+        const int kidx = c * BK + (threadIdx.x >> 4);
+        const float w = kidx < Kd ? __ldg(sc + kidx) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] *= w;
+      }
+    } else {
+      fetchA_kcontig(Ab, lda, M, Kd, m0, c * BK, vecA, r);
+      if (sc) {
+        const int kq = c * BK + (threadIdx.x & 3) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float w = kq + q < Kd ? __ldg(sc + kq + q) : 0.f;
+          r[q] *= w;
+          r[4 + q] *= w;
+        }
+      }
+    }
   };
   auto sA = [&](float (*As)[AS_LD], const float (&r)[8]) {
     if (transA) storeA_rcontig(As, r); else storeA_kcontig(As, r);
@@ -359,21 +381,32 @@ bgemm_kernel(int transA, int transB, int M, int Nn, int Kd, float alpha, const f
 #pragma unroll
     for (int c = 0; c < TN; ++c) {
       const int n = n0 + tx * TN + c;
-      if (n < Nn) Cb[(long long)m * ldc + n] = alpha * acc[r][c];
+      if (n < Nn) {
+        float* dst = Cb + (long long)m * ldc + n;
+        *dst = beta != 0.f ? fmaf(beta, *dst, alpha * acc[r][c]) : alpha * acc[r][c];
+      }
     }
   }
+}
+
+int launch_bgemm_ex(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                    long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                    long long strideC, const float* scaleK, long long strideScale, float beta, int lower_only,
+                    cudaStream_t st) {
+  if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
+  const bool vecA = ptr_vec_ok(A, lda) && (strideA % 4 == 0);
+  const bool vecB = ptr_vec_ok(B, ldb) && (strideB % 4 == 0);
+  dim3 grid(ceil_div(M, BM) * ceil_div(N, BN), batch);
+  bgemm_kernel<<<grid, NTHREADS, 0, st>>>(transA, transB, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc,
+                                          strideC, vecA, vecB, scaleK, strideScale, beta, lower_only);
+  return check_launch("bgemm_kernel");
 }
 
 int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
                  long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                  long long strideC, cudaStream_t st) {
-  if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
-  const bool vecA = ptr_vec_ok(A, lda) && (strideA % 4 == 0);
-  const bool vecB = ptr_vec_ok(B, ldb) && (strideB % 4 == 0);
-  dim3 grid(ceil_div(M, BM) * ceil_div(N, BN), batch);
-  bgemm_kernel<<<grid, NTHREADS, 0, st>>>(transA, transB, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C,
-                                          ldc, strideC, vecA, vecB);
-  return check_launch("bgemm_kernel");
+  return launch_bgemm_ex(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
+                         nullptr, 0, 0.f, 0, st);
 }
 
 int launch_logdens_full(const float* X, int N, int D, const float* means, const float* linv, const float* cst,

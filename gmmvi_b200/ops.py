@@ -248,6 +248,28 @@ def stein_diag(X, means, stds, W, G):
     return Hneg, gneg
 
 
+def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=4 << 30):
+    """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32)."""
+    X, y, W = _chk(samples, "samples"), _chk(rewards, "rewards"), _chk(weights, "weights")
+    means, linv, l2 = _chk(means, "means"), _chk(linv, "linv"), _chk(regularizers, "regularizers")
+    N, D = X.shape
+    K = means.shape[0]
+    dev = X.device
+    per = _lib.lib().gvi_more_workspace(1, N, D)
+    chunk = int(max(1, min(K, memory_budget_bytes // max(per, 1))))
+    nbytes = _lib.lib().gvi_more_workspace(chunk, N, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=dev, dtype=torch.float32)
+    quad = torch.empty((K, D, D), device=dev, dtype=torch.float32)
+    lin = torch.empty((K, D), device=dev, dtype=torch.float32)
+    ok = torch.ones(K, device=dev, dtype=torch.int32)
+    F = D * (D + 1) // 2 + D + 1
+    panels = (F + 127) // 128
+    _call("gvi_more_fit_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), W.data_ptr(), y.data_ptr(),
+          l2.data_ptr(), K, chunk, quad.data_ptr(), lin.data_ptr(), ok.data_ptr(), ws.data_ptr(), nbytes, _stream(),
+          kernels=((K + chunk - 1) // chunk) * (9 + 4 * panels))
+    return quad, lin, ok
+
+
 UPDATE_MODES = {"trust-region": 0, "direct": 1, "iBLR": 2}
 last_update_evals = None      # int32[K]: KL evaluations per component of the most recent full-covariance update
 

@@ -89,7 +89,15 @@ class MoreNgEstimator(NgEstimator):
         model_densities, lq = model.log_densities_also_individual(samples)
         log_ratios = (target_lnpdfs - model_densities).contiguous()
         iw = self._importance_weights(lq, mapping, background_densities, want_W=True)
-        quad, lin = self.least_square_fitter.fit_quadratic_batched(model.l2_regularizers, samples, log_ratios,
-                                                                   iw["W"], model.means, model.chol_cov)
-        g = torch.bmm(quad, model.means.unsqueeze(2)).squeeze(2) - lin
-        return quad.contiguous(), g.contiguous()
+        if model.diagonal_covs:
+            raise NotImplementedError("MORE does not support diagonal covariances (least_squares.py:172 inverts the "
+                                      "Cholesky factor as a matrix)")
+        if model.shard is not None:
+            raise NotImplementedError("MORE is not supported together with multi-GPU sharding")
+        linv, _, _ = model.prepared()
+        quad, lin, ok = self.least_square_fitter.fit_quadratic_batched(model.l2_regularizers, samples, log_ratios,
+                                                                       iw["W"], model.means, linv)
+        self.last_ok = ok
+        # expected_gradient_neg = reward_quad mu - reward_lin   (ng_estimator.py:369-373)
+        g = ops.bgemm(quad, model.means.unsqueeze(2).contiguous()).squeeze(2) - lin
+        return quad, g.contiguous()

@@ -14,5 +14,6 @@ class QuadFunc:
         self.num_quad_features = dim * (dim + 1) // 2
         self.num_features = self.num_quad_features + dim + 1
 
-    def fit_quadratic_batched(self, regularizers, samples, rewards, weights, means, chols):
-        return ops.more_fit(regularizers, samples, rewards, weights, means, chols)
+    def fit_quadratic_batched(self, regularizers, samples, rewards, weights, means, linv):
+        """least_squares.py:126-191 for all components: -> (quad_term[K,D,D], lin_term[K,D], ok[K])."""
+        return ops.more_fit(regularizers, samples, rewards, weights, means, linv)

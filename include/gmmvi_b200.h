@@ -99,6 +99,17 @@ int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const f
 int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* W,
                        const float* G, int K, float* Hneg, float* gneg, void* stream);
 
+/* ---- MORE natural-gradient estimator -----------------------------------------------------------
+ * Weighted ridge regression on quadratic features of the whitened samples, per component (ng_estimator.py:296-376,
+ * least_squares.py:34-191): quad[k] = reward_quad (= expected_hessian_neg), lin[k] = reward_lin.
+ * W[K,N] importance weights, y[N] = target_lnpdf - log q, l2reg[K]; linv from gvi_prepare_full_f32.
+ * Components are processed `chunk` at a time (workspace grows with chunk); ok[k] (caller-initialised to 1) is
+ * cleared when the normal matrix of component k is not positive definite. */
+size_t gvi_more_workspace(int chunk, int N, int D);
+int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const float* linv, const float* W,
+                     const float* y, const float* l2reg, int K, int chunk, float* quad, float* lin, int32_t* ok,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* ---- component updates -------------------------------------------------------------------------
  * mode 0: KL-constrained (ng_based_component_updater.py:431-524; bisection :335-429, kl :244-333)
  * mode 1: direct NG step  (:97-141)        mode 2: iBLR (:160-223)

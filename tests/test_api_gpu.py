@@ -197,3 +197,55 @@ def test_cpu_tensor_is_rejected():
     from gmmvi_b200 import ops, _lib
     with pytest.raises(_lib.GmmviLibraryError):
         ops.mixture_lse(torch.zeros(2, 3), torch.zeros(2))
+
+
+def test_more_iteration_matches_oracle():
+    """MORE estimator + trust-region updates through the module API (BASELINE config C3's algorithm, small shape)."""
+    K, D, desired = 3, 6, 400
+    cfg = base_config("trust-region", "trust-region", False, desired, stepsize=0.05)
+    cfg["ng_estimator_type"] = "MORE"
+    cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": 1e-8,
+                                  "use_self_normalized_importance_weights": True}
+    gmmvi, og, otarget = build_pair(K, D, cfg, seed=4)
+    og.initial_regularizer = 1e-8
+    og.l2_regularizers = np.full(K, 1e-8)
+    odb = O.OracleSampleDB(D, False, False, None, np.float64)
+    ocfg = O.IterationConfig(desired_samples_per_component=desired, ng_estimator="MORE", weight_stepsize=0.1)
+    rng = np.random.default_rng(123)
+    for it in range(2):
+        E = rng.standard_normal((K * desired, D)).astype(np.float32)
+        out = O.train_iter(og, odb, otarget, ocfg, lambda k, D_, n: E[k * desired:(k + 1) * desired].T.astype(np.float64))
+        samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=torch.as_tensor(E).cuda())
+        H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
+        assert rel_err(H.cpu().numpy(), out["H_neg"]) < 2e-3
+        assert rel_err(g.cpu().numpy(), out["g_neg"]) < 2e-3
+        gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
+        assert rel_err(gmmvi.model.means.cpu().numpy(), og.means) < 2e-3
+        assert rel_err(gmmvi.model.chol_cov.cpu().numpy(), og.chol_cov) < 2e-3
+
+
+def test_more_c3_shape():
+    """BASELINE config C3 shape (D=100 -> F=5151 features, N >= F), two components: the blocked Cholesky path."""
+    from gmmvi_b200 import ops
+    from test_kernels_gpu import make_problem, gmm32_of, dev
+    K, D, N = 2, 100, 6000
+    g, X = make_problem(K, D, N, seed=9, scale=0.5)
+    g32 = gmm32_of(g)
+    g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
+                       g32.chol_cov.astype(np.float64), False, initial_regularizer=1e-6)
+    X64 = X.astype(np.float64)
+    rng = np.random.default_rng(10)
+    Q = rng.standard_normal((D, D)); Q = Q @ Q.T / D + np.eye(D)
+    tl = (-0.5 * np.einsum("ni,ij,nj->n", X64, Q, X64)).astype(np.float32)
+    mapping = np.sort(rng.integers(0, K, N)).astype(np.int32); mapping[-1] = K - 1
+    lq64 = O.component_log_densities(g_in, X64)
+    bg = O.logsumexp(lq64 + g_in.log_weights[:, None], axis=0).astype(np.float32)
+    Href, gref = O.more_ng(g_in, X64, mapping, bg.astype(np.float64), tl.astype(np.float64))
+    linv, prec, cst, _ = ops.prepare_full(dev(g32.chol_cov))
+    lq = ops.logdens_full(dev(X), dev(g32.means), linv, cst)
+    logq = ops.mixture_lse(lq, dev(g32.log_weights))
+    iw = ops.importance_weights(lq, dev(bg), None, True, None, True)
+    l2 = torch.full((K,), 1e-6, device="cuda")
+    quad, lin, ok = ops.more_fit(l2, dev(X), dev(tl) - logq, iw["W"], dev(g32.means), linv)
+    assert ok.cpu().numpy().all()
+    assert rel_err(quad.cpu().numpy(), Href) < 5e-3

@@ -375,3 +375,35 @@ def test_bgemm(ta, tb):
     ref = (A.transpose(0, 2, 1) if ta else A).astype(np.float64) @ (B.transpose(0, 2, 1) if tb else B).astype(np.float64)
     out = ops.bgemm(dev(A), dev(B), ta, tb, 0.5)
     assert rel_err(out.cpu().numpy(), 0.5 * ref) < 1e-5
+
+
+@pytest.mark.parametrize("K,D,N,self_norm", [(3, 4, 300, True), (4, 12, 1500, True), (2, 20, 2000, False),
+                                              (2, 40, 4000, True)])
+def test_more_estimator(K, D, N, self_norm):
+    """MORE against the oracle (ng_estimator.py:296-376): needs N >= F = D(D+1)/2 + D + 1 samples."""
+    from gmmvi_b200 import ops
+    g, X = make_problem(K, D, N, seed=80 + D, scale=1.0)
+    g32 = gmm32_of(g)
+    g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
+                       g32.chol_cov.astype(np.float64), False, initial_regularizer=1e-8)
+    rng = np.random.default_rng(81)
+    X64 = X.astype(np.float64)
+    # a smooth target: quadratic + small non-quadratic perturbation
+    Q = rng.standard_normal((D, D)); Q = Q @ Q.T / D + np.eye(D)
+    tl = (-0.5 * np.einsum("ni,ij,nj->n", X64, Q, X64) + 0.1 * np.sin(X64).sum(1)).astype(np.float32)
+    mapping = np.sort(rng.integers(0, K, N)).astype(np.int32)
+    mapping[-1] = K - 1
+    lq64 = O.component_log_densities(g_in, X64)
+    bg = O.logsumexp(lq64 + g_in.log_weights[:, None], axis=0).astype(np.float32)
+    Href, gref = O.more_ng(g_in, X64, mapping, bg.astype(np.float64), tl.astype(np.float64), None, False, self_norm)
+    linv, prec, cst, _ = ops.prepare_full(dev(g32.chol_cov))
+    lq = ops.logdens_full(dev(X), dev(g32.means), linv, cst)
+    logq = ops.mixture_lse(lq, dev(g32.log_weights))
+    iw = ops.importance_weights(lq, dev(bg), None, self_norm, None, True)
+    y = dev(tl) - logq
+    l2 = torch.full((K,), 1e-8, device="cuda")
+    quad, lin, ok = ops.more_fit(l2, dev(X), y, iw["W"], dev(g32.means), linv, memory_budget_bytes=64 << 20)
+    assert ok.cpu().numpy().all()
+    gneg = (quad @ dev(g32.means).unsqueeze(2)).squeeze(2) - lin
+    assert rel_err(quad.cpu().numpy(), Href) < 2e-3, rel_err(quad.cpu().numpy(), Href)
+    assert rel_err(gneg.cpu().numpy(), gref) < 2e-3
