@@ -324,6 +324,10 @@ __global__ void sample_diag_kernel(const float* __restrict__ eps, const int32_t*
 // Batched GEMM  C[b] = alpha * opA(A[b]) opB(B[b])
 // =================================================================================================
 // C[b] = alpha * opA(A[b]) diag(scaleK[b]) opB(B[b]) + beta * C[b];  lower_only skips tiles strictly above the diagonal
+// LONGK: reductions longer than 2048 are accumulated in 512-element segments that are folded into a second
+// accumulator set (two-level summation), which keeps the fp32 rounding error of e.g. Phi^T W Phi over thousands of
+// samples at the level of a blocked BLAS instead of growing linearly with the reduction length.
+template <bool LONGK>
 __global__ void __launch_bounds__(NTHREADS)
 bgemm_kernel(int transA, int transB, int M, int Nn, int Kd, float alpha, const float* __restrict__ A, int lda,
              long long strideA, const float* __restrict__ B, int ldb, long long strideB, float* __restrict__ C,
@@ -372,7 +376,27 @@ bgemm_kernel(int transA, int transB, int M, int Nn, int Kd, float alpha, const f
   auto sB = [&](float (*Bs)[BS_LD], const float (&r)[4]) {
     if (transB) storeB_kcontig(Bs, r); else storeB_rcontig(Bs, r);
   };
-  tile_mainloop(acc, sm, 0, ceil_div(Kd, BK), ty, tx, fA, sA, fB, sB);
+  if constexpr (LONGK) {
+    float tot[TM][TN];
+    zero_acc(tot);
+    const int nchunks = ceil_div(Kd, BK);
+    for (int c0 = 0; c0 < nchunks; c0 += 32) {
+      tile_mainloop(acc, sm, c0, min(nchunks, c0 + 32), ty, tx, fA, sA, fB, sB);
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) {
+          tot[r][c] += acc[r][c];
+          acc[r][c] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = tot[r][c];
+  } else {
+    tile_mainloop(acc, sm, 0, ceil_div(Kd, BK), ty, tx, fA, sA, fB, sB);
+  }
   float* Cb = C + b * strideC;
 #pragma unroll
   for (int r = 0; r < TM; ++r) {
@@ -397,8 +421,12 @@ int launch_bgemm_ex(int transA, int transB, int batch, int M, int N, int Kd, flo
   const bool vecA = ptr_vec_ok(A, lda) && (strideA % 4 == 0);
   const bool vecB = ptr_vec_ok(B, ldb) && (strideB % 4 == 0);
   dim3 grid(ceil_div(M, BM) * ceil_div(N, BN), batch);
-  bgemm_kernel<<<grid, NTHREADS, 0, st>>>(transA, transB, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc,
-                                          strideC, vecA, vecB, scaleK, strideScale, beta, lower_only);
+  if (Kd > 2048)
+    bgemm_kernel<true><<<grid, NTHREADS, 0, st>>>(transA, transB, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C,
+                                                  ldc, strideC, vecA, vecB, scaleK, strideScale, beta, lower_only);
+  else
+    bgemm_kernel<false><<<grid, NTHREADS, 0, st>>>(transA, transB, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C,
+                                                   ldc, strideC, vecA, vecB, scaleK, strideScale, beta, lower_only);
   return check_launch("bgemm_kernel");
 }
 
