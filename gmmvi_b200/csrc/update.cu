@@ -26,7 +26,7 @@ int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float 
 
 constexpr int UPD_THREADS = 1024;
 
-__device__ __forceinline__ long long tri(int i) { return (long long)i * (i + 1) / 2; }
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 // Rlow[a][b] = R[max(a,b)][min(a,b)]  (tf.linalg.cholesky only reads the lower triangle)
 __global__ void mirror_lower_kernel(const float* __restrict__ R, int D, float* __restrict__ out) {
@@ -70,8 +70,9 @@ update_vectors_kernel(const float* __restrict__ means, const float* __restrict__
 // ---- packed lower-triangular linear algebra on a CTA ---------------------------------------------
 // A: packed lower triangle (row i at tri(i)); dm1: diagonal of the SPD input minus one (in), delta of
 // the pivots (out).  Returns false (uniformly) on a non-positive pivot.
-// Rows are processed by quads: the 4 lanes of a quad split the dot product of one row, so that a 1024-thread
-// CTA keeps 32 warps of independent shared-memory loads in flight (the loops are latency bound).
+// Both routines are blocked by 4 columns: the bulk of the work is a panel update in which every element of a row
+// that is fetched from shared memory feeds 4 accumulators (5 loads per 4 FMAs instead of 2 per FMA), rows are
+// split over quads of lanes so that a 1024-thread CTA has 32 warps in flight, and there are 3 barriers per 4 columns.
 constexpr int QUAD = 4;
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -82,70 +83,179 @@ __device__ __forceinline__ float quad_sum(float v) {
 __device__ bool chol_packed(float* A, float* dm1, int D) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int sub = tid & (QUAD - 1), slot = tid / QUAD, nslots = nt / QUAD;
-  for (int j = 0; j < D; ++j) {
-    const float* rj = A + tri(j);
-    for (int i0 = j; i0 < D; i0 += nslots) {
-      const int i = i0 + slot;
-      float s0 = 0.f, s1 = 0.f;
-      const float* ri = A + tri(i < D ? i : j);
-      if (i < D) {
-        int m = sub;
-        for (; m + QUAD < j; m += 2 * QUAD) {
-          s0 = fmaf(ri[m], rj[m], s0);
-          s1 = fmaf(ri[m + QUAD], rj[m + QUAD], s1);
+  for (int j0 = 0; j0 < D; j0 += 4) {
+    const int nb = min(4, D - j0);
+    // ---- panel update: subtract the contribution of the columns < j0 from rows >= j0, columns [j0, j0 + nb)
+    if (j0 > 0) {
+      const float* r0 = A + tri(j0);
+      const float* r1 = A + tri(min(j0 + 1, D - 1));
+      const float* r2 = A + tri(min(j0 + 2, D - 1));
+      const float* r3 = A + tri(min(j0 + 3, D - 1));
+      for (int i0 = j0; i0 < D; i0 += nslots) {
+        const int i = i0 + slot;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (i < D) {
+          const float* ri = A + tri(i);
+          for (int m = sub; m < j0; m += QUAD) {
+            const float a = ri[m];
+            s0 = fmaf(a, r0[m], s0);
+            s1 = fmaf(a, r1[m], s1);
+            s2 = fmaf(a, r2[m], s2);
+            s3 = fmaf(a, r3[m], s3);
+          }
         }
-        if (m < j) s0 = fmaf(ri[m], rj[m], s0);
-      }
-      const float s = quad_sum(s0 + s1);
-      if (i < D && sub == 0) {
-        if (i == j) {
-          const float d = dm1[j] - s;
-          dm1[j] = d;
-          A[tri(j) + j] = sqrtf(1.f + d);
-        } else {
-          A[tri(i) + j] = ri[j] - s;
+        s0 = quad_sum(s0); s1 = quad_sum(s1); s2 = quad_sum(s2); s3 = quad_sum(s3);
+        if (i < D && sub == 0) {
+          float* ri = A + tri(i);
+          const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = j0 + c;
+            if (c < nb && j <= i) {
+              if (j == i) dm1[i] -= sv[c];
+              else ri[j] -= sv[c];
+            }
+          }
         }
       }
     }
     __syncthreads();
-    const float c = A[tri(j) + j];
-    if (!(c > 0.f) || !isfinite(c)) return false;
-    const float ic = 1.f / c;
-    for (int i = j + 1 + tid; i < D; i += nt) A[tri(i) + j] *= ic;
+    // ---- 4 x 4 diagonal block, factored redundantly by every thread (l = lower factor, dn = pivot - 1)
+    float l[4][4], dn[4];
+    bool good = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) l[c][c2] = 0.f;
+      dn[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nb) {
+        const float* rc = A + tri(j0 + c) + j0;
+        float dd = dm1[j0 + c];
+#pragma unroll
+        for (int c2 = 0; c2 < c; ++c2) {
+          float v = rc[c2];
+#pragma unroll
+          for (int c3 = 0; c3 < c2; ++c3) v = fmaf(-l[c][c3], l[c2][c3], v);
+          l[c][c2] = v / l[c2][c2];
+          dd = fmaf(-l[c][c2], l[c][c2], dd);
+        }
+        const float piv = 1.f + dd;
+        if (!(piv > 0.f) || !isfinite(piv)) good = false;
+        dn[c] = dd;
+        l[c][c] = sqrtf(piv);
+      } else {
+        l[c][c] = 1.f;
+      }
+    }
+    __syncthreads();          // every thread has read the block before it is overwritten
+    if (!good) return false;  // uniform: all threads computed the same pivots
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nb) {
+          float* rc = A + tri(j0 + c) + j0;
+          dm1[j0 + c] = dn[c];
+#pragma unroll
+          for (int c2 = 0; c2 <= c; ++c2) rc[c2] = l[c][c2];
+        }
+    }
+    const float i0v = 1.f / l[0][0], i1v = 1.f / l[1][1], i2v = 1.f / l[2][2], i3v = 1.f / l[3][3];
+    for (int i = j0 + nb + tid; i < D; i += nt) {
+      float* ri = A + tri(i) + j0;
+      const float x0 = ri[0] * i0v;
+      ri[0] = x0;
+      if (nb > 1) {
+        const float x1 = (ri[1] - x0 * l[1][0]) * i1v;
+        ri[1] = x1;
+        if (nb > 2) {
+          const float x2 = (ri[2] - x0 * l[2][0] - x1 * l[2][1]) * i2v;
+          ri[2] = x2;
+          if (nb > 3) ri[3] = (ri[3] - x0 * l[3][0] - x1 * l[3][1] - x2 * l[3][2]) * i3v;
+        }
+      }
+    }
     __syncthreads();
   }
   return true;
 }
 
-// In-place inverse of the packed lower-triangular factor.
+// In-place inverse of the packed lower-triangular factor, column blocks of 4 from the right:
+// X21 = -(X22 C21) X11 with X11 the inverse of the 4 x 4 diagonal block.
 __device__ void inv_packed(float* A, int D) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int sub = tid & (QUAD - 1), slot = tid / QUAD, nslots = nt / QUAD;
-  for (int j = D - 1; j >= 0; --j) {
-    const float xjj = 1.f / A[tri(j) + j];
-    float sreg[4];   // supports D <= 4 * nslots
+  const int nblk = (D + 3) / 4;
+  for (int bi = nblk - 1; bi >= 0; --bi) {
+    const int j0 = bi * 4, nb = min(4, D - j0), r0 = j0 + nb;
+    // inverse of the diagonal block (redundantly per thread)
+    float l[4][4], x[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        l[c][c2] = (c < nb && c2 <= c) ? A[tri(j0 + c) + j0 + c2] : (c == c2 ? 1.f : 0.f);
+        x[c][c2] = 0.f;
+      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      x[c][c] = 1.f / l[c][c];
+#pragma unroll
+      for (int r = c + 1; r < 4; ++r) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int c2 = c; c2 < r; ++c2) sacc = fmaf(l[r][c2], x[c2][c], sacc);
+        x[r][c] = -sacc / l[r][r];
+      }
+    }
+    // bulk = X22[i, :] C21 for the rows below the block
+    float res[4][4];       // up to 4 rows per slot (D <= 4 * nslots)
     int cnt = 0;
-    for (int i0 = j + 1; i0 < D; i0 += nslots, ++cnt) {
+    for (int i0 = r0; i0 < D; i0 += nslots, ++cnt) {
       const int i = i0 + slot;
-      float s0 = 0.f, s1 = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       if (i < D) {
         const float* ri = A + tri(i);
-        int m = j + 1 + sub;
-        for (; m + QUAD <= i; m += 2 * QUAD) {
-          s0 = fmaf(ri[m], A[tri(m) + j], s0);
-          s1 = fmaf(ri[m + QUAD], A[tri(m + QUAD) + j], s1);
+        int idx = tri(r0 + sub) + j0;                 // C[m][j0] for m = r0 + sub
+        for (int m = r0 + sub; m <= i; m += QUAD) {
+          const float a = ri[m];
+          const float* cm = A + idx;
+          s0 = fmaf(a, cm[0], s0);
+          if (nb > 1) s1 = fmaf(a, cm[1], s1);
+          if (nb > 2) s2 = fmaf(a, cm[2], s2);
+          if (nb > 3) s3 = fmaf(a, cm[3], s3);
+          idx += QUAD * m + (QUAD * (QUAD + 1)) / 2;   // tri(m + 4) - tri(m) = 4 m + 10
         }
-        if (m <= i) s0 = fmaf(ri[m], A[tri(m) + j], s0);
       }
-      sreg[cnt] = -quad_sum(s0 + s1) * xjj;
+      s0 = quad_sum(s0); s1 = quad_sum(s1); s2 = quad_sum(s2); s3 = quad_sum(s3);
+      // X21 row = -bulk X11
+      res[cnt][0] = -(s0 * x[0][0] + s1 * x[1][0] + s2 * x[2][0] + s3 * x[3][0]);
+      res[cnt][1] = -(s1 * x[1][1] + s2 * x[2][1] + s3 * x[3][1]);
+      res[cnt][2] = -(s2 * x[2][2] + s3 * x[3][2]);
+      res[cnt][3] = -(s3 * x[3][3]);
     }
     __syncthreads();
     cnt = 0;
-    for (int i0 = j + 1; i0 < D; i0 += nslots, ++cnt) {
+    for (int i0 = r0; i0 < D; i0 += nslots, ++cnt) {
       const int i = i0 + slot;
-      if (i < D && sub == 0) A[tri(i) + j] = sreg[cnt];
+      if (i < D && sub == 0) {
+        float* ri = A + tri(i) + j0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nb) ri[c] = res[cnt][c];
+      }
     }
-    if (tid == 0) A[tri(j) + j] = xjj;
+    if (tid == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nb) {
+          float* rc = A + tri(j0 + c) + j0;
+#pragma unroll
+          for (int c2 = 0; c2 <= c; ++c2) rc[c2] = x[c][c2];
+        }
+    }
     __syncthreads();
   }
 }
@@ -223,7 +333,7 @@ update_full_kernel(int mode, const float* __restrict__ means, const float* __res
   extern __shared__ float smem[];
   __shared__ float red[33];
   const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const long long npk = tri(D);
+  const long long npk = (long long)tri(D);
   float* hrev = smem;            // [D]
   float* v = smem + D;           // [D]
   float* u = smem + 2 * D;       // [D]
