@@ -29,6 +29,10 @@ int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float 
                  long long strideC, cudaStream_t st);
 int launch_stein_stats_full(const float* X, int N, int D, const float* means, const float* W,
                             const uint8_t* active, const float* G, int K, float* M, cudaStream_t st);
+int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                     long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                     long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
+size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
 
 // =================================================================================================
 // prepare_full: one CTA per component, fp64 arithmetic, thread-per-column forward substitution.
@@ -344,6 +348,30 @@ importance_weights_ext_kernel(const float* __restrict__ lq, const float* __restr
 // =================================================================================================
 // Stein finalisation and diagonal Stein
 // =================================================================================================
+// gneg[k][d] = - sum_n W[k][n] G[n][d], skipping the 128-sample blocks that carry no weight
+__global__ void __launch_bounds__(256)
+stein_gsum_kernel(const float* __restrict__ W, const uint8_t* __restrict__ active, const float* __restrict__ G, int N,
+                  int D, float* __restrict__ gneg) {
+  const int k = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Wk = W + (long long)k * N;
+  const int nblk = ceil_div(N, 128);
+  float a0 = 0.f, a1 = 0.f;
+  for (int b = 0; b < nblk; ++b) {
+    if (active != nullptr && active[(long long)k * nblk + b] == 0) continue;
+    const int n1 = min(N, (b + 1) * 128);
+    if (d < D) {
+      int n = b * 128;
+      for (; n + 1 < n1; n += 2) {
+        a0 = fmaf(__ldg(Wk + n), G[(long long)n * D + d], a0);
+        a1 = fmaf(__ldg(Wk + n + 1), G[(long long)(n + 1) * D + d], a1);
+      }
+      if (n < n1) a0 = fmaf(__ldg(Wk + n), G[(long long)n * D + d], a0);
+    }
+  }
+  if (d < D) gneg[(long long)k * D + d] = -(a0 + a1);
+}
+
 __global__ void stein_finalize_kernel(const float* __restrict__ T, int D, int symmetrize, float* __restrict__ H) {
   const int k = blockIdx.y;
   const float* Tk = T + (long long)k * D * D;
@@ -640,7 +668,8 @@ extern "C" int gvi_importance_weights_ext_f32(const float* lq, const float* bg, 
 }
 
 extern "C" size_t gvi_stein_full_workspace(int K, int D) {
-  return (size_t)2 * (K > 0 ? K : 0) * D * D * sizeof(float);
+  if (K <= 0) return 0;
+  return ((size_t)2 * K * D * D + tc_gemm_workspace_floats(K, D, D, D)) * sizeof(float);
 }
 extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec,
                                   const float* W, const uint8_t* active, const float* G, int K, int symmetrize,
@@ -658,12 +687,14 @@ extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* mea
   float* T = M + (size_t)K * D * D;
   int rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
   if (rc) return rc;
-  // gneg = -W G   ([K x N] [N x D])
-  rc = launch_bgemm(0, 0, 1, K, D, N, -1.f, W, N, 0, G, D, 0, gneg, D, 0, st);
-  if (rc) return rc;
+  {
+    dim3 gg(ceil_div(D, 256), K);
+    stein_gsum_kernel<<<gg, 256, 0, st>>>(W, active, G, N, D, gneg);
+    if ((rc = check_launch("stein_gsum_kernel"))) return rc;
+  }
   // T_k = P_k M_k
-  rc = launch_bgemm(0, 0, K, D, D, D, 1.f, prec, D, (long long)D * D, M, D, (long long)D * D, T, D,
-                    (long long)D * D, st);
+  rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, prec, D, (long long)D * D, M, D, (long long)D * D, T, D,
+                        (long long)D * D, T + (size_t)K * D * D, tc_gemm_workspace_floats(K, D, D, D), st);
   if (rc) return rc;
   dim3 grid(min(ceil_div(D * D, 256), 1024), K);
   stein_finalize_kernel<<<grid, 256, 0, st>>>(T, D, symmetrize, Hneg);

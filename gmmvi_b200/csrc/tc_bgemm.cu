@@ -1,0 +1,345 @@
+// Batched GEMM on the tcgen05 tensor cores in 3xTF32 split precision (fp32-grade results):
+//     C[b] (M x N) = alpha * A[b] (M x K) * B[b]^T (N x K),   operands pre-split into TF32 hi / lo parts.
+// Used for the D x D x D products of the component update (B = L^T R L), the Stein finalisation (P M), the
+// precision matrices (Linv^T Linv) and the MORE un-whitening; the reference issues these as tf.matmul on
+// [D, D] tensors inside per-component Python loops (ng_based_component_updater.py:107-112, 176-180, 458;
+// ng_estimator.py:183-186; least_squares.py:184).
+//
+// Persistent, warp-specialised: warp 0 = TMA producer (A hi/lo 128 x 32, B hi/lo NT x 32 per k-block, 128B swizzle,
+// 2-stage ring), warp 1 = MMA issuer (3 tcgen05.mma per 8-wide k-step, fp32 accumulators in TMEM, double buffered),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> alpha -> global).
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace gvi {
+namespace tcg {
+using namespace tcx;
+
+constexpr int TILE_M = 128;
+constexpr int KBLK = 32;
+constexpr int STAGES = 2;
+constexpr int THREADS = 256;
+constexpr int A_BYTES = TILE_M * 128;
+constexpr int B_BYTES = 256 * 128;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;
+
+struct Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, int batch, int M,
+                int N, int Kd, float alpha, float* __restrict__ C, int ldc, long long strideC) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt_n = ceil_div(M, TILE_M), nt_n = ceil_div(N, ACC_COLS);
+  const long long total = (long long)batch * mt_n * nt_n;
+  const int nkb = ceil_div(Kd, KBLK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  auto decode = [&](long long w, int& b, int& m0, int& n0, int& nt) {
+    b = (int)(w / (mt_n * nt_n));
+    const int r = (int)(w % (mt_n * nt_n));
+    m0 = (r / nt_n) * TILE_M;
+    n0 = (r % nt_n) * ACC_COLS;
+    nt = min(ACC_COLS, (N - n0 + 15) & ~15);      // MMA N: multiple of 16, rows beyond N are zero-filled by TMA
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        int b, m0, n0, nt;
+        decode(w, b, m0, n0, nt);
+        const int nrows_b = (nt + 31) & ~31;     // TMA boxes are 32 rows high
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&bars->full[s], 2u * A_BYTES + 2u * nrows_b * 128u);
+          tma_load_3d(st, &mapAh, &bars->full[s], kb * KBLK, m0, b);
+          tma_load_3d(st + A_BYTES, &mapAl, &bars->full[s], kb * KBLK, m0, b);
+          for (int r = 0; r < nrows_b; r += 32) {
+            tma_load_3d(st + 2 * A_BYTES + r * 128, &mapBh, &bars->full[s], kb * KBLK, n0 + r, b);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES + r * 128, &mapBl, &bars->full[s], kb * KBLK, n0 + r, b);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      long long it = 0;
+      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        int b, m0, n0, nt;
+        decode(w, b, m0, n0, nt);
+        const int buf = (int)(it & 1);
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&bars->acc_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(nt);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KBLK / 8; ++ks) {
+            const uint64_t a_hi = make_desc(st + ks * 32);
+            const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
+            const uint64_t b_hi = make_desc(st + 2 * A_BYTES + ks * 32);
+            const uint64_t b_lo = make_desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(&bars->empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&bars->acc_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    long long it = 0;
+    const bool vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && (strideC % 4 == 0);
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      int b, m0, n0, nt;
+      decode(w, b, m0, n0, nt);
+      const int buf = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&bars->acc_full[buf], use & 1);
+      tc_fence_after();
+      const int m = m0 + 32 * q + lane;
+      float* crow = C + b * strideC + (long long)m * ldc + n0;
+      for (int c = 0; c * 32 < nt; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + c * 32), v);
+        tmem_ld_wait();
+        if (m < M) {
+          const int ncol = min(32, N - (n0 + c * 32));
+          if (vec && ncol == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(crow + c * 32 + i) =
+                  make_float4(alpha * __uint_as_float(v[i]), alpha * __uint_as_float(v[i + 1]),
+                              alpha * __uint_as_float(v[i + 2]), alpha * __uint_as_float(v[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol) crow[c * 32 + i] = alpha * __uint_as_float(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// in [b][R][C] (row pitch ld) -> hi / lo [b][C][R]  (transposed split)
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ in, int R, int Cc, int ld, long long stride_in,
+                                            float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* src = in + b * stride_in;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? src[(long long)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  const long long ob = (long long)b * R * Cc;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) {
+      const float x = tile[threadIdx.x][i];
+      const float h = to_tf32(x);
+      hi[ob + (long long)c * R + r] = h;
+      lo[ob + (long long)c * R + r] = to_tf32(x - h);
+    }
+  }
+}
+
+__global__ void split_tf32_strided_kernel(const float* __restrict__ in, int R, int Cc, int ld, long long stride_in,
+                                          float* __restrict__ hi, float* __restrict__ lo) {
+  const int b = blockIdx.y;
+  const float* src = in + b * stride_in;
+  const long long ob = (long long)b * R * Cc;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)R * Cc;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Cc), c = (int)(e % Cc);
+    const float x = src[(long long)r * ld + c];
+    const float h = to_tf32(x);
+    hi[ob + e] = h;
+    lo[ob + e] = to_tf32(x - h);
+  }
+}
+
+static int num_sms_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace tcg
+
+bool tc_gemm_supported(int M, int N, int Kd) { return M > 0 && N > 0 && Kd >= 4 && (Kd % 4 == 0); }
+
+// Split (optionally transposing) a batch of row-major matrices into TF32 hi / lo parts, densely packed.
+//   trans == 0: out[b][R][C] = in[b][R][C];  trans == 1: out[b][C][R] = in[b][R][C]^T
+int launch_split_tf32(const float* in, int batch, int R, int Cc, int ld, long long stride_in, int trans, float* hi,
+                      float* lo, cudaStream_t st) {
+  if (batch <= 0 || R <= 0 || Cc <= 0) return GVI_OK;
+  if (trans) {
+    dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), batch), block(32, 8);
+    tcg::split_tf32_transpose_kernel<<<grid, block, 0, st>>>(in, R, Cc, ld, stride_in, hi, lo);
+    return check_launch("split_tf32_transpose_kernel");
+  }
+  dim3 grid((unsigned)min((long long)1024, ((long long)R * Cc + 255) / 256), batch);
+  tcg::split_tf32_strided_kernel<<<grid, 256, 0, st>>>(in, R, Cc, ld, stride_in, hi, lo);
+  return check_launch("split_tf32_strided_kernel");
+}
+
+// C[b] = alpha * A[b] B[b]^T with A [b][M][Kd], B [b][N][Kd] densely packed hi / lo operands
+int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
+                    const float* Bl, float* C, int ldc, long long strideC, cudaStream_t st) {
+  if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
+  if (!tc_gemm_supported(M, N, Kd)) {
+    set_last_error("tc_bgemm: unsupported shape M=%d N=%d K=%d", M, N, Kd);
+    return GVI_ERR_UNSUPPORTED;
+  }
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = tcx::make_map_3d(&mAh, Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+  if ((rc = tcx::make_map_3d(&mAl, Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+  if ((rc = tcx::make_map_3d(&mBh, Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+  if ((rc = tcx::make_map_3d(&mBl, Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tcg::tc_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("tc_bgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return GVI_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const long long total = (long long)batch * ceil_div(M, tcg::TILE_M) * ceil_div(N, tcg::ACC_COLS);
+  const int grid = (int)min((long long)tcg::num_sms_cached(), total);
+  tcg::tc_bgemm_kernel<<<grid, tcg::THREADS, tcg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, batch, M, N, Kd, alpha, C, ldc,
+                                                                   strideC);
+  return check_launch("tc_bgemm_kernel");
+}
+
+// C[b] = alpha * opA(A[b]) opB(B[b]) for row-major fp32 inputs, like launch_bgemm; ws holds the split operands:
+// 2 * batch * (M*Kd + N*Kd) floats.
+size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd) {
+  return (size_t)2 * batch * ((size_t)M * Kd + (size_t)N * Kd) + 256;
+}
+int launch_tc_gemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                   long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                   long long strideC, float* ws, cudaStream_t st) {
+  float* Ah = ws;
+  float* Al = Ah + (size_t)batch * M * Kd;
+  float* Bh = Al + (size_t)batch * M * Kd;
+  float* Bl = Bh + (size_t)batch * N * Kd;
+  int rc;
+  // A operand must be [M][Kd]: transA == 0 -> A is [M][Kd] already; transA == 1 -> A is [Kd][M], transpose it
+  if (transA) rc = launch_split_tf32(A, batch, Kd, M, lda, strideA, 1, Ah, Al, st);
+  else        rc = launch_split_tf32(A, batch, M, Kd, lda, strideA, 0, Ah, Al, st);
+  if (rc) return rc;
+  // B operand must be [N][Kd]: transB == 0 -> B is [Kd][N], transpose it; transB == 1 -> B is [N][Kd] already
+  if (transB) rc = launch_split_tf32(B, batch, N, Kd, ldb, strideB, 0, Bh, Bl, st);
+  else        rc = launch_split_tf32(B, batch, Kd, N, ldb, strideB, 1, Bh, Bl, st);
+  if (rc) return rc;
+  return launch_tc_bgemm(batch, M, N, Kd, alpha, Ah, Al, Bh, Bl, C, ldc, strideC, st);
+}
+
+int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                 long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                 long long strideC, cudaStream_t st);
+
+static bool tc_gemm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GMMVI_B200_TC_GEMM");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Tensor-core GEMM when the shape allows it and the caller provided split workspace, else the SIMT tile engine.
+int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                     long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                     long long strideC, float* ws, size_t ws_floats, cudaStream_t st) {
+  if (tc_gemm_enabled() && ws != nullptr && tc_gemm_supported(M, N, Kd) && M >= 64 && N >= 32 &&
+      ws_floats >= tc_gemm_workspace_floats(batch, M, N, Kd) && (reinterpret_cast<uintptr_t>(ws) % 16 == 0))
+    return launch_tc_gemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, ws,
+                          st);
+  return launch_bgemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, st);
+}
+
+}  // namespace gvi
+
+using namespace gvi;
+
+extern "C" int gvi_tc_bgemm_supported(int M, int N, int Kd) { return tc_gemm_supported(M, N, Kd) ? 1 : 0; }
+
+extern "C" size_t gvi_tc_bgemm_workspace(int batch, int M, int N, int Kd) {
+  return tc_gemm_workspace_floats(batch, M, N, Kd) * sizeof(float);
+}
+
+extern "C" int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A,
+                                int lda, long long strideA, const float* B, int ldb, long long strideB, float* C,
+                                int ldc, long long strideC, void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(batch >= 0 && M >= 0 && N >= 0 && Kd >= 0, "gvi_tc_bgemm_f32: bad sizes");
+  if (batch == 0 || M == 0 || N == 0) return GVI_OK;
+  GVI_REQUIRE(A && B && C && ws, "gvi_tc_bgemm_f32: null pointer");
+  if (!tc_gemm_supported(M, N, Kd)) {
+    set_last_error("gvi_tc_bgemm_f32: unsupported shape (K must be a positive multiple of 4)");
+    return GVI_ERR_UNSUPPORTED;
+  }
+  if (ws_bytes < gvi_tc_bgemm_workspace(batch, M, N, Kd)) {
+    set_last_error("gvi_tc_bgemm_f32: workspace %zu < %zu", ws_bytes, gvi_tc_bgemm_workspace(batch, M, N, Kd));
+    return GVI_ERR_WORKSPACE;
+  }
+  return launch_tc_gemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
+                        (float*)ws, (cudaStream_t)stream);
+}

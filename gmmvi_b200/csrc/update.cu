@@ -24,6 +24,11 @@ int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float 
                  long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                  long long strideC, cudaStream_t st);
 
+int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                     long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                     long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
+size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
+
 constexpr int UPD_THREADS = 1024;
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -553,8 +558,9 @@ using namespace gvi;
 
 extern "C" size_t gvi_update_full_workspace(int K, int D) {
   if (K <= 0) return 0;
-  size_t f = (size_t)4 * K * D * D + (size_t)K * D;
+  size_t f = (size_t)4 * K * D * D + (size_t)K * D + 64;
   if (upd_smem_bytes(D) > kMaxDynSmem) f += (size_t)K * D * (D + 1) / 2;
+  f = (f + 63) / 64 * 64 + tc_gemm_workspace_floats(K, D, D, D);
   return f * sizeof(float);
 }
 
@@ -583,17 +589,21 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
   float* B2 = Bm + (size_t)K * DD;
   float* hv = B2 + (size_t)K * DD;
   float* gscr = hv + (size_t)K * D;
+  size_t used = (size_t)4 * K * DD + (size_t)K * D + 64;
+  if (upd_smem_bytes(D) > kMaxDynSmem) used += (size_t)K * D * (D + 1) / 2;
+  float* tcws = (float*)ws + (used + 63) / 64 * 64;
+  const size_t tcws_floats = tc_gemm_workspace_floats(K, D, D, D);
   dim3 g1(min(ceil_div(D * D, 256), 1024), K);
   mirror_lower_kernel<<<g1, 256, 0, st>>>(Hneg, D, Rlow);
   int rc = check_launch("mirror_lower_kernel");
   if (rc) return rc;
   // T = Rlow L ;  B = L^T T
-  rc = launch_bgemm(0, 0, K, D, D, D, 1.f, Rlow, D, DD, chols, D, DD, T, D, DD, st);
+  rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, Rlow, D, DD, chols, D, DD, T, D, DD, tcws, tcws_floats, st);
   if (rc) return rc;
-  rc = launch_bgemm(1, 0, K, D, D, D, 1.f, chols, D, DD, T, D, DD, Bm, D, DD, st);
+  rc = launch_gemm_auto(1, 0, K, D, D, D, 1.f, chols, D, DD, T, D, DD, Bm, D, DD, tcws, tcws_floats, st);
   if (rc) return rc;
   if (mode == 2) {
-    rc = launch_bgemm(0, 0, K, D, D, D, 1.f, Bm, D, DD, Bm, D, DD, B2, D, DD, st);
+    rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, Bm, D, DD, Bm, D, DD, B2, D, DD, tcws, tcws_floats, st);
     if (rc) return rc;
   }
   update_vectors_kernel<<<K, 256, D * sizeof(float), st>>>(means, chols, Hneg, gneg, D, mode != 2, hv);

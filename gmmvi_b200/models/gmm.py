@@ -59,7 +59,14 @@ class GMM:
         """(linv, prec, cst): inverse Cholesky factors, precisions and log-normalisers of the current
         full-covariance components (one `gvi_prepare_full_f32` per parameter change)."""
         if self._prepared is None or self._prepared[0] != self._version:
-            linv, prec, cst, _ = ops.prepare_full(self._chol_cov, want_prec=True)
+            rng_ = self.shard.component_range(self.num_components) if self.shard is not None else None
+            if rng_ is None:
+                linv, prec, cst, _ = ops.prepare_full(self._chol_cov, want_prec=True)
+            else:       # components sharded over the ranks, derived operands all-gathered
+                a, b = rng_
+                K = self.num_components
+                parts = ops.prepare_full(self._chol_cov[a:b].contiguous(), want_prec=True)[:3]
+                linv, prec, cst = (self.shard.all_gather_rows(p, K) for p in parts)
             self._prepared = (self._version, linv, prec, cst)
         return self._prepared[1:]
 

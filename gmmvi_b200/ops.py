@@ -347,8 +347,9 @@ def sample_components(diagonal: bool, eps, offsets, means, chols, max_rows_per_c
     return X, mapping
 
 
-def bgemm(A, B, transA=False, transB=False, alpha=1.0):
-    """Batched C[b] = alpha * op(A[b]) op(B[b]) for 3-D tensors (or 2-D, batch 1)."""
+def bgemm(A, B, transA=False, transB=False, alpha=1.0, tensor_cores=None):
+    """Batched C[b] = alpha * op(A[b]) op(B[b]) for 3-D tensors (or 2-D, batch 1).  tensor_cores=True forces the
+    tcgen05 3xTF32 kernel, False the SIMT engine, None picks the tensor cores when the shape allows."""
     A, B = _chk(A, "A"), _chk(B, "B")
     squeeze = A.dim() == 2
     if squeeze:
@@ -357,7 +358,17 @@ def bgemm(A, B, transA=False, transB=False, alpha=1.0):
     M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
     N = B.shape[1] if transB else B.shape[2]
     Cc = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
-    _call("gvi_bgemm_f32", int(transA), int(transB), batch, M, N, Kd, float(alpha), A.data_ptr(), A.shape[2],
-          A.shape[1] * A.shape[2], B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], Cc.data_ptr(), N, M * N,
-          _stream())
+    use_tc = tensor_cores
+    if use_tc is None:
+        use_tc = USE_TENSOR_CORES and M >= 64 and N >= 32 and bool(_lib.lib().gvi_tc_bgemm_supported(M, N, Kd))
+    if use_tc:
+        nbytes = _lib.lib().gvi_tc_bgemm_workspace(batch, M, N, Kd)
+        ws = torch.empty(nbytes // 4 + 4, device=A.device, dtype=torch.float32)
+        _call("gvi_tc_bgemm_f32", int(transA), int(transB), batch, M, N, Kd, float(alpha), A.data_ptr(), A.shape[2],
+              A.shape[1] * A.shape[2], B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], Cc.data_ptr(), N, M * N,
+              ws.data_ptr(), nbytes, _stream(), kernels=3)
+    else:
+        _call("gvi_bgemm_f32", int(transA), int(transB), batch, M, N, Kd, float(alpha), A.data_ptr(), A.shape[2],
+              A.shape[1] * A.shape[2], B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], Cc.data_ptr(), N, M * N,
+              _stream())
     return Cc[0] if squeeze else Cc

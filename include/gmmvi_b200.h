@@ -150,6 +150,15 @@ int gvi_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float
                   long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                   long long strideC, void* stream);
 
+/* The same product on the tcgen05 tensor cores in 3xTF32 split precision (fp32-grade result); `ws` holds the
+ * TF32 hi / lo copies of both operands.  The estimator / updater entry points use it internally when the shape
+ * allows (K % 4 == 0) and fall back to the SIMT engine otherwise. */
+int gvi_tc_bgemm_supported(int M, int N, int Kd);
+size_t gvi_tc_bgemm_workspace(int batch, int M, int N, int Kd);
+int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                     long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                     long long strideC, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

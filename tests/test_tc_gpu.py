@@ -44,3 +44,17 @@ def test_tc_logdens_many_tiles_and_components():
     # deterministic: same bits on a second launch
     a2 = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=True)
     assert torch.equal(a, a2)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("b,M,N,Kd", [(3, 256, 256, 256), (2, 70, 45, 132), (1, 300, 520, 64), (5, 128, 16, 36)])
+def test_tc_bgemm(ta, tb, b, M, N, Kd):
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(70 + M)
+    A = rng.standard_normal((b, Kd, M) if ta else (b, M, Kd)).astype(np.float32)
+    B = rng.standard_normal((b, N, Kd) if tb else (b, Kd, N)).astype(np.float32)
+    ref = (A.transpose(0, 2, 1) if ta else A).astype(np.float64) @ (B.transpose(0, 2, 1) if tb else B).astype(np.float64)
+    out = ops.bgemm(dev(A), dev(B), ta, tb, 0.5, tensor_cores=True)
+    simt = ops.bgemm(dev(A), dev(B), ta, tb, 0.5, tensor_cores=False)
+    assert rel_err(simt.cpu().numpy(), 0.5 * ref) < 1e-5
+    assert rel_err(out.cpu().numpy(), 0.5 * ref) < 5e-6, rel_err(out.cpu().numpy(), 0.5 * ref)
