@@ -26,6 +26,12 @@ _SIGNATURES = {
     "gvi_split_tf32_f32": (C.c_int, [c_f, C.c_longlong, c_f, c_f, c_vp]),
     "gvi_logdens_full_tc_supported": (C.c_int, [C.c_int]),
     "gvi_logdens_full_tc_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),
+    "gvi_logdens_full_h16_supported": (C.c_int, [C.c_int]),
+    "gvi_h16_padded_dim": (C.c_int, [C.c_int]),
+    "gvi_split_h16_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_vp, c_vp, c_f, c_vp]),
+    "gvi_group_absmax_f32": (C.c_int, [c_f, C.c_longlong, C.c_int, C.c_int, c_f, c_vp]),
+    "gvi_logdens_full_h16_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_vp, c_vp, c_f, c_f, C.c_int, c_f,
+                                           c_vp]),
     "gvi_logdens_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, C.c_int, c_f, c_vp]),
     "gvi_mixture_lse_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_vp]),
     "gvi_mixture_grad_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),

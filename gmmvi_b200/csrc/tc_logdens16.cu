@@ -1,0 +1,460 @@
+// Full-covariance component log densities, tcgen05 kind::f16 in "2 x fp16" split precision with the
+// component's inverse Cholesky factor RESIDENT in shared memory (sm_100a only).
+//
+//   lq[k, n] = cst[k] - 1/2 | Linv_k (x_n - mu_k) |^2            (models/full_cov_gmm.py:56-62)
+//
+// Why a second tensor-core kernel next to tc_logdens.cu (3xTF32): that kernel streams both operands from L2
+// for every (component, 128-sample tile) work item -- 423 KB per item -- and ncu shows it limited by the
+// L2 -> SM path and by the TF32 rate at the same time.  fp16 operands are half as wide and run at twice the
+// TF32 rate, which (a) halves the tensor time and (b) lets the lower-triangular k-blocks of BOTH split
+// halves of Linv_k (160 KB at D = 256) stay in shared memory while a CTA streams sample tiles past them, so
+// the only per-item L2 traffic left is the 128 KB sample tile.
+//
+// Precision.  x = hi + lo with hi = rn_f16(x s), lo = rn_f16(x s - hi): 22 significand bits, the same as the
+// TF32 split, PROVIDED nothing overflows or underflows fp16's 5-bit exponent.  Both operands are therefore
+// scaled by exact powers of two: the A tile (x_n - mu_k, 128 rows) by s_tk chosen from the bound
+// max_n |x_n|_inf + |mu_k|_inf so that |a| < 2^14, the factor Linv_k by t_k chosen from max |Linv_k| likewise; the epilogue multiplies the
+// sum of squares by (s t)^-2.  An element 2^-17 of its row's bound still keeps 22 bits; smaller ones lose
+// bits gradually (absolute error 2^-39 of the bound), which is below fp32's own rounding of the dot product.
+// The products hi*hi, lo*hi, hi*lo are exact in the fp32 accumulator (11 x 11 bits).
+//
+// Triangular structure.  K-step jb (16 columns j of Linv) only feeds output columns i >= 16 jb, so the MMA
+// of that step runs with N = Dp - 16 jb: 53 % of the dense MMA work at D = 256.
+//
+// Warp roles (512 threads, one persistent CTA per SM, each CTA owns a CONTIGUOUS range of the k-major work list):
+//   warp 0      TMA: loads the hi / lo k-blocks of Linv_k (padded fp16 [K, Dp, Dp]) when the component changes
+//   warp 1      MMA issuer (one thread): 3 tcgen05.mma per 16-column step
+//   warp 2      TMEM allocator (2 x 256 fp32 columns, double buffered accumulators)
+//   warps 4-7   epilogue: tcgen05.ld, row sums of squares, un-scaling, lq store
+//   warps 8-15  A producers: x - mu_k in fp32 (cancellation happens BEFORE the split), scale, split into fp16
+//               hi / lo, write the K-major SWIZZLE_128B operand; global loads run one stage ahead
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace gvi {
+namespace h16 {
+using namespace tcx;
+
+constexpr int TILE_M = 128;
+constexpr int KB = 64;                    // fp16 elements per 128-byte swizzle row = columns per stage
+constexpr int STAGES = 2;
+constexpr int THREADS = 512;
+constexpr int A_BYTES = TILE_M * 128;     // 16 KB per hi / lo
+constexpr int STAGE_BYTES = 2 * A_BYTES;  // 32 KB
+constexpr int ACC_COLS = 256;
+constexpr int TMEM_COLS = 512;
+
+__host__ __device__ inline int padded_dim(int D) { return (D + KB - 1) / KB * KB; }
+// rows of the packed lower-triangular block storage: block kb keeps rows 64 kb .. Dp-1
+__host__ __device__ inline int block_row_offset(int Dp, int kb) { return kb * Dp - KB * (kb * (kb - 1) / 2); }
+__host__ __device__ inline int packed_rows(int Dp) { return block_row_offset(Dp, Dp / KB); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// Power of two s with b * s < 2^14 for the non-negative bound b (exponent clamped to +-40).
+__host__ __device__ __forceinline__ float pow2_scale(float b) {
+#ifdef __CUDA_ARCH__
+  const int e = (__float_as_int(b) >> 23) & 0xff;
+#else
+  union { float f; int i; } u; u.f = b;
+  const int e = (u.i >> 23) & 0xff;
+#endif
+  int se = 127 + 13 - (e - 127);
+  se = se < 87 ? 87 : (se > 167 ? 167 : se);
+#ifdef __CUDA_ARCH__
+  return __int_as_float(se << 23);
+#else
+  union { float f; int i; } v; v.i = se << 23;
+  return v.f;
+#endif
+}
+
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+struct Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t b_full;
+  uint64_t b_free;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                   const float* __restrict__ X, const float* __restrict__ tileinf, int N, int D, int Dp,
+                   const float* __restrict__ means, const float* __restrict__ minf,
+                   const float* __restrict__ tmax, const float* __restrict__ cst, int K, float* __restrict__ lq) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int brows = packed_rows(Dp);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + (size_t)brows * 128;
+  uint8_t* a_base = smem + (size_t)brows * 256;
+  Barriers* bars = reinterpret_cast<Barriers*>(a_base + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ceil_div(N, TILE_M);
+  const long long total = (long long)T * K;
+  const int nkb = Dp / KB;
+  const long long w_begin = total * blockIdx.x / gridDim.x;
+  const long long w_end = total * (blockIdx.x + 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 8);          // one elected arrive per producer warp
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 4);     // one elected arrive per epilogue warp
+    }
+    mbar_init(&bars->b_full, 1);
+    mbar_init(&bars->b_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    reg_dec<64>();
+    if (warp == 0) {
+      // ---------------- TMA: Linv_k (hi, lo) becomes resident whenever the component changes ----------------
+      if (lane == 0 && w_end > w_begin) {
+        const int k_first = (int)(w_begin / T), k_last = (int)((w_end - 1) / T);
+        int nload = 0;
+        for (int k = k_first; k <= k_last; ++k, ++nload) {
+          if (nload > 0) mbar_wait(&bars->b_free, (uint32_t)((nload - 1) & 1));
+          mbar_arrive_expect_tx(&bars->b_full, 2u * (uint32_t)brows * 128u);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int row0 = block_row_offset(Dp, kb);
+            for (int r = 0; r < Dp - kb * KB; r += 64) {
+              tma_load_2d(b_hi + (size_t)(row0 + r) * 128, &map_hi, &bars->b_full, kb * KB, k * Dp + kb * KB + r);
+              tma_load_2d(b_lo + (size_t)(row0 + r) * 128, &map_lo, &bars->b_full, kb * KB, k * Dp + kb * KB + r);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        long long it = 0;
+        int cur_k = -1, nload = 0;
+        const uint32_t bhi_addr = smem_u32(b_hi), blo_addr = smem_u32(b_lo);
+        for (long long w = w_begin; w < w_end; ++w, ++it) {
+          const int k = (int)(w / T);
+          if (k != cur_k) {
+            mbar_wait(&bars->b_full, (uint32_t)(nload & 1));
+            ++nload;
+            cur_k = k;
+          }
+          const int buf = (int)(it & 1);
+          const uint32_t use = (uint32_t)(it >> 1);
+          mbar_wait(&bars->acc_empty[buf], (use & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&bars->full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(a_base + s * STAGE_BYTES);
+            const uint32_t boff = (uint32_t)block_row_offset(Dp, kb) * 128u;
+#pragma unroll
+            for (int ks = 0; ks < KB / 16; ++ks) {
+              const int j0 = kb * KB + ks * 16;
+              const uint32_t idesc = make_idesc_f16(Dp - j0);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + j0);
+              const uint64_t a_hi = make_desc(st + ks * 32);
+              const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
+              const uint64_t bd_hi = make_desc(bhi_addr + boff + (uint32_t)(ks * 16) * 128u + ks * 32);
+              const uint64_t bd_lo = make_desc(blo_addr + boff + (uint32_t)(ks * 16) * 128u + ks * 32);
+              umma_f16(d_tmem, a_hi, bd_hi, idesc, j0 != 0 ? 1u : 0u);
+              umma_f16(d_tmem, a_lo, bd_hi, idesc, 1u);
+              umma_f16(d_tmem, a_hi, bd_lo, idesc, 1u);
+            }
+            umma_commit(&bars->empty[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit(&bars->acc_full[buf]);
+          // last item of this component in my range: the resident factor may be overwritten once these MMAs retire
+          if (w + 1 < w_end && (int)((w + 1) / T) != k) umma_commit(&bars->b_free);
+        }
+      }
+    }
+  } else if (wg == 1) {
+    reg_dec<80>();
+    // ---------------- epilogue: row sums of squares ----------------
+    const int q = warp - 4;
+    long long it = 0;
+    const int ncol32 = Dp / 32;
+    for (long long w = w_begin; w < w_end; ++w, ++it) {
+      const int k = (int)(w / T), t = (int)(w % T);
+      const int n = t * TILE_M + 32 * q + lane;
+      // operands of the un-scaling factor 1 / (s t): the same inputs as the producers use
+      const float xi = __ldg(tileinf + t), mi = __ldg(minf + k), tm = __ldg(tmax + k), c = __ldg(cst + k);
+      const int buf = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&bars->acc_full[buf], use & 1);
+      tc_fence_after();
+      float s0 = 0.f, s1 = 0.f;
+      for (int cb = 0; cb < ncol32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + cb * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
+          s0 = fmaf(a, a, s0);
+          s1 = fmaf(b, b, s1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+      const float f = 1.0f / (pow2_scale(xi + mi) * pow2_scale(tm));
+      if (n < N) lq[(long long)k * N + n] = c - 0.5f * (((s0 + s1) * f) * f);
+    }
+  } else {
+    reg_inc<184>();
+    // ---------------- A producers ----------------
+    // A warp-wide 128-bit load covers two complete 256-byte row segments (64 fp32 columns): lane l reads the float4
+    // c2 = l % 16 of row rsub + 16 q (rsub = 2 * producer warp + l / 16, q = 0..7) and writes its four fp16 hi / lo
+    // values as one 8-byte store each into the 128B-swizzled operand.
+    const int pw = warp - 8;
+    const int c2 = lane & 15;
+    const int rsub = 2 * pw + (lane >> 4);
+    const int swz = (((c2 >> 1) ^ (rsub & 7)) << 4) + ((c2 & 1) << 3);   // (row & 7) == (rsub & 7) for all my rows
+    const bool vec_ok = (D % 4 == 0);
+    int s = 0;
+    uint32_t ph = 0;
+    const long long nitems = (w_end - w_begin) * nkb;
+    long long w_ld = w_begin, w_st = w_begin;
+    int kb_ld = 0;
+    int k_ld = 0, t_ld = 0;
+    if (w_end > w_begin) {
+      k_ld = (int)(w_ld / T);
+      t_ld = (int)(w_ld % T);
+    }
+    struct Regs {
+      float4 x[8];
+      float4 m;
+      float xi, mi;
+    };
+    auto issue = [&](Regs& R) {
+      const int col = kb_ld * KB + c2 * 4;
+      const int nb = t_ld * TILE_M + rsub;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int n = nb + 16 * q;
+        R.x[q] = n < N ? load4(X + (long long)n * D + col, D - col, vec_ok) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      R.m = load4(means + (long long)k_ld * D + col, D - col, vec_ok);
+      R.xi = __ldg(tileinf + t_ld);
+      R.mi = __ldg(minf + k_ld);
+      if (++kb_ld == nkb) {
+        kb_ld = 0;
+        if (++w_ld < w_end) {
+          k_ld = (int)(w_ld / T);
+          t_ld = (int)(w_ld % T);
+        }
+      }
+    };
+    auto emit = [&](const Regs& R) {
+      const float sc = pow2_scale(R.xi + R.mi);
+      // (x - m) sc == fma(x, sc, -(m sc)) bit for bit: scaling by a power of two commutes with rounding
+      const float m0 = -R.m.x * sc, m1 = -R.m.y * sc, m2 = -R.m.z * sc, m3 = -R.m.w * sc;
+      mbar_wait(&bars->empty[s], ph ^ 1);
+      uint8_t* st = a_base + s * STAGE_BYTES + swz;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float v0 = fmaf(R.x[q].x, sc, m0), v1 = fmaf(R.x[q].y, sc, m1);
+        const float v2 = fmaf(R.x[q].z, sc, m2), v3 = fmaf(R.x[q].w, sc, m3);
+        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+        const int off = (rsub + 16 * q) * 128;
+        *reinterpret_cast<uint2*>(st + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(st + A_BYTES + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->full[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    };
+    // register ring of three stages: the global loads run two stages ahead of the conversion
+    Regs R0, R1, R2;
+    if (nitems > 0) issue(R0);
+    if (nitems > 1) issue(R1);
+    for (long long j = 0; j < nitems; j += 3) {
+      if (j + 2 < nitems) issue(R2);
+      emit(R0);
+      if (j + 1 < nitems) {
+        if (j + 3 < nitems) issue(R0);
+        emit(R1);
+      }
+      if (j + 2 < nitems) {
+        if (j + 4 < nitems) issue(R1);
+        emit(R2);
+      }
+    }
+    (void)w_st;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// One CTA per component: t = max |Linv_k| -> scale 2^e with |Linv| 2^e < 2^14; write zero-padded fp16 hi / lo.
+__global__ void __launch_bounds__(256)
+split_h16_kernel(const float* __restrict__ linv, int D, int Dp, __half* __restrict__ hi, __half* __restrict__ lo,
+                 float* __restrict__ tmax) {
+  __shared__ float scratch[34];
+  const int k = blockIdx.x;
+  const float* src = linv + (long long)k * D * D;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) m = fmaxf(m, fabsf(src[i]));
+  m = block_max(m, scratch);
+  if (threadIdx.x == 0) tmax[k] = m;
+  const float sc = pow2_scale(m);
+  __half* dh = hi + (long long)k * Dp * Dp;
+  __half* dl = lo + (long long)k * Dp * Dp;
+  for (int i = threadIdx.x; i < Dp * Dp; i += blockDim.x) {
+    const int r = i / Dp, cidx = i - r * Dp;
+    float v = 0.f;
+    if (r < D && cidx <= r) v = src[r * D + cidx] * sc;      // strictly-upper entries are structurally zero
+    const __half h = __float2half_rn(v);
+    dh[i] = h;
+    dl[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// out[g] = max |in[r, c]| over the rows r of group g (group consecutive rows: one contiguous chunk)
+__global__ void __launch_bounds__(256)
+group_absmax_kernel(const float* __restrict__ in, long long rows, int cols, int group, float* __restrict__ out) {
+  __shared__ float scratch[34];
+  const long long r0 = (long long)blockIdx.x * group;
+  const long long nr = min((long long)group, rows - r0);
+  const float* p = in + r0 * cols;
+  const long long n = nr * cols;
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(p + i)));
+  m = block_max(m, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = m;
+}
+
+static int make_map_h16(CUtensorMap* map, const void* base, int K, int Dp) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+    return GVI_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)K * (cuuint64_t)Dp};
+  cuuint64_t gstride[1] = {(cuuint64_t)Dp * 2};
+  cuuint32_t box[2] = {KB, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (fp16 Linv) failed with CUresult %d", (int)r);
+    return GVI_ERR_CUDA;
+  }
+  return GVI_OK;
+}
+
+static size_t smem_bytes(int Dp) {
+  return (size_t)packed_rows(Dp) * 256 + STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+}  // namespace h16
+}  // namespace gvi
+
+using namespace gvi;
+
+extern "C" int gvi_logdens_full_h16_supported(int D) { return (D >= 1 && D <= 256) ? 1 : 0; }
+extern "C" int gvi_h16_padded_dim(int D) { return h16::padded_dim(D); }
+
+extern "C" int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void* lo, float* tmax, void* stream) {
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_split_h16_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(linv && hi && lo && tmax, "gvi_split_h16_f32: null pointer");
+  h16::split_h16_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(linv, D, h16::padded_dim(D), (__half*)hi, (__half*)lo,
+                                                             tmax);
+  return check_launch("split_h16_kernel");
+}
+
+extern "C" int gvi_group_absmax_f32(const float* in, long long rows, int cols, int group, float* out, void* stream) {
+  GVI_REQUIRE(rows >= 0 && cols > 0 && group > 0, "gvi_group_absmax_f32: bad sizes");
+  if (rows == 0) return GVI_OK;
+  GVI_REQUIRE(in && out, "gvi_group_absmax_f32: null pointer");
+  const long long groups = (rows + group - 1) / group;
+  h16::group_absmax_kernel<<<(unsigned)groups, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, group, out);
+  return check_launch("group_absmax_kernel");
+}
+
+extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, int N, int D, const float* means,
+                                        const float* minf, const void* linv_hi, const void* linv_lo,
+                                        const float* tmax, const float* cst, int K, float* lq, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_logdens_full_h16_f32: bad sizes");
+  if (!gvi_logdens_full_h16_supported(D)) {
+    set_last_error("gvi_logdens_full_h16_f32: D=%d unsupported (needs 1 <= D <= 256)", D);
+    return GVI_ERR_UNSUPPORTED;
+  }
+  if (N == 0 || K == 0) return GVI_OK;
+  GVI_REQUIRE(X && tileinf && means && minf && linv_hi && linv_lo && tmax && cst && lq,
+              "gvi_logdens_full_h16_f32: null pointer");
+  GVI_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(means) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(linv_hi) % 16 == 0 && reinterpret_cast<uintptr_t>(linv_lo) % 16 == 0,
+              "gvi_logdens_full_h16_f32: operands must be 16-byte aligned");
+  const int Dp = h16::padded_dim(D);
+  GVI_REQUIRE((long long)K * Dp < 2147483647LL, "gvi_logdens_full_h16_f32: K*D too large");
+  CUtensorMap map_hi, map_lo;
+  int rc = h16::make_map_h16(&map_hi, linv_hi, K, Dp);
+  if (rc) return rc;
+  rc = h16::make_map_h16(&map_lo, linv_lo, K, Dp);
+  if (rc) return rc;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(h16::logdens_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)h16::smem_bytes(256));
+    if (e != cudaSuccess) {
+      set_last_error("gvi_logdens_full_h16_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      num_sms = 0;
+      return GVI_ERR_CUDA;
+    }
+  }
+  const long long total = (long long)ceil_div(N, h16::TILE_M) * K;
+  const int grid = (int)min((long long)num_sms, total);
+  h16::logdens_h16_kernel<<<grid, h16::THREADS, h16::smem_bytes(Dp), (cudaStream_t)stream>>>(
+      map_hi, map_lo, X, tileinf, N, D, Dp, means, minf, tmax, cst, K, lq);
+  return check_launch("logdens_h16_kernel");
+}

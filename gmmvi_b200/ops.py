@@ -30,10 +30,57 @@ USE_TENSOR_CORES = os.environ.get("GMMVI_B200_TC", "1") != "0"
 _SPLIT_CACHE = []       # [(key, linv, hi, lo)]
 
 
-def logdens_kernel_name(D: int = 256) -> str:
+# which tensor-core log-density kernel: "h16" (2 x fp16 split, resident factor), "tf32" (3xTF32, streamed)
+TC_KIND = os.environ.get("GMMVI_B200_TC_KIND", "h16")
+H16_MIN_DIM = 32        # below this the SIMT kernel wins (the fp16 operand is padded to 64 columns)
+
+
+def logdens_kernel_kind(D: int) -> str:
+    if USE_TENSOR_CORES and TC_KIND == "h16" and H16_MIN_DIM <= D <= 256:
+        return "h16"
     if USE_TENSOR_CORES and _lib.lib().gvi_logdens_full_tc_supported(int(D)):
-        return "gvi::tc::tc_logdens_kernel (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM)"
-    return "gvi::logdens_full_kernel (SIMT fp32 tile engine)"
+        return "tf32"
+    return "simt"
+
+
+def logdens_kernel_name(D: int = 256) -> str:
+    return {"h16": "gvi::h16::logdens_h16_kernel (tcgen05 kind::f16, 2 x fp16 split, resident Linv, TMA + TMEM)",
+            "tf32": "gvi::tc::tc_logdens_kernel (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM)",
+            "simt": "gvi::logdens_full_kernel (SIMT fp32 tile engine)"}[logdens_kernel_kind(int(D))]
+
+
+_H16_CACHE = []         # [(key, linv, hi, lo, tmax)]
+_ABSMAX_CACHE = []      # [(key, tensor, out)]
+
+
+def split_h16(linv):
+    """Zero-padded, power-of-two scaled fp16 (hi, lo) copies of the inverse Cholesky factors + tmax[K]."""
+    key = (linv.data_ptr(), linv._version, tuple(linv.shape))
+    for k_, _, hi, lo, tmax in _H16_CACHE:
+        if k_ == key:
+            return hi, lo, tmax
+    K, D, _ = linv.shape
+    Dp = _lib.lib().gvi_h16_padded_dim(D)
+    hi = torch.empty((K, Dp, Dp), device=linv.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    tmax = torch.empty(K, device=linv.device, dtype=torch.float32)
+    _call("gvi_split_h16_f32", linv.data_ptr(), K, D, hi.data_ptr(), lo.data_ptr(), tmax.data_ptr(), _stream())
+    _H16_CACHE.insert(0, (key, linv, hi, lo, tmax))
+    del _H16_CACHE[3:]
+    return hi, lo, tmax
+
+
+def group_absmax(t, group=1):
+    """out[g] = max |t[r, c]| over the rows r in [g * group, (g + 1) * group) (cached per buffer version)."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), group)
+    for k_, _, out in _ABSMAX_CACHE:
+        if k_ == key:
+            return out
+    out = torch.empty((t.shape[0] + group - 1) // group, device=t.device, dtype=torch.float32)
+    _call("gvi_group_absmax_f32", t.data_ptr(), t.shape[0], t.shape[1], group, out.data_ptr(), _stream())
+    _ABSMAX_CACHE.insert(0, (key, t, out))
+    del _ABSMAX_CACHE[6:]
+    return out
 
 
 def split_tf32(linv):
@@ -110,8 +157,22 @@ def logdens_full(X, means, linv, cst, out=None, memo=True, tensor_cores=None):
             if k_ == key:
                 return lq_
     lq = out if out is not None else torch.empty((K, N), device=X.device, dtype=torch.float32)
-    use_tc = USE_TENSOR_CORES if tensor_cores is None else tensor_cores
-    if use_tc and N > 0 and K > 0 and _lib.lib().gvi_logdens_full_tc_supported(D):
+    if tensor_cores is None:
+        kind = logdens_kernel_kind(D)
+    elif tensor_cores is False:
+        kind = "simt"
+    else:
+        kind = tensor_cores if isinstance(tensor_cores, str) else logdens_kernel_kind(D)
+        if kind == "tf32" and not _lib.lib().gvi_logdens_full_tc_supported(D):
+            kind = "simt"
+    if N == 0 or K == 0:
+        kind = "simt"
+    if kind == "h16":
+        hi, lo, tmax = split_h16(linv)
+        _call("gvi_logdens_full_h16_f32", X.data_ptr(), group_absmax(X, 128).data_ptr(), N, D, means.data_ptr(),
+              group_absmax(means, 1).data_ptr(), hi.data_ptr(), lo.data_ptr(), tmax.data_ptr(), cst.data_ptr(), K,
+              lq.data_ptr(), _stream())
+    elif kind == "tf32":
         hi, lo = split_tf32(linv)
         _call("gvi_logdens_full_tc_f32", X.data_ptr(), N, D, means.data_ptr(), hi.data_ptr(), lo.data_ptr(),
               cst.data_ptr(), K, lq.data_ptr(), _stream())

@@ -54,6 +54,20 @@ int gvi_split_tf32_f32(const float* in, long long n, float* hi, float* lo, void*
 int gvi_logdens_full_tc_supported(int D);
 int gvi_logdens_full_tc_f32(const float* X, int N, int D, const float* means, const float* linv_hi,
                             const float* linv_lo, const float* cst, int K, float* lq, void* stream);
+/* Same result with tcgen05 kind::f16 in "2 x fp16" split precision (22 significand bits like the TF32 split, at
+ * twice the tensor rate) and the factor of the current component RESIDENT in shared memory, so that only the
+ * sample tile streams from L2.  Operands: gvi_split_h16_f32(linv) -> zero-padded fp16 hi / lo copies
+ * [K, Dp, Dp] (Dp = gvi_h16_padded_dim(D)), scaled per component by the power of two derived from
+ * tmax[k] = max |linv_k|;  tileinf[t] = max |X[n,d]| over the 128 samples of tile t and minf[k] = max_d
+ * |means[k,d]| (gvi_group_absmax_f32 with group 128 / 1) bound |x_n - mu_k| and give the power-of-two scale of
+ * the A operand of work item (k, t).  Any 1 <= D <= 256. */
+int gvi_logdens_full_h16_supported(int D);
+int gvi_h16_padded_dim(int D);
+int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void* lo, float* tmax, void* stream);
+int gvi_group_absmax_f32(const float* in, long long rows, int cols, int group, float* out, void* stream);
+int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, int N, int D, const float* means, const float* minf,
+                             const void* linv_hi, const void* linv_lo, const float* tmax, const float* cst, int K,
+                             float* lq, void* stream);
 /* lq[k,n] = -D/2 log 2pi - sum log std_k - 1/2 sum_d ((mu_kd - x_nd)/std_kd)^2   models/diagonal_gmm.py:31-34,47-53 */
 int gvi_logdens_diag_f32(const float* X, int N, int D, const float* means, const float* stds, int K, float* lq,
                          void* stream);

@@ -36,6 +36,8 @@ def timed(fn):
 
 if which == "logdens":
     timed(lambda: ops.logdens_full(X, means, linv, cst, memo=False))
+elif which == "logdens_tf32":
+    timed(lambda: ops.logdens_full(X, means, linv, cst, memo=False, tensor_cores="tf32"))
 elif which == "logdens_simt":
     timed(lambda: ops.logdens_full(X, means, linv, cst, memo=False, tensor_cores=False))
 elif which == "prepare":

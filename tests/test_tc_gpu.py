@@ -1,4 +1,5 @@
-"""tcgen05 (3xTF32) log-density kernel against the fp64 oracle and the exact-fp32 SIMT kernel."""
+"""tcgen05 log-density kernels (3xTF32 streamed, 2 x fp16 resident) against the fp64 oracle and the exact-fp32
+SIMT kernel."""
 import numpy as np
 import pytest
 import torch
@@ -9,15 +10,16 @@ from test_kernels_gpu import make_problem, gmm32_of, dev, rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("kind", ["tf32", "h16"])
 @pytest.mark.parametrize("K,D,N", [(1, 32, 1), (3, 32, 127), (5, 64, 128), (4, 96, 129), (3, 128, 1000),
                                    (7, 256, 513), (2, 224, 300)])
-def test_tc_logdens_matches_oracle(K, D, N):
+def test_tc_logdens_matches_oracle(K, D, N, kind):
     from gmmvi_b200 import ops
     g, X = make_problem(K, D, N, seed=100 + D, scale=30.0)
     g32 = gmm32_of(g)
     linv, prec, cst, ok = ops.prepare_full(dev(g32.chol_cov))
     Xd, md = dev(X), dev(g32.means)
-    lq_tc = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=True)
+    lq_tc = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=kind)
     lq_simt = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=False)
     torch.cuda.synchronize()
     g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
@@ -30,20 +32,67 @@ def test_tc_logdens_matches_oracle(K, D, N):
     assert err.max() < 5e-6, err.max()
 
 
-def test_tc_logdens_many_tiles_and_components():
-    """More work items than SMs: exercises the persistent loop, both TMEM buffers and the stage ring wrap."""
+@pytest.mark.parametrize("kind", ["tf32", "h16"])
+def test_tc_logdens_many_tiles_and_components(kind):
+    """More work items than SMs: exercises the persistent loop, both TMEM buffers, the stage ring wrap and (h16) the
+    reload of the resident factor when a CTA's work range crosses a component boundary."""
     from gmmvi_b200 import ops
     K, D, N = 40, 64, 128 * 12 + 5
     g, X = make_problem(K, D, N, seed=7, scale=10.0)
     g32 = gmm32_of(g)
     linv, prec, cst, ok = ops.prepare_full(dev(g32.chol_cov))
     Xd, md = dev(X), dev(g32.means)
-    a = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=True)
+    a = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=kind)
     b = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=False)
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
     # deterministic: same bits on a second launch
-    a2 = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=True)
+    a2 = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores=kind)
     assert torch.equal(a, a2)
+
+
+@pytest.mark.parametrize("K,D,N", [(3, 100, 700), (2, 200, 257), (6, 20, 300), (2, 10, 64), (300, 64, 130), (2, 37, 90)])
+def test_h16_logdens_odd_dims(K, D, N):
+    """fp16 path on dimensions that are not multiples of 64 (zero-padded operand) / not multiples of 4 (scalar
+    loads), and with more components than SMs (several factor reloads per CTA)."""
+    from gmmvi_b200 import ops
+    g, X = make_problem(K, D, N, seed=300 + D, scale=30.0)
+    g32 = gmm32_of(g)
+    linv, prec, cst, ok = ops.prepare_full(dev(g32.chol_cov))
+    Xd, md = dev(X), dev(g32.means)
+    a = ops.logdens_full(Xd, md, linv, cst, memo=False, tensor_cores="h16")
+    g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
+                       g32.chol_cov.astype(np.float64), False)
+    ref = O.component_log_densities(g_in, X.astype(np.float64))
+    err = np.abs(a.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < 5e-6, err.max()
+
+
+@pytest.mark.parametrize("mean_scale,cov_scale", [(1000.0, 1e-4), (1e-3, 1e-6), (3e4, 1.0), (0.0, 1e4)])
+def test_h16_logdens_dynamic_range(mean_scale, cov_scale):
+    """The power-of-two operand scaling must hold the 1e-5 tolerance when the means are far from the origin and the
+    covariances tiny (x - mu cancels to 1e-5 of |x|), tiny everything, and huge covariances."""
+    from gmmvi_b200 import ops
+    K, D, n_per = 4, 64, 100
+    rng = np.random.default_rng(11)
+    means = (rng.standard_normal((K, D)) * mean_scale).astype(np.float32)
+    A = rng.standard_normal((K, D, D))
+    cov = (A @ A.transpose(0, 2, 1) / D + np.eye(D)) * cov_scale
+    chol = np.linalg.cholesky(cov).astype(np.float32)
+    X = np.concatenate([means[k] + (chol[k].astype(np.float64) @ rng.standard_normal((D, n_per))).T for k in range(K)])
+    X = X.astype(np.float32)
+    linv, prec, cst, ok = ops.prepare_full(dev(chol))
+    a = ops.logdens_full(dev(X), dev(means), linv, cst, memo=False, tensor_cores="h16")
+    g_in = O.OracleGMM(np.zeros(K), means.astype(np.float64), chol.astype(np.float64), False)
+    ref = O.component_log_densities(g_in, X.astype(np.float64))
+    own = np.repeat(np.arange(K), n_per)
+    got = a.cpu().numpy()
+    # own-component entries are the cancellation-sensitive ones
+    e_own = np.abs(got[own, np.arange(K * n_per)] - ref[own, np.arange(K * n_per)]) / np.abs(ref[own, np.arange(K * n_per)])
+    assert e_own.max() < 1e-5, e_own.max()
+    # all entries: 1e-5 relative (north_star tolerance for log densities)
+    fin = np.isfinite(ref)
+    e_all = np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    assert e_all.max() < 1e-5, e_all.max()
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
