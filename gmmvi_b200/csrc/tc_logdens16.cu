@@ -87,6 +87,9 @@ __host__ __device__ __forceinline__ float pow2_scale(float b) {
 #endif
 }
 
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
@@ -246,12 +249,12 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     const int pw = warp - 8;
     const int c2 = lane & 15;
     const int rsub = 2 * pw + (lane >> 4);
-    const int swz = (((c2 >> 1) ^ (rsub & 7)) << 4) + ((c2 & 1) << 3);   // (row & 7) == (rsub & 7) for all my rows
-    const bool vec_ok = (D % 4 == 0);
+    // (row & 7) == (rsub & 7) for all my rows
+    const uint32_t a_smem = smem_u32(a_base) + (uint32_t)(rsub * 128 + ((((c2 >> 1) ^ (rsub & 7)) << 4) + ((c2 & 1) << 3)));
     int s = 0;
     uint32_t ph = 0;
     const long long nitems = (w_end - w_begin) * nkb;
-    long long w_ld = w_begin, w_st = w_begin;
+    long long w_ld = w_begin;
     int kb_ld = 0;
     int k_ld = 0, t_ld = 0;
     if (w_end > w_begin) {
@@ -262,16 +265,21 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       float4 x[8];
       float4 m;
       float xi, mi;
+      bool colok;
     };
+    // Loads are never predicated: rows past N and columns past D (zero padding of the operand) are clamped to valid
+    // addresses; clamped rows are never stored by the epilogue and clamped columns are multiplied by a zero scale.
     auto issue = [&](Regs& R) {
       const int col = kb_ld * KB + c2 * 4;
+      R.colok = col < D;
+      const int colc = min(col, D - 4);
       const int nb = t_ld * TILE_M + rsub;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int n = nb + 16 * q;
-        R.x[q] = n < N ? load4(X + (long long)n * D + col, D - col, vec_ok) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = min(nb + 16 * q, N - 1);
+        R.x[q] = __ldg(reinterpret_cast<const float4*>(X + (long long)n * D + colc));
       }
-      R.m = load4(means + (long long)k_ld * D + col, D - col, vec_ok);
+      R.m = __ldg(reinterpret_cast<const float4*>(means + (long long)k_ld * D + colc));
       R.xi = __ldg(tileinf + t_ld);
       R.mi = __ldg(minf + k_ld);
       if (++kb_ld == nkb) {
@@ -283,11 +291,11 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       }
     };
     auto emit = [&](const Regs& R) {
-      const float sc = pow2_scale(R.xi + R.mi);
+      const float sc = R.colok ? pow2_scale(R.xi + R.mi) : 0.f;
       // (x - m) sc == fma(x, sc, -(m sc)) bit for bit: scaling by a power of two commutes with rounding
       const float m0 = -R.m.x * sc, m1 = -R.m.y * sc, m2 = -R.m.z * sc, m3 = -R.m.w * sc;
       mbar_wait(&bars->empty[s], ph ^ 1);
-      uint8_t* st = a_base + s * STAGE_BYTES + swz;
+      const uint32_t st = a_smem + (uint32_t)(s * STAGE_BYTES);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float v0 = fmaf(R.x[q].x, sc, m0), v1 = fmaf(R.x[q].y, sc, m1);
@@ -295,11 +303,8 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-        const int off = (rsub + 16 * q) * 128;
-        *reinterpret_cast<uint2*>(st + off) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-        *reinterpret_cast<uint2*>(st + A_BYTES + off) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+        sts64(st + q * 2048, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        sts64(st + A_BYTES + q * 2048, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
       }
       fence_proxy_async();
       __syncwarp();
@@ -322,7 +327,6 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         emit(R2);
       }
     }
-    (void)w_st;
   }
   tc_fence_before();
   __syncthreads();
@@ -397,7 +401,7 @@ static size_t smem_bytes(int Dp) {
 
 using namespace gvi;
 
-extern "C" int gvi_logdens_full_h16_supported(int D) { return (D >= 1 && D <= 256) ? 1 : 0; }
+extern "C" int gvi_logdens_full_h16_supported(int D) { return (D >= 4 && D <= 256 && D % 4 == 0) ? 1 : 0; }
 extern "C" int gvi_h16_padded_dim(int D) { return h16::padded_dim(D); }
 
 extern "C" int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void* lo, float* tmax, void* stream) {
@@ -423,7 +427,7 @@ extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, in
                                         const float* tmax, const float* cst, int K, float* lq, void* stream) {
   GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_logdens_full_h16_f32: bad sizes");
   if (!gvi_logdens_full_h16_supported(D)) {
-    set_last_error("gvi_logdens_full_h16_f32: D=%d unsupported (needs 1 <= D <= 256)", D);
+    set_last_error("gvi_logdens_full_h16_f32: D=%d unsupported (needs D %% 4 == 0, 4 <= D <= 256)", D);
     return GVI_ERR_UNSUPPORTED;
   }
   if (N == 0 || K == 0) return GVI_OK;

@@ -36,7 +36,7 @@ H16_MIN_DIM = 32        # below this the SIMT kernel wins (the fp16 operand is p
 
 
 def logdens_kernel_kind(D: int) -> str:
-    if USE_TENSOR_CORES and TC_KIND == "h16" and H16_MIN_DIM <= D <= 256:
+    if USE_TENSOR_CORES and TC_KIND == "h16" and D >= H16_MIN_DIM and _lib.lib().gvi_logdens_full_h16_supported(int(D)):
         return "h16"
     if USE_TENSOR_CORES and _lib.lib().gvi_logdens_full_tc_supported(int(D)):
         return "tf32"
@@ -164,6 +164,8 @@ def logdens_full(X, means, linv, cst, out=None, memo=True, tensor_cores=None):
     else:
         kind = tensor_cores if isinstance(tensor_cores, str) else logdens_kernel_kind(D)
         if kind == "tf32" and not _lib.lib().gvi_logdens_full_tc_supported(D):
+            kind = "simt"
+        if kind == "h16" and not _lib.lib().gvi_logdens_full_h16_supported(D):
             kind = "simt"
     if N == 0 or K == 0:
         kind = "simt"

@@ -60,7 +60,7 @@ int gvi_logdens_full_tc_f32(const float* X, int N, int D, const float* means, co
  * [K, Dp, Dp] (Dp = gvi_h16_padded_dim(D)), scaled per component by the power of two derived from
  * tmax[k] = max |linv_k|;  tileinf[t] = max |X[n,d]| over the 128 samples of tile t and minf[k] = max_d
  * |means[k,d]| (gvi_group_absmax_f32 with group 128 / 1) bound |x_n - mu_k| and give the power-of-two scale of
- * the A operand of work item (k, t).  Any 1 <= D <= 256. */
+ * the A operand of work item (k, t).  D % 4 == 0, 4 <= D <= 256. */
 int gvi_logdens_full_h16_supported(int D);
 int gvi_h16_padded_dim(int D);
 int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void* lo, float* tmax, void* stream);
