@@ -21,13 +21,15 @@
 // Triangular structure.  K-step jb (16 columns j of Linv) only feeds output columns i >= 16 jb, so the MMA
 // of that step runs with N = Dp - 16 jb: 53 % of the dense MMA work at D = 256.
 //
-// Warp roles (512 threads, one persistent CTA per SM, each CTA owns a CONTIGUOUS range of the k-major work list):
+// Warp roles (768 threads, one persistent CTA per SM, each CTA owns a CONTIGUOUS range of the k-major work list):
 //   warp 0      TMA: loads the hi / lo k-blocks of Linv_k (padded fp16 [K, Dp, Dp]) when the component changes
 //   warp 1      MMA issuer (one thread): 3 tcgen05.mma per 16-column step
 //   warp 2      TMEM allocator (2 x 256 fp32 columns, double buffered accumulators)
 //   warps 4-7   epilogue: tcgen05.ld, row sums of squares, un-scaling, lq store
-//   warps 8-15  A producers: x - mu_k in fp32 (cancellation happens BEFORE the split), scale, split into fp16
-//               hi / lo, write the K-major SWIZZLE_128B operand; global loads run one stage ahead
+//   warps 8-23  A producers, two groups of 8 warps on alternate 32-column stages: x - mu_k in fp32 (cancellation
+//               happens BEFORE the split), scale, split into fp16 hi / lo (FFMA2 / F2FP / FHFMA), write the K-major
+//               SWIZZLE_64B operand; each thread keeps the global loads of its next two stages in flight
+// Register budget by setmaxnreg: control warps 48, epilogue 80, producers 88 (the pool is the launch allocation, 80 x 768).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 
@@ -36,11 +38,12 @@ namespace h16 {
 using namespace tcx;
 
 constexpr int TILE_M = 128;
-constexpr int KB = 64;                    // fp16 elements per 128-byte swizzle row = columns per stage
-constexpr int STAGES = 2;
-constexpr int THREADS = 512;
-constexpr int A_BYTES = TILE_M * 128;     // 16 KB per hi / lo
-constexpr int STAGE_BYTES = 2 * A_BYTES;  // 32 KB
+constexpr int KB = 64;                    // B: fp16 elements per 128-byte swizzle row = columns per resident k-block
+constexpr int KA = 32;                    // A: columns per pipeline stage (64-byte rows, SWIZZLE_64B)
+constexpr int STAGES = 4;
+constexpr int THREADS = 768;              // 4 control + 4 epilogue + 2 x 8 producer warps
+constexpr int A_BYTES = TILE_M * 64;      // 8 KB per hi / lo
+constexpr int STAGE_BYTES = 2 * A_BYTES;  // 16 KB
 constexpr int ACC_COLS = 256;
 constexpr int TMEM_COLS = 512;
 
@@ -69,6 +72,17 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// K-major SWIZZLE_64B shared-memory matrix descriptor: 8-row x 64-byte atoms, 512 B between atoms (SBO)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
 // Power of two s with b * s < 2^14 for the non-negative bound b (exponent clamped to +-40).
 __host__ __device__ __forceinline__ float pow2_scale(float b) {
 #ifdef __CUDA_ARCH__
@@ -89,6 +103,87 @@ __host__ __device__ __forceinline__ float pow2_scale(float b) {
 
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// fp32x2 FMA (one issue slot for two lanes of math) and the mixed-precision v - float(h) (FHFMA): sm_100 only
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  float2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2v(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  float2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float sub_f32_f16(float v, unsigned short h) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(h), "h"((unsigned short)0xBC00), "f"(v));
+  return d;
+}
+// Wait whose fast path is a single try_wait; the bounded spin (trap instead of hang) is kept out of line.
+__device__ __forceinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_fast(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (!ok) mbar_wait_slow(addr, parity);
+}
+// mbarrier wait that lets the hardware suspend the thread (up to `ns`) instead of spinning through issue slots
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
@@ -117,10 +212,11 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   Barriers* bars = reinterpret_cast<Barriers*>(a_base + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = ceil_div(N, TILE_M);
-  const long long total = (long long)T * K;
+  const long long total = (long long)T * K;      // < 2^31 (checked by the host)
   const int nkb = Dp / KB;
-  const long long w_begin = total * blockIdx.x / gridDim.x;
-  const long long w_end = total * (blockIdx.x + 1) / gridDim.x;
+  const int nst = Dp / KA;               // pipeline stages per work item
+  const int w_begin = (int)(total * blockIdx.x / gridDim.x);
+  const int w_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -143,14 +239,14 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
 
   const int wg = warp >> 2;
   if (wg == 0) {
-    reg_dec<64>();
+    reg_dec<56>();
     if (warp == 0) {
       // ---------------- TMA: Linv_k (hi, lo) becomes resident whenever the component changes ----------------
       if (lane == 0 && w_end > w_begin) {
-        const int k_first = (int)(w_begin / T), k_last = (int)((w_end - 1) / T);
+        const int k_first = w_begin / T, k_last = (w_end - 1) / T;
         int nload = 0;
         for (int k = k_first; k <= k_last; ++k, ++nload) {
-          if (nload > 0) mbar_wait(&bars->b_free, (uint32_t)((nload - 1) & 1));
+          if (nload > 0) mbar_wait_sleepy(&bars->b_free, (uint32_t)((nload - 1) & 1));
           mbar_arrive_expect_tx(&bars->b_full, 2u * (uint32_t)brows * 128u);
           for (int kb = 0; kb < nkb; ++kb) {
             const int row0 = block_row_offset(Dp, kb);
@@ -163,77 +259,91 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       }
     } else if (warp == 1) {
       // ---------------- MMA issuer ----------------
-      if (lane == 0) {
-        int s = 0;
-        uint32_t ph = 0;
-        long long it = 0;
-        int cur_k = -1, nload = 0;
-        const uint32_t bhi_addr = smem_u32(b_hi), blo_addr = smem_u32(b_lo);
-        for (long long w = w_begin; w < w_end; ++w, ++it) {
-          const int k = (int)(w / T);
-          if (k != cur_k) {
-            mbar_wait(&bars->b_full, (uint32_t)(nload & 1));
-            ++nload;
-            cur_k = k;
-          }
-          const int buf = (int)(it & 1);
-          const uint32_t use = (uint32_t)(it >> 1);
-          mbar_wait(&bars->acc_empty[buf], (use & 1) ^ 1);
+      // The whole warp runs the loop with warp-uniform values (descriptors live in uniform registers); only the
+      // tcgen05 instructions themselves are issued by one elected lane.  A lane-0 branch around the loop would
+      // make ptxas move every descriptor through R2UR inside an ELECT loop: ~30 instructions per MMA.
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      int cur_k = -1, nload = 0;
+      const uint64_t a_desc0 = make_desc_sw64(smem_u32(a_base));
+      const uint64_t bhi_desc0 = make_desc(smem_u32(b_hi)), blo_desc0 = make_desc(smem_u32(b_lo));
+      for (int w = w_begin; w < w_end; ++w, ++it) {
+        const int k = w / T;
+        if (k != cur_k) {
+          mbar_wait_sleepy(&bars->b_full, (uint32_t)(nload & 1));
+          ++nload;
+          cur_k = k;
+        }
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait_sleepy(&bars->acc_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        for (int si = 0; si < nst; ++si) {
+          mbar_wait_fast(smem_u32(&bars->full[s]), ph);
           tc_fence_after();
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&bars->full[s], ph);
-            tc_fence_after();
-            const uint32_t st = smem_u32(a_base + s * STAGE_BYTES);
-            const uint32_t boff = (uint32_t)block_row_offset(Dp, kb) * 128u;
+          const int kb = si >> 1;
+          // descriptor start-address fields are in 16-byte units; the sums stay below 2^14 (smem < 256 KB)
+          const uint32_t boff16 = (uint32_t)block_row_offset(Dp, kb) * 8u;
+          const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)(s * STAGE_BYTES) >> 4);
+          if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < KB / 16; ++ks) {
-              const int j0 = kb * KB + ks * 16;
+            for (int ks = 0; ks < KA / 16; ++ks) {
+              const int j0 = si * KA + ks * 16;
+              const int kq = (si & 1) * 2 + ks;          // 16-column step inside B's 64-column block
               const uint32_t idesc = make_idesc_f16(Dp - j0);
               const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + j0);
-              const uint64_t a_hi = make_desc(st + ks * 32);
-              const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
-              const uint64_t bd_hi = make_desc(bhi_addr + boff + (uint32_t)(ks * 16) * 128u + ks * 32);
-              const uint64_t bd_lo = make_desc(blo_addr + boff + (uint32_t)(ks * 16) * 128u + ks * 32);
+              const uint64_t a_hi = a_st + (uint64_t)(ks * 2);
+              const uint64_t a_lo = a_hi + (uint64_t)(A_BYTES >> 4);
+              const uint64_t boffk = (uint64_t)(boff16 + (uint32_t)(kq * 16) * 8u + (uint32_t)(kq * 2));
+              const uint64_t bd_hi = bhi_desc0 + boffk;
+              const uint64_t bd_lo = blo_desc0 + boffk;
               umma_f16(d_tmem, a_hi, bd_hi, idesc, j0 != 0 ? 1u : 0u);
               umma_f16(d_tmem, a_lo, bd_hi, idesc, 1u);
               umma_f16(d_tmem, a_hi, bd_lo, idesc, 1u);
             }
             umma_commit(&bars->empty[s]);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (si == nst - 1) {
+              umma_commit(&bars->acc_full[buf]);
+              // last item of this component in my range: the resident factor may be overwritten once these
+              // MMAs retire
+              if (w + 1 < w_end && (w + 1) / T != k) umma_commit(&bars->b_free);
+            }
           }
-          umma_commit(&bars->acc_full[buf]);
-          // last item of this component in my range: the resident factor may be overwritten once these MMAs retire
-          if (w + 1 < w_end && (int)((w + 1) / T) != k) umma_commit(&bars->b_free);
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (wg == 1) {
-    reg_dec<80>();
+    reg_dec<72>();
     // ---------------- epilogue: row sums of squares ----------------
     const int q = warp - 4;
-    long long it = 0;
+    int it = 0;
     const int ncol32 = Dp / 32;
-    for (long long w = w_begin; w < w_end; ++w, ++it) {
-      const int k = (int)(w / T), t = (int)(w % T);
+    for (int w = w_begin; w < w_end; ++w, ++it) {
+      const int k = w / T, t = w - k * T;
       const int n = t * TILE_M + 32 * q + lane;
       // operands of the un-scaling factor 1 / (s t): the same inputs as the producers use
       const float xi = __ldg(tileinf + t), mi = __ldg(minf + k), tm = __ldg(tmax + k), c = __ldg(cst + k);
-      const int buf = (int)(it & 1);
+      const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&bars->acc_full[buf], use & 1);
+      mbar_wait_sleepy(&bars->acc_full[buf], use & 1);
       tc_fence_after();
-      float s0 = 0.f, s1 = 0.f;
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
       for (int cb = 0; cb < ncol32; ++cb) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + cb * 32), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
-          s0 = fmaf(a, a, s0);
-          s1 = fmaf(b, b, s1);
+        for (int i = 0; i < 32; i += 4) {
+          const float2 a = make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          const float2 b = make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          s01 = ffma2v(a, a, s01);
+          s23 = ffma2v(b, b, s23);
         }
       }
+      const float s0 = s01.x + s23.x, s1 = s01.y + s23.y;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
@@ -241,91 +351,108 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       if (n < N) lq[(long long)k * N + n] = c - 0.5f * (((s0 + s1) * f) * f);
     }
   } else {
-    reg_inc<184>();
+    reg_inc<88>();
     // ---------------- A producers ----------------
-    // A warp-wide 128-bit load covers two complete 256-byte row segments (64 fp32 columns): lane l reads the float4
-    // c2 = l % 16 of row rsub + 16 q (rsub = 2 * producer warp + l / 16, q = 0..7) and writes its four fp16 hi / lo
-    // values as one 8-byte store each into the 128B-swizzled operand.
-    const int pw = warp - 8;
-    const int c2 = lane & 15;
-    const int rsub = 2 * pw + (lane >> 4);
-    // (row & 7) == (rsub & 7) for all my rows
-    const uint32_t a_smem = smem_u32(a_base) + (uint32_t)(rsub * 128 + ((((c2 >> 1) ^ (rsub & 7)) << 4) + ((c2 & 1) << 3)));
-    int s = 0;
-    uint32_t ph = 0;
-    const long long nitems = (w_end - w_begin) * nkb;
-    long long w_ld = w_begin;
-    int kb_ld = 0;
+    // A warp-wide 128-bit load covers four complete 128-byte row segments (32 fp32 columns): lane l reads the float4
+    // c = l % 8 of row rsub + 32 q (rsub = 4 * producer warp + l / 8, q = 0..3) and writes its four fp16 hi / lo
+    // values as one 8-byte store each into the 64B-swizzled operand.
+    // Two groups of 8 warps convert alternate stages (group g owns the stages si = g, g + 2, ... of every work
+    // item), so two stages are being converted at any time and a group's fence / barrier latency is covered by
+    // the other group's math.  A warp-wide 128-bit load covers four complete 128-byte row segments (32 fp32
+    // columns): lane l reads the float4 c = l % 8 of row rsub + 32 q (rsub = 4 * warp-in-group + l / 8, q = 0..3)
+    // and writes its four fp16 hi / lo values as one 8-byte store each into the 64B-swizzled operand.
+    const int grp = (warp - 8) >> 3;
+    const int pw = (warp - 8) & 7;
+    const int c = lane & 7;
+    const int rsub = 4 * pw + (lane >> 3);
+    // ((row >> 1) & 3) == ((rsub >> 1) & 3) for all my rows
+    uint32_t a_smem = smem_u32(a_base) + (uint32_t)(grp * STAGE_BYTES) +
+                      (uint32_t)(rsub * 64 + ((((c >> 1) ^ ((rsub >> 1) & 3)) << 4) + ((c & 1) << 3)));
+    uint32_t empty_bar = smem_u32(&bars->empty[grp]), full_bar = smem_u32(&bars->full[grp]);
+    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+    const float4* __restrict__ M4 = reinterpret_cast<const float4*>(means);
+    const int D4 = D >> 2;
+    const int hst = nst >> 1;                                  // my stages per work item
+    const int nitems = (w_end - w_begin) * hst;
+    const int stride4 = 32 * D4;                               // float4 units between my consecutive rows
+    // keep the per-thread constants in registers (ptxas otherwise re-derives them from %tid in every stage)
+    asm volatile("" : "+r"(a_smem), "+r"(empty_bar), "+r"(full_bar));
+
+    // ---- load stream state ----
+    int h_ld = 0;                                              // my stage inside the work item
     int k_ld = 0, t_ld = 0;
     if (w_end > w_begin) {
-      k_ld = (int)(w_ld / T);
-      t_ld = (int)(w_ld % T);
+      k_ld = w_begin / T;
+      t_ld = w_begin - k_ld * T;
     }
+    // ---- store stream state ----
+    int h_st = 0, jj_st = 0;
+    float sc_cur = 0.f;
     struct Regs {
-      float4 x[8];
+      float4 x[4];
       float4 m;
       float xi, mi;
-      bool colok;
     };
-    // Loads are never predicated: rows past N and columns past D (zero padding of the operand) are clamped to valid
-    // addresses; clamped rows are never stored by the epilogue and clamped columns are multiplied by a zero scale.
+    // Loads are never predicated: columns past D (zero padding of the operand) are clamped to valid addresses and
+    // multiplied by a zero scale.  Offsets are 32-bit float4 indices (the host checks N * D < 2^31).
     auto issue = [&](Regs& R) {
-      const int col = kb_ld * KB + c2 * 4;
-      R.colok = col < D;
-      const int colc = min(col, D - 4);
-      const int nb = t_ld * TILE_M + rsub;
+      const int col4 = (2 * h_ld + grp) * (KA / 4) + c;
+      const int colc4 = min(col4, D4 - 1);
+      const int row0 = t_ld * TILE_M + rsub;
+      if (row0 + 96 < N) {                                     // all four of my rows exist
+        const int i0 = row0 * D4 + colc4;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int n = min(nb + 16 * q, N - 1);
-        R.x[q] = __ldg(reinterpret_cast<const float4*>(X + (long long)n * D + colc));
+        for (int q = 0; q < 4; ++q) R.x[q] = __ldg(X4 + (i0 + q * stride4));
+      } else {                                                 // tail of the sample range: clamp (never stored)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) R.x[q] = __ldg(X4 + (min(row0 + 32 * q, N - 1) * D4 + colc4));
       }
-      R.m = __ldg(reinterpret_cast<const float4*>(means + (long long)k_ld * D + colc));
-      R.xi = __ldg(tileinf + t_ld);
-      R.mi = __ldg(minf + k_ld);
-      if (++kb_ld == nkb) {
-        kb_ld = 0;
-        if (++w_ld < w_end) {
-          k_ld = (int)(w_ld / T);
-          t_ld = (int)(w_ld % T);
-        }
+      R.m = __ldg(M4 + (k_ld * D4 + colc4));
+      if (h_ld == 0) {
+        R.xi = __ldg(tileinf + t_ld);
+        R.mi = __ldg(minf + k_ld);
+      }
+      if (++h_ld == hst) {
+        h_ld = 0;
+        if (++t_ld == T) { t_ld = 0; ++k_ld; }
       }
     };
     auto emit = [&](const Regs& R) {
-      const float sc = R.colok ? pow2_scale(R.xi + R.mi) : 0.f;
+      if (h_st == 0) sc_cur = pow2_scale(R.xi + R.mi);
+      const bool colok = (2 * h_st + grp) * (KA / 4) + c < D4;
+      const float sc = colok ? sc_cur : 0.f;
+      if (++h_st == hst) h_st = 0;
       // (x - m) sc == fma(x, sc, -(m sc)) bit for bit: scaling by a power of two commutes with rounding
-      const float m0 = -R.m.x * sc, m1 = -R.m.y * sc, m2 = -R.m.z * sc, m3 = -R.m.w * sc;
-      mbar_wait(&bars->empty[s], ph ^ 1);
-      const uint32_t st = a_smem + (uint32_t)(s * STAGE_BYTES);
+      const float2 nm01 = make_float2(-R.m.x * sc, -R.m.y * sc), nm23 = make_float2(-R.m.z * sc, -R.m.w * sc);
+      const uint32_t sl = (uint32_t)(jj_st & 1);               // my slot: stage ring entry grp + 2 sl
+      mbar_wait_fast(empty_bar + sl * 16, (uint32_t)(((jj_st >> 1) & 1) ^ 1));
+      ++jj_st;
+      const uint32_t st = a_smem + sl * (2 * STAGE_BYTES);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float v0 = fmaf(R.x[q].x, sc, m0), v1 = fmaf(R.x[q].y, sc, m1);
-        const float v2 = fmaf(R.x[q].z, sc, m2), v3 = fmaf(R.x[q].w, sc, m3);
-        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-        sts64(st + q * 2048, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      for (int q = 0; q < 4; ++q) {
+        const float2 v01 = ffma2(make_float2(R.x[q].x, R.x[q].y), sc, nm01);
+        const float2 v23 = ffma2(make_float2(R.x[q].z, R.x[q].w), sc, nm23);
+        const __half2 h01 = __floats2half2_rn(v01.x, v01.y), h23 = __floats2half2_rn(v23.x, v23.y);
+        const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+        const __half2 l01 = __floats2half2_rn(sub_f32_f16(v01.x, (unsigned short)(u01 & 0xffffu)),
+                                              sub_f32_f16(v01.y, (unsigned short)(u01 >> 16)));
+        const __half2 l23 = __floats2half2_rn(sub_f32_f16(v23.x, (unsigned short)(u23 & 0xffffu)),
+                                              sub_f32_f16(v23.y, (unsigned short)(u23 >> 16)));
+        sts64(st + q * 2048, u01, u23);
         sts64(st + A_BYTES + q * 2048, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->full[s]);
-      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (lane == 0) mbar_arrive_addr(full_bar + sl * 16);
     };
-    // register ring of three stages: the global loads run two stages ahead of the conversion
-    Regs R0, R1, R2;
+    // register ring of two of my stages: the global loads run one stage of this group (two stages of the
+    // pipeline, 32 KB per SM counting both groups... plus the one being converted) ahead of the conversion
+    Regs R0, R1;
     if (nitems > 0) issue(R0);
-    if (nitems > 1) issue(R1);
-    for (long long j = 0; j < nitems; j += 3) {
-      if (j + 2 < nitems) issue(R2);
+    for (int j = 0; j < nitems; j += 2) {
+      if (j + 1 < nitems) issue(R1);
       emit(R0);
-      if (j + 1 < nitems) {
-        if (j + 3 < nitems) issue(R0);
-        emit(R1);
-      }
-      if (j + 2 < nitems) {
-        if (j + 4 < nitems) issue(R1);
-        emit(R2);
-      }
+      if (j + 1 < nitems) { if (j + 2 < nitems) issue(R0); emit(R1); }
     }
   }
   tc_fence_before();
@@ -437,7 +564,9 @@ extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, in
                   reinterpret_cast<uintptr_t>(linv_hi) % 16 == 0 && reinterpret_cast<uintptr_t>(linv_lo) % 16 == 0,
               "gvi_logdens_full_h16_f32: operands must be 16-byte aligned");
   const int Dp = h16::padded_dim(D);
-  GVI_REQUIRE((long long)K * Dp < 2147483647LL, "gvi_logdens_full_h16_f32: K*D too large");
+  GVI_REQUIRE((long long)K * Dp < 2147483647LL && (long long)N * D < 2147483647LL &&
+                  (long long)ceil_div(N, h16::TILE_M) * K * 8 < 2147483647LL,
+              "gvi_logdens_full_h16_f32: K*D, N*D or the work list too large (32-bit offsets)");
   CUtensorMap map_hi, map_lo;
   int rc = h16::make_map_h16(&map_hi, linv_hi, K, Dp);
   if (rc) return rc;
