@@ -16,6 +16,7 @@
 // The diagonal of M is carried as (diag - 1) so that logdet and tr(M^-1) - D keep full relative accuracy
 // when eta is large (small steps), where the reference's fp32 formula cancels catastrophically.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/gmmvi_b200.h"
 
 namespace gvi {
@@ -28,6 +29,13 @@ int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
 size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
+
+bool update_blocked_supported(int D);
+int launch_update_full_blocked(int mode, const float* means, const float* chols, const float* Bm, const float* B2,
+                               const float* hv, const float* stepsizes, const float* last_etas,
+                               const float* num_updates, int K, int D, float temperature, float* out_means,
+                               float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals,
+                               cudaStream_t st);
 
 constexpr int UPD_THREADS = 1024;
 
@@ -609,6 +617,9 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
   update_vectors_kernel<<<K, 256, D * sizeof(float), st>>>(means, chols, Hneg, gneg, D, mode != 2, hv);
   rc = check_launch("update_vectors_kernel");
   if (rc) return rc;
+  if (update_blocked_supported(D) && !getenv("GMMVI_B200_UPDATE_PANEL"))
+    return launch_update_full_blocked(mode, means, chols, Bm, B2, hv, stepsizes, last_etas, num_updates, K, D,
+                                      temperature, out_means, out_chols, success, etas, kls, evals, st);
   const size_t full = upd_smem_bytes(D);
   const int use_global = full > kMaxDynSmem;
   const size_t smem = use_global ? (size_t)4 * D * sizeof(float) : full;
