@@ -40,38 +40,59 @@ struct Smem {
   float* idiag;   // [32] reciprocal diagonal of the current diagonal block
   float* red;     // [33]
   int* flag;
+  const int* blk_bi;  // [36] row block of packed block index
 };
 
 // ---- assembly: A~[a][b] = a1 B[D-1-a][D-1-b] (+ a2 B2[..]) for b < a, dm1[a] = the diagonal value ----------------
-__device__ void assemble(const Smem& s, const float* __restrict__ B, const float* __restrict__ B2, float a1, float a2,
+// One 16-byte chunk (row a, columns 4q..4q+3 of a block) per thread and step; the four source elements are
+// contiguous (in reverse order) in row D-1-a of B.
+__device__ __noinline__ void assemble(const Smem s, const float* __restrict__ B, const float* __restrict__ B2, float a1, float a2,
                          int D, int nbk) {
   const int tid = threadIdx.x;
-  for (int bi = 0; bi < nbk; ++bi)
-    for (int bj = 0; bj <= bi; ++bj) {
-      float* blk = s.A + (tri(bi) + bj) * BS;
-      for (int e = tid; e < BS; e += THREADS) {
-        const int r = e >> 5, c = e & 31;
-        const int a = bi * NB + r, b = bj * NB + c;
-        float val = 0.f;
-        if (a < D && b <= a) {
-          const long long g = (long long)(D - 1 - a) * D + (D - 1 - b);
-          val = a1 * __ldg(B + g);
-          if (B2) val = fmaf(a2, __ldg(B2 + g), val);
+  const int nchunk = tri(nbk) * (BS / 4);
+  const bool vec = (D & 3) == 0;
+  for (int e = tid; e < nchunk; e += THREADS) {
+    const int blk = e >> 8, r = (e >> 3) & 31, q = e & 7;
+    const int bi = s.blk_bi[blk], bj = blk - tri(bi);
+    const int a = bi * NB + r, b0 = bj * NB + 4 * q;
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a < D && b0 <= a) {
+      const long long g = (long long)(D - 1 - a) * D + (D - 1 - b0 - 3);     // element for b0 + 3; b0 is at g + 3
+      if (vec) {      // D % 4 == 0 and b0 % 4 == 0: aligned, and b0 + 3 < D because a < D
+        const float4 t = __ldg(reinterpret_cast<const float4*>(B + g));
+        vals[0] = a1 * t.w; vals[1] = a1 * t.z; vals[2] = a1 * t.y; vals[3] = a1 * t.x;
+        if (B2) {
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(B2 + g));
+          vals[0] = fmaf(a2, t2.w, vals[0]); vals[1] = fmaf(a2, t2.z, vals[1]);
+          vals[2] = fmaf(a2, t2.y, vals[2]); vals[3] = fmaf(a2, t2.x, vals[3]);
         }
-        if (a == b) {
-          s.dm1[a] = val;
-          blk[sw(r, c)] = 1.f;
-        } else {
-          blk[sw(r, c)] = (b < a) ? val : 0.f;
-        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (b0 + c < D) {
+            vals[c] = a1 * __ldg(B + g + 3 - c);
+            if (B2) vals[c] = fmaf(a2, __ldg(B2 + g + 3 - c), vals[c]);
+          }
       }
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int b = b0 + c;
+      if (b == a) {
+        s.dm1[a] = vals[c];
+        vals[c] = 1.f;
+      } else if (b > a) {
+        vals[c] = 0.f;
+      }
+    }
+    st4(s.A + blk * BS + sw4(r, q), make_float4(vals[0], vals[1], vals[2], vals[3]));
+  }
 }
 
 // ---- Cholesky of one 32 x 32 diagonal block by one warp (lane = row) ------------------------------------------
 // In: lower part of the block + dm1 (diagonal - 1).  Out: factor (diagonal entries = l_jj), dm1 = pivot - 1,
 // idiag = 1 / l_jj.  Returns false on a non-positive / non-finite pivot (same value in every lane).
-__device__ bool chol_diag(float* blk, float* dm1p, float* idiag) {
+__device__ __noinline__ bool chol_diag(float* blk, float* dm1p, float* idiag) {
   const int i = threadIdx.x & 31;
   float a[NB];
 #pragma unroll
@@ -80,129 +101,154 @@ __device__ bool chol_diag(float* blk, float* dm1p, float* idiag) {
     a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
   }
   float dd = dm1p[i];
+  float myinv = 1.f;
   bool good = true;
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
+    // column j: l_ij = (a_ij - sum_{m<j} l_im l_jm) / l_jj.  Row j (m < j) is already final in shared memory
+    // (lane j stored its entries as they were produced) and is read as broadcast 128-bit loads.
+    float s0 = a[j], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < (j + 3) / 4; ++q) {
+      const float4 cv = ld4(blk + sw4(j, q));
+      if (4 * q < j) s0 = fmaf(-a[4 * q], cv.x, s0);
+      if (4 * q + 1 < j) s1 = fmaf(-a[4 * q + 1], cv.y, s1);
+      if (4 * q + 2 < j) s2 = fmaf(-a[4 * q + 2], cv.z, s2);
+      if (4 * q + 3 < j) s3 = fmaf(-a[4 * q + 3], cv.w, s3);
+    }
     const float ddj = __shfl_sync(0xffffffffu, dd, j);
     const float piv = 1.f + ddj;
     if (!(piv > 0.f) || !isfinite(piv)) good = false;
-    const float ljj = sqrtf(piv);
-    const float inv = 1.f / ljj;
-    float s0 = a[j], s1 = 0.f;
-#pragma unroll
-    for (int m = 0; m < j; ++m) {
-      const float ljm = __shfl_sync(0xffffffffu, a[m], j);
-      if (m & 1) s1 = fmaf(-a[m], ljm, s1);
-      else s0 = fmaf(-a[m], ljm, s0);
-    }
-    const float lij = (s0 + s1) * inv;
+    const float inv = rsqrtf(piv);
+    const float lij = ((s0 + s1) + (s2 + s3)) * inv;
+    float val;
     if (i > j) {
-      a[j] = lij;
+      val = lij;
       dd = fmaf(-lij, lij, dd);
     } else if (i == j) {
-      a[j] = ljj;
+      val = piv * inv;
+      myinv = inv;
     } else {
-      a[j] = 0.f;
+      val = 0.f;
     }
+    a[j] = val;
+    blk[sw(i, j)] = val;
+    __syncwarp();
   }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) st4(blk + sw4(i, q), make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]));
   dm1p[i] = dd;
-  float di = 0.f;
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-    if (i == j) di = a[j];
-  idiag[i] = 1.f / di;
+  idiag[i] = myinv;
+  __syncwarp();
   return good;
 }
 
-// ---- blocked Cholesky of the whole matrix ----------------------------------------------------------------------
-__device__ bool chol_blocked(const Smem& s, int nbk) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int p = 0; p < nbk; ++p) {
-    float* Cpp = s.A + (tri(p) + p) * BS;
-    if (warp == 0) {
-      const bool good = chol_diag(Cpp, s.dm1 + p * NB, s.idiag);
-      if (lane == 0) *s.flag = good ? 0 : 1;
+// ---- panel solve: row g of the panel below diagonal block p, x C_pp^T = a (one thread per row) -----------------
+__device__ __noinline__ void panel_solve(const Smem s, int p, int n) {
+  const int tid = threadIdx.x;
+  const float* Cpp = s.A + (tri(p) + p) * BS;
+  for (int g = tid; g < n * NB; g += THREADS) {
+    const int ib = g >> 5, r = g & 31;
+    float* blk = s.A + (tri(p + 1 + ib) + p) * BS;
+    float x[NB];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = ld4(blk + sw4(r, q));
+      x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
     }
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float acc0 = x[j], acc1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < (j + 3) / 4; ++q) {
+        const float4 cv = ld4(Cpp + sw4(j, q));       // C_pp[j][4q .. 4q+3], broadcast
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < j) {
+            if (e & 1) acc1 = fmaf(-x[4 * q + e], comp(cv, e), acc1);
+            else acc0 = fmaf(-x[4 * q + e], comp(cv, e), acc0);
+          }
+      }
+      x[j] = (acc0 + acc1) * s.idiag[j];
+    }
+    float* pt = s.PT + ib * BS;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) pt[j * NB + r] = x[j];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st4(blk + sw4(r, q), make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+  }
+}
+
+// ---- one trailing-update task: C(p+1+ii, p+1+jj) -= P_ii P_jj^T, 4 x 8 register tile per lane ---------------
+__device__ __noinline__ void trailing_task(const Smem s, int p, int ii, int jj) {
+  const int lane = threadIdx.x & 31;
+  const int ry = lane >> 2, cx = lane & 3;
+  const float* Pi = s.PT + ii * BS + 4 * ry;
+  const float* Pj = s.PT + jj * BS + 8 * cx;
+  float acc[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < NB; ++k) {
+    const float4 av = ld4(Pi + k * NB);
+    const float4 b0 = ld4(Pj + k * NB), b1 = ld4(Pj + k * NB + 4);
+    const float ar[4] = {av.x, av.y, av.z, av.w};
+    const float bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(ar[r], bc[c], acc[r][c]);
+  }
+  const int bi = p + 1 + ii, bj = p + 1 + jj;
+  float* blk = s.A + (tri(bi) + bj) * BS;
+  const bool diag = (bi == bj);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = 4 * ry + r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* ptr = blk + sw4(row, 2 * cx + h);
+      float4 cur = ld4(ptr);
+      float cv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = 8 * cx + 4 * h + e;
+        if (!diag || col < row) cv[e] -= acc[r][4 * h + e];
+        else if (col == row) s.dm1[bi * NB + row] -= acc[r][4 * h + e];
+      }
+      st4(ptr, make_float4(cv[0], cv[1], cv[2], cv[3]));
+    }
+  }
+}
+
+// ---- blocked Cholesky of the whole matrix ----------------------------------------------------------------------
+__device__ __noinline__ bool chol_blocked(const Smem s, int nbk) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    const bool good = chol_diag(s.A, s.dm1, s.idiag);
+    if (lane == 0) *s.flag = good ? 0 : 1;
+  }
+  __syncthreads();
+  for (int p = 0; p < nbk; ++p) {
+    // the diagonal block (p, p) has been factored (by warp 0, overlapped with the previous trailing update)
     if (*s.flag) return false;
     const int n = nbk - 1 - p;                 // row blocks below the diagonal block
     if (n == 0) break;
-    // ---- panel solve: row g of the panel, x C_pp^T = a  (one thread per row)
-    for (int g = tid; g < n * NB; g += THREADS) {
-      const int ib = g >> 5, r = g & 31;
-      float* blk = s.A + (tri(p + 1 + ib) + p) * BS;
-      float x[NB];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = ld4(blk + sw4(r, q));
-        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        float acc = x[j];
-#pragma unroll
-        for (int q = 0; q < (j + 3) / 4; ++q) {
-          const float4 cv = ld4(Cpp + sw4(j, q));       // C_pp[j][4q .. 4q+3], broadcast
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (4 * q + e < j) acc = fmaf(-x[4 * q + e], comp(cv, e), acc);
-        }
-        x[j] = acc * s.idiag[j];
-      }
-      float* pt = s.PT + ib * BS;
-#pragma unroll
-      for (int j = 0; j < NB; ++j) pt[j * NB + r] = x[j];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) st4(blk + sw4(r, q), make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
-    }
+    panel_solve(s, p, n);
     __syncthreads();
-    // ---- trailing update: C(bi, bj) -= P_bi P_bj^T, one warp per block, 4 x 8 register tile per lane
+    // ---- trailing update: C(bi, bj) -= P_bi P_bj^T, one warp per block, 4 x 8 register tile per lane.
+    // Warp 0 takes the next diagonal block (task 0) and factors it right away while the other warps work
+    // through the remaining tasks.
     const int ntask = tri(n);
-    const int ry = lane >> 2, cx = lane & 3;
-    for (int t = warp; t < ntask; t += NWARPS) {
+    for (int t = (warp == 0 ? 0 : warp); t < ntask; t += (warp == 0 ? ntask : NWARPS - 1)) {
       int ii = 0;
       while (tri(ii + 1) <= t) ++ii;
-      const int jj = t - tri(ii);
-      const float* Pi = s.PT + ii * BS + 4 * ry;
-      const float* Pj = s.PT + jj * BS + 8 * cx;
-      float acc[4][8];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < NB; ++k) {
-        const float4 av = ld4(Pi + k * NB);
-        const float4 b0 = ld4(Pj + k * NB), b1 = ld4(Pj + k * NB + 4);
-        const float ar[4] = {av.x, av.y, av.z, av.w};
-        const float bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(ar[r], bc[c], acc[r][c]);
-      }
-      const int bi = p + 1 + ii, bj = p + 1 + jj;
-      float* blk = s.A + (tri(bi) + bj) * BS;
-      const bool diag = (bi == bj);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = 4 * ry + r;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float* ptr = blk + sw4(row, 2 * cx + h);
-          float4 cur = ld4(ptr);
-          float cv[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = 8 * cx + 4 * h + e;
-            if (!diag || col < row) cv[e] -= acc[r][4 * h + e];
-            else if (col == row) s.dm1[bi * NB + row] -= acc[r][4 * h + e];
-          }
-          st4(ptr, make_float4(cv[0], cv[1], cv[2], cv[3]));
-        }
-      }
+      trailing_task(s, p, ii, t - tri(ii));
+    }
+    if (warp == 0) {
+      __syncwarp();
+      const bool good = chol_diag(s.A + (tri(p + 1) + p + 1) * BS, s.dm1 + (p + 1) * NB, s.idiag);
+      if (lane == 0) *s.flag = good ? 0 : 1;
     }
     __syncthreads();
   }
@@ -210,8 +256,10 @@ __device__ bool chol_blocked(const Smem& s, int nbk) {
 }
 
 // ---- in-place inverse of the blocked lower-triangular factor --------------------------------------------------
-__device__ void inv_blocked(const Smem& s, int nbk) {
+// Returns this thread's share of sum_{i>j} X_ij^2 (the strictly lower part of the inverse).
+__device__ __noinline__ float inv_blocked(const Smem s, int nbk) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float sq = 0.f;
   // diagonal blocks, one warp each: lane c solves for column c of the inverse
   for (int b = warp; b < nbk; b += NWARPS) {
     float* blk = s.A + (tri(b) + b) * BS;
@@ -232,7 +280,10 @@ __device__ void inv_blocked(const Smem& s, int nbk) {
     }
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < NB; ++r) blk[sw(r, lane)] = y[r];
+    for (int r = 0; r < NB; ++r) {
+      blk[sw(r, lane)] = y[r];
+      if (r != lane) sq = fmaf(y[r], y[r], sq);      // y[r] = 0 above the diagonal
+    }
   }
   __syncthreads();
   // column blocks from the right: X_ip = -(sum_{k=p+1..i} X_ik C_kp) X_pp
@@ -295,9 +346,12 @@ __device__ void inv_blocked(const Smem& s, int nbk) {
       float* Xo = s.A + (tri(bi) + p) * BS;
       st4(Xo + sw4(lane, 2 * cq), make_float4(-acc[0], -acc[1], -acc[2], -acc[3]));
       st4(Xo + sw4(lane, 2 * cq + 1), make_float4(-acc[4], -acc[5], -acc[6], -acc[7]));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sq = fmaf(acc[c], acc[c], sq);
     }
     __syncthreads();
   }
+  return sq;
 }
 
 struct KlTerms {
@@ -306,7 +360,7 @@ struct KlTerms {
 };
 
 // Assemble M~, factor, invert, evaluate the KL terms.  On return (ok): A holds X = chol(M~)^-1 and u = M~^-1 h~.
-__device__ KlTerms eval_whitened(const Smem& s, const float* __restrict__ B, const float* __restrict__ B2, float a1,
+__device__ __noinline__ KlTerms eval_whitened(const Smem s, const float* __restrict__ B, const float* __restrict__ B2, float a1,
                                  float a2, int D, int nbk, float inv_eta) {
   const int tid = threadIdx.x;
   const int Dp = nbk * NB;
@@ -321,19 +375,8 @@ __device__ KlTerms eval_whitened(const Smem& s, const float* __restrict__ B, con
   float ld = 0.f;
   for (int j = tid; j < Dp; j += THREADS) ld += log1pf(s.dm1[j]);
   ld = block_sum(ld, s.red);
-  inv_blocked(s, nbk);
   // tr(M^-1) - D = sum_j (-delta_j / (1 + delta_j)) + sum_{i>j} X_ij^2
-  float tr = 0.f;
-  const int nblk = tri(nbk);
-  for (int e = tid; e < nblk * BS; e += THREADS) {
-    const int b = e >> 10, r = (e >> 5) & 31, pc = e & 31;
-    const int c = ((((pc >> 2) ^ (r & 7)) << 2) | (pc & 3));       // logical column of this storage slot
-    int bi = 0;
-    while (tri(bi + 1) <= b) ++bi;
-    const bool is_diag_elem = (b == tri(bi) + bi) && (r == c);
-    const float x = s.A[e];
-    if (!is_diag_elem) tr = fmaf(x, x, tr);
-  }
+  float tr = inv_blocked(s, nbk);
   for (int j = tid; j < Dp; j += THREADS) tr -= s.dm1[j] / (1.f + s.dm1[j]);
   tr = block_sum(tr, s.red);
   // v = X h~ (thread per row), u = X^T v (thread per column)
@@ -383,7 +426,13 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
   __shared__ float red[33];
   __shared__ float idiag[NB];
   __shared__ int flag;
+  __shared__ int blk_bi[MAXBLK * (MAXBLK + 1) / 2];
   const int k = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < MAXBLK * (MAXBLK + 1) / 2) {
+    int bi = 0;
+    while (tri(bi + 1) <= tid) ++bi;
+    blk_bi[tid] = bi;
+  }
   const int nbk = (D + NB - 1) / NB, Dp = nbk * NB;
   Smem s;
   s.A = ub_smem;
@@ -395,6 +444,7 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
   s.idiag = idiag;
   s.red = red;
   s.flag = &flag;
+  s.blk_bi = blk_bi;
   const float* B = Bmat + (long long)k * D * D;
   const float* B2 = (mode == 2) ? B2mat + (long long)k * D * D : nullptr;
   const float* L = chols + (long long)k * D * D;
