@@ -34,7 +34,9 @@ _SIGNATURES = {
                                            c_vp]),
     "gvi_logdens_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, C.c_int, c_f, c_vp]),
     "gvi_mixture_lse_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_vp]),
-    "gvi_mixture_grad_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),
+    "gvi_mixture_grad_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_mixture_grad_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp,
+                                            C.c_size_t, c_vp]),
     "gvi_mixture_grad_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, c_f, c_vp]),
     "gvi_importance_weights_f32": (C.c_int, [c_f, c_f, c_i, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_vp, c_vp]),
     "gvi_row_max_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_vp]),

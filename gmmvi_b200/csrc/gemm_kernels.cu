@@ -151,11 +151,40 @@ logdens_full_kernel(const float* __restrict__ X, int N, int D, const float* __re
 //   grad[n, i] = - sum_k sum_j r_kn (x_nj - mu_kj) P_k[j, i];   grid = (ceil(N/128), ceil(D/64)).
 //   Components whose responsibility is below e^-60 for the whole 128-sample block are skipped.
 // =================================================================================================
+// mask[b][k / 32] bit (k % 32): some sample of the 128-sample block b has responsibility > e^-60 for component k.
+// One warp per 32 samples, warp ballots instead of block-wide barriers; lq is read exactly once, coalesced.
+__global__ void __launch_bounds__(128)
+resp_mask_kernel(const float* __restrict__ lq, const float* __restrict__ logw, const float* __restrict__ logq, int K,
+                 int N, uint32_t* __restrict__ mask) {
+  extern __shared__ uint32_t smask[];
+  const int words = ceil_div(K, 32);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) smask[i] = 0u;
+  __syncthreads();
+  const int n = blockIdx.x * BM + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const float lqn = n < N ? logq[n] : 0.f;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u;
+      a[u] = (n < N && k < K) ? __ldg(lq + (long long)k * N + n) + __ldg(logw + k) - lqn : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const unsigned any = __ballot_sync(0xffffffffu, a[u] > -60.f);
+      if (any && lane == 0) atomicOr(&smask[(k0 + u) >> 5], 1u << ((k0 + u) & 31));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < words; i += blockDim.x) mask[(long long)blockIdx.x * words + i] = smask[i];
+}
+
 __global__ void __launch_bounds__(NTHREADS)
 mixture_grad_full_kernel(const float* __restrict__ X, int N, int D, const float* __restrict__ means,
                          const float* __restrict__ prec, const float* __restrict__ lq,
                          const float* __restrict__ logw, const float* __restrict__ logq, int K,
-                         float* __restrict__ grad, bool vecX, bool vecP) {
+                         const uint32_t* __restrict__ mask, float* __restrict__ grad, bool vecX, bool vecP) {
   __shared__ SmemTiles sm;
   const int n0 = blockIdx.x * BM, i0 = blockIdx.y * BN;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -168,17 +197,20 @@ mixture_grad_full_kernel(const float* __restrict__ X, int N, int D, const float*
     const int n = n0 + rr + 64 * h;
     lqn[h] = n < N ? logq[n] : 0.f;
   }
-  for (int k = 0; k < K; ++k) {
+  const int words = ceil_div(K, 32);
+  const uint32_t* bmask = mask + (long long)blockIdx.x * words;
+  for (int wd = 0; wd < words; ++wd) {
+   uint32_t bits = __ldg(bmask + wd);          // same word in every thread: the loop below is uniform
+   while (bits) {
+    const int k = wd * 32 + (__ffs(bits) - 1);
+    bits &= bits - 1;
     float resp[2];
-    bool any = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int n = n0 + rr + 64 * h;
       const float a = n < N ? (lq[(long long)k * N + n] + logw[k] - lqn[h]) : -INFINITY;
       resp[h] = a > -60.f ? expf(a) : 0.f;
-      any |= resp[h] > 0.f;
     }
-    if (!__syncthreads_or(any)) continue;
     const float* mu = means + (long long)k * D;
     const float* Pk = prec + (long long)k * D * D;
     auto fA = [&](int c, float (&r)[8]) {
@@ -196,6 +228,7 @@ mixture_grad_full_kernel(const float* __restrict__ X, int N, int D, const float*
     auto fB = [&](int c, float (&r)[4]) { fetchB_rcontig(Pk, D, D, D, i0, c * BK, vecP, r); };
     auto sB = [&](float (*Bs)[BS_LD], const float (&r)[4]) { storeB_rcontig(Bs, r); };
     tile_mainloop(acc, sm, 0, ceil_div(D, BK), ty, tx, fA, sA, fB, sB);
+   }
   }
 #pragma unroll
   for (int r = 0; r < TM; ++r) {
@@ -466,15 +499,29 @@ extern "C" int gvi_logdens_full_f32(const float* X, int N, int D, const float* m
   return launch_logdens_full(X, N, D, means, linv, cst, K, lq, (cudaStream_t)stream);
 }
 
+extern "C" size_t gvi_mixture_grad_full_workspace(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return (size_t)ceil_div(N, BM) * ceil_div(K, 32) * sizeof(uint32_t);
+}
+
 extern "C" int gvi_mixture_grad_full_f32(const float* X, int N, int D, const float* means, const float* prec,
                                          const float* lq, const float* logw, const float* logq, int K, float* grad,
-                                         void* stream) {
+                                         void* ws, size_t ws_bytes, void* stream) {
   GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_mixture_grad_full_f32: bad sizes");
   if (N == 0) return GVI_OK;
-  GVI_REQUIRE(X && means && prec && lq && logw && logq && grad, "gvi_mixture_grad_full_f32: null pointer");
+  GVI_REQUIRE(X && means && prec && lq && logw && logq && grad && ws, "gvi_mixture_grad_full_f32: null pointer");
+  if (ws_bytes < gvi_mixture_grad_full_workspace(N, K)) {
+    set_last_error("gvi_mixture_grad_full_f32: workspace %zu < %zu", ws_bytes, gvi_mixture_grad_full_workspace(N, K));
+    return GVI_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* mask = (uint32_t*)ws;
+  resp_mask_kernel<<<ceil_div(N, BM), 128, ceil_div(K, 32) * sizeof(uint32_t), st>>>(lq, logw, logq, K, N, mask);
+  int rc = check_launch("resp_mask_kernel");
+  if (rc) return rc;
   dim3 grid(ceil_div(N, BM), ceil_div(D, BN));
-  mixture_grad_full_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(X, N, D, means, prec, lq, logw, logq, K,
-                                                                       grad, ptr_vec_ok(X, D), ptr_vec_ok(prec, D));
+  mixture_grad_full_kernel<<<grid, NTHREADS, 0, st>>>(X, N, D, means, prec, lq, logw, logq, K, mask, grad,
+                                                      ptr_vec_ok(X, D), ptr_vec_ok(prec, D));
   return check_launch("mixture_grad_full_kernel");
 }
 

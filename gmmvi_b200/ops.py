@@ -214,8 +214,10 @@ def mixture_grad_full(X, means, prec, lq, logw, logq):
     N, D = X.shape
     K = means.shape[0]
     grad = torch.empty_like(X)
+    nbytes = _lib.lib().gvi_mixture_grad_full_workspace(N, K)
+    ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.int32)
     _call("gvi_mixture_grad_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), lq.data_ptr(),
-          logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), _stream())
+          logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), ws.data_ptr(), nbytes, _stream(), kernels=2)
     return grad
 
 

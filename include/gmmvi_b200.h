@@ -75,8 +75,10 @@ int gvi_logdens_diag_f32(const float* X, int N, int D, const float* means, const
 int gvi_mixture_lse_f32(const float* lq, const float* logw, int K, int N, float* out, void* stream);
 /* grad[n,:] = -sum_k r_kn Sigma_k^-1 (x_n - mu_k), r = exp(lq + logw - logq): the analytic form of the
  * GradientTape in models/gmm.py:294-300.  prec = linv^T linv from gvi_prepare_full_f32. */
+size_t gvi_mixture_grad_full_workspace(int N, int K);   /* bit mask of the components each 128-sample block touches */
 int gvi_mixture_grad_full_f32(const float* X, int N, int D, const float* means, const float* prec, const float* lq,
-                              const float* logw, const float* logq, int K, float* grad, void* stream);
+                              const float* logw, const float* logq, int K, float* grad, void* ws, size_t ws_bytes,
+                              void* stream);
 int gvi_mixture_grad_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* lq,
                               const float* logw, const float* logq, int K, float* grad, void* stream);
 
