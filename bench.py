@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 K_COMP, DIM, PER_COMP = 512, 256, 128
 TARGET_COMPONENTS = 10
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+# captures (profiles/r01_ncu_*.txt), keyed by (kernel kind, K, D, samples per launch); other shapes report null
+NCU_DRAM_TRAFFIC = {("h16", 512, 256, 65536): 1.847489e9 + 138.376448e6}
 PRIOR_SCALE = 31.63          # configs/experiment_configs/gmm100.yml:11 (GMM-target experiments)
 
 
@@ -337,7 +340,10 @@ def run_ours(args):
                    "kl_evaluations_per_component": kl_evals_stats},
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                     "frac": achieved / tc_peak, "traffic": None,
+                     "frac": achieved / tc_peak,
+                     "traffic": NCU_DRAM_TRAFFIC.get((kind, K, D, int(X.shape[0]))),
+                     "traffic_source": "profiles/r01_ncu_h16_logdens.txt (bytes per launch)",
+                     "algorithmic_bytes": 4.0 * (X.shape[0] * D + 2 * K * D * D // 2 + K * X.shape[0]),
                      "kernel": ops.logdens_kernel_name(D), "launch_ms": ld_ms,
                      "algorithmic_flop_per_pair": D * D + 4 * D,
                      "executed_mma_flop_per_pair": mma_flop_pair,
