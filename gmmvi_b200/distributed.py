@@ -5,9 +5,12 @@ Partitioning: the iteration's global sample index space [
 from the counter-based generator (value depends only on the global row), evaluates log-densities / target /
 gradients for them, and contributes partial per-component sums.  Exchange steps:
   * importance-weight normalisers: all-reduce MAX [K] + 2 x all-reduce SUM [K]
-  * Stein statistics: all-reduce SUM of (-E[H]) [K,D,D] and (-E[g]) [K,D]
+  * Stein statistics (-E[H]) [K,D,D] and (-E[g]) [K,D]: reduce-scatter by component when K divides evenly (the
+    component update only needs its own shard), all-reduce otherwise
   * expected log-ratios for the weight update: all-reduce SUM [K]
-  * component update: components are sharded K/world per rank, the new (mean, Cholesky) are all-gathered.
+  * component update: components are sharded K/world per rank, the new (mean, Cholesky) are all-gathered; the
+    gathers of the Cholesky factors and of the precisions run asynchronously and are only waited for at their
+    first use (next sampling step / next gradient), overlapping the weight-update log-density pass.
 Model parameters and all O(K) learner state are replicated and stay bit-identical on every rank because every
 collective returns the same bits to all ranks."""
 from __future__ import annotations
@@ -39,6 +42,25 @@ class ShardContext:
             return local
         out = torch.empty((total_rows,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
         dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    def all_gather_rows_async(self, local: torch.Tensor, total_rows: int):
+        """Like all_gather_rows, but returns (out, work): the caller must `work.wait()` (a stream dependency, not a
+        host block) before the first use of `out`; `work` is None when nothing is in flight."""
+        if self.world == 1:
+            return local, None
+        out = torch.empty((total_rows,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=self.group, async_op=True)
+        return out, work
+
+    def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
+        """Sum `full` [rows, ...] over the ranks and return this rank's equal row block [rows / world, ...]."""
+        if self.world == 1:
+            return full
+        rows = full.shape[0]
+        assert rows % self.world == 0
+        out = torch.empty((rows // self.world,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype)
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
         return out
 
     # ---- index arithmetic (pure host logic; covered by the gloo tests) ----------------------------------

@@ -27,7 +27,7 @@ class StudentTMixture_LNPDF(LNPDF):
     def _component_terms(self, x):
         g = self._g
         x = x.to(torch.float32).contiguous()
-        _, _, cst = g.prepared()
+        _, _, cst = g.prepared(need_prec=False)
         lq = g.component_log_densities(x)                       # cst_j - m_j / 2
         D, nu = g.num_dimensions, float(self.alpha)
         logdet_part = cst + 0.5 * D * log(2 * pi)               # - sum log diag L_j

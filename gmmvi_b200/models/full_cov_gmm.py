@@ -44,7 +44,7 @@ class FullCovGMM(GMM):
 
     def component_log_density(self, index: int, samples: torch.Tensor) -> torch.Tensor:
         """models/full_cov_gmm.py:41-47."""
-        linv, _, cst = self.prepared()
+        linv, _, cst = self.prepared(need_prec=False)
         i = int(index)
         return ops.logdens_full(samples, self.means[i:i + 1].contiguous(), linv[i:i + 1].contiguous(),
                                 cst[i:i + 1].contiguous())[0]
@@ -59,7 +59,7 @@ class FullCovGMM(GMM):
 
     def component_log_densities(self, samples: torch.Tensor) -> torch.Tensor:
         """models/full_cov_gmm.py:56-62 -> [K, N]."""
-        linv, _, cst = self.prepared()
+        linv, _, cst = self.prepared(need_prec=False)
         return ops.logdens_full(samples, self.means, linv, cst)
 
     def _mixture_grad(self, samples, lq, logq, logw=None, index=None):

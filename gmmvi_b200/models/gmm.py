@@ -27,6 +27,9 @@ class GMM:
         self._version = 0
         self.shard = None              # gmmvi_b200.distributed.ShardContext when samples are sharded over GPUs
         self._prepared = None          # (version, linv, prec, cst) for full covariances
+        self._prec_work = None         # in-flight all-gather of prec (sharded runs)
+        self._chol_work = None         # in-flight all-gather of chol_cov (sharded component update)
+        self._local_chol = None        # (version, a, b, chol[a:b]) of the most recent sharded update
         self.log_weights = log_weights
         self._means = means
         self._chol_cov = chol_covs
@@ -44,30 +47,61 @@ class GMM:
 
     @property
     def chol_cov(self) -> torch.Tensor:
+        if self._chol_work is not None:          # asynchronous all-gather of the sharded update: first use waits
+            self._chol_work.wait()
+            self._chol_work = None
         return self._chol_cov
 
     @chol_cov.setter
     def chol_cov(self, v):
+        if self._chol_work is not None:
+            self._chol_work.wait()
+        self._chol_work = None
+        self._local_chol = None
         self._chol_cov = v
         self._version += 1
+
+    def set_components_sharded(self, new_means, chol_full, chol_work, a, b, chol_local):
+        """Result of a component-sharded update: `chol_full` is still being all-gathered (`chol_work`), the rows
+        [a, b) this rank computed itself are available at once (they feed the sharded `prepared()`)."""
+        self.means = new_means.contiguous()
+        self.chol_cov = chol_full
+        self._chol_work = chol_work
+        self._local_chol = (self._version, a, b, chol_local)
 
     @property
     def device(self):
         return self._means.device
 
-    def prepared(self):
+    def prepared(self, need_prec: bool = True):
         """(linv, prec, cst): inverse Cholesky factors, precisions and log-normalisers of the current
-        full-covariance components (one `gvi_prepare_full_f32` per parameter change)."""
+        full-covariance components (one `gvi_prepare_full_f32` per parameter change).  In sharded runs every rank
+        prepares its own components and the results are all-gathered; the gather of `prec` is asynchronous and only
+        waited for when a caller asks for it (`need_prec`)."""
         if self._prepared is None or self._prepared[0] != self._version:
             rng_ = self.shard.component_range(self.num_components) if self.shard is not None else None
+            if self._prec_work is not None:
+                self._prec_work.wait()
+                self._prec_work = None
             if rng_ is None:
-                linv, prec, cst, _ = ops.prepare_full(self._chol_cov, want_prec=True)
+                linv, prec, cst, _ = ops.prepare_full(self.chol_cov, want_prec=True)
             else:       # components sharded over the ranks, derived operands all-gathered
                 a, b = rng_
                 K = self.num_components
-                parts = ops.prepare_full(self._chol_cov[a:b].contiguous(), want_prec=True)[:3]
-                linv, prec, cst = (self.shard.all_gather_rows(p, K) for p in parts)
+                lc = self._local_chol
+                if lc is not None and lc[0] == self._version and (lc[1], lc[2]) == (a, b):
+                    mine = lc[3]
+                else:
+                    mine = self.chol_cov[a:b].contiguous()
+                l_loc, p_loc, c_loc = ops.prepare_full(mine, want_prec=True)[:3]
+                linv = self.shard.all_gather_rows(l_loc, K)
+                cst = self.shard.all_gather_rows(c_loc, K)
+                prec, self._prec_work = self.shard.all_gather_rows_async(p_loc, K)
+                self._prec_keep = p_loc
             self._prepared = (self._version, linv, prec, cst)
+        if need_prec and self._prec_work is not None:
+            self._prec_work.wait()
+            self._prec_work = None
         return self._prepared[1:]
 
     # ---- abstract per-family pieces ---------------------------------------------------------------

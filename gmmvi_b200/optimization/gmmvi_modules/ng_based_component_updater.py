@@ -48,9 +48,13 @@ class NgBasedComponentUpdater:
                 self._mode, m.diagonal_covs, sl(m.means), sl(m.chol_cov), sl(expected_hessians_neg),
                 sl(expected_gradients_neg), sl(stepsizes), sl(m.last_log_etas), sl(m.num_received_updates),
                 self.temperature)
-            means, chols, succ, etas, kls = (shard.all_gather_rows(p, K) for p in parts)
+            means, succ, etas, kls = (shard.all_gather_rows(parts[i], K) for i in (0, 2, 3, 4))
+            chols, chol_work = shard.all_gather_rows_async(parts[1], K)
         self.last_success, self.last_kls, self.last_etas = succ, kls, etas
-        m.replace_components(means, chols)
+        if rng_ is None:
+            m.replace_components(means, chols)
+        else:
+            m.set_components_sharded(means, chols, chol_work, rng_[0], rng_[1], parts[1])
         m.num_received_updates = m.num_received_updates + 1.0
         l2 = m.l2_regularizers                                            # quirk 11, :135-138
         m.l2_regularizers = torch.where(succ.bool(),

@@ -42,7 +42,7 @@ class SampleSelector:
         raise NotImplementedError
 
     def _prepared(self):
-        return None if self.model.diagonal_covs else self.model.prepared()
+        return None if self.model.diagonal_covs else self.model.prepared(need_prec=False)
 
 
 class VipsSampleSelector(SampleSelector):
