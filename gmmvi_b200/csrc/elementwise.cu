@@ -264,21 +264,36 @@ prepare_blocked_kernel(const float* __restrict__ chol, int D, int nb, float* __r
 // =================================================================================================
 // mixture logsumexp over components: out[n] = LSE_k(lq[k,n] + logw[k])
 // =================================================================================================
-__global__ void mixture_lse_kernel(const float* __restrict__ lq, const float* __restrict__ logw, int K, int N,
-                                   float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// 64 samples per CTA x 4 interleaved slices of the component range (online max / sum per slice, merged through
+// shared memory): 4 x the parallelism of a thread per sample, which matters for sharded runs with few samples per GPU.
+__global__ void __launch_bounds__(256)
+mixture_lse_kernel(const float* __restrict__ lq, const float* __restrict__ logw, int K, int N, float* __restrict__ out) {
+  __shared__ float sm_m[4][64], sm_s[4][64];
+  const int sx = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int n = blockIdx.x * 64 + sx;
   float m = -INFINITY, s = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float v = lq[(long long)k * N + n] + __ldg(logw + k);
-    if (v > m) {
-      s = s * expf(m - v) + 1.f;   // m == -inf -> s*0
-      m = v;
-    } else if (v > -INFINITY) {
-      s += expf(v - m);
+  if (n < N) {
+    for (int k = sl; k < K; k += 4) {
+      const float v = __ldg(lq + (long long)k * N + n) + __ldg(logw + k);
+      if (v > m) {
+        s = s * expf(m - v) + 1.f;   // m == -inf -> s*0
+        m = v;
+      } else if (v > -INFINITY) {
+        s += expf(v - m);
+      }
     }
   }
-  out[n] = (m > -INFINITY) ? m + logf(s) : -INFINITY;
+  sm_m[sl][sx] = m;
+  sm_s[sl][sx] = s;
+  __syncthreads();
+  if (sl == 0 && n < N) {
+    float mm = fmaxf(fmaxf(sm_m[0][sx], sm_m[1][sx]), fmaxf(sm_m[2][sx], sm_m[3][sx]));
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (sm_m[i][sx] > -INFINITY) ss += sm_s[i][sx] * expf(sm_m[i][sx] - mm);
+    out[n] = (mm > -INFINITY) ? mm + logf(ss) : -INFINITY;
+  }
 }
 
 // =================================================================================================
@@ -731,7 +746,7 @@ extern "C" int gvi_mixture_lse_f32(const float* lq, const float* logw, int K, in
   GVI_REQUIRE(K >= 0 && N >= 0, "gvi_mixture_lse_f32: bad sizes");
   if (N == 0) return GVI_OK;
   GVI_REQUIRE(lq && logw && out, "gvi_mixture_lse_f32: null pointer");
-  mixture_lse_kernel<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(lq, logw, K, N, out);
+  mixture_lse_kernel<<<ceil_div(N, 64), 256, 0, (cudaStream_t)stream>>>(lq, logw, K, N, out);
   return check_launch("mixture_lse_kernel");
 }
 

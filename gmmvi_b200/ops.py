@@ -262,28 +262,46 @@ def importance_weights_sharded(lq, bg, shard, self_normalized=True, rho=None, wa
     f = lambda: torch.empty(K, device=dev, dtype=torch.float32)
     m = f()
     _call("gvi_row_max_f32", lq.data_ptr(), bg.data_ptr(), K, N, m.data_ptr(), _stream())
-    shard.all_reduce_max_(m)
-    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
-    if self_normalized:
-        s = f()
-        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, m.data_ptr(), s.data_ptr(), _stream())
-        shard.all_reduce_sum_(s)
-        lse = (m + torch.log(s)).contiguous()
-        s2 = f()
-        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), s2.data_ptr(), _stream())
-        shard.all_reduce_sum_(s2)
-        scale = (1.0 / s2).contiguous()
-    else:
-        import math
-        lse = torch.full((K,), math.log(float(n_total)), device=dev, dtype=torch.float32)
-        scale = None
     W = torch.empty((K, N), device=dev, dtype=torch.float32) if want_W else None
     dot = f() if want_dot else None
     active = torch.empty((K, (N + 127) // 128), device=dev, dtype=torch.uint8) if want_active else None
-    _call("gvi_importance_weights_ext_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), _ptr(scale),
-          m.data_ptr(), _ptr(rho), _ptr(W), _ptr(dot), _ptr(active), _stream())
-    if dot is not None:
-        shard.all_reduce_sum_(dot)
+    if self_normalized:
+        # One all-gather of the per-rank (max, sum of exponentials) pairs replaces the MAX and the first SUM
+        # all-reduce: every rank merges the pairs itself (same bits everywhere).
+        m_safe = torch.where(torch.isfinite(m), m, torch.zeros_like(m)).contiguous()    # rows without a finite entry
+        s = f()
+        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, m_safe.data_ptr(), s.data_ptr(), _stream())
+        pairs = shard.all_gather_rows(torch.stack([m, m_safe, s]).unsqueeze(0).contiguous(), shard.world)  # [P, 3, K]
+        m = pairs[:, 0].max(dim=0).values
+        m = torch.where(torch.isfinite(m), m, torch.zeros_like(m)).contiguous()
+        term = torch.where(pairs[:, 2] > 0, pairs[:, 2] * torch.exp(pairs[:, 1] - m), torch.zeros_like(pairs[:, 2]))
+        lse = (m + torch.log(term.sum(dim=0))).contiguous()
+        s2 = f()
+        _call("gvi_row_sumexp_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), s2.data_ptr(), _stream())
+        if want_W or not want_dot:
+            shard.all_reduce_sum_(s2)
+            scale = (1.0 / s2).contiguous()
+            _call("gvi_importance_weights_ext_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(),
+                  scale.data_ptr(), m.data_ptr(), _ptr(rho), _ptr(W), _ptr(dot), _ptr(active), _stream())
+            if dot is not None:
+                shard.all_reduce_sum_(dot)
+        else:
+            # only the expected log-ratios are wanted: the second normaliser (the reference normalises twice) and
+            # the un-normalised dot products travel in ONE all-reduce
+            _call("gvi_importance_weights_ext_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), None,
+                  m.data_ptr(), _ptr(rho), None, dot.data_ptr(), _ptr(active), _stream())
+            both = torch.stack([s2, dot]).contiguous()
+            shard.all_reduce_sum_(both)
+            dot = (both[1] / both[0]).contiguous()
+    else:
+        import math
+        shard.all_reduce_max_(m)
+        m = torch.where(torch.isfinite(m), m, torch.zeros_like(m)).contiguous()
+        lse = torch.full((K,), math.log(float(n_total)), device=dev, dtype=torch.float32)
+        _call("gvi_importance_weights_ext_f32", lq.data_ptr(), bg.data_ptr(), K, N, lse.data_ptr(), None,
+              m.data_ptr(), _ptr(rho), _ptr(W), _ptr(dot), _ptr(active), _stream())
+        if dot is not None:
+            shard.all_reduce_sum_(dot)
     return dict(W=W, dot=dot, ess=None, active=active)
 
 
