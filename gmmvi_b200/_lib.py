@@ -42,7 +42,7 @@ _SIGNATURES = {
     "gvi_row_max_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_vp]),
     "gvi_row_sumexp_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_vp]),
     "gvi_importance_weights_ext_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_vp, c_vp]),
-    "gvi_stein_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_stein_full_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gvi_stein_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_vp, c_f, C.c_int, C.c_int, c_f, c_f,
                                      c_vp, C.c_size_t, c_vp]),
     "gvi_stein_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_vp]),

@@ -2,6 +2,7 @@
 // weight updates and the counter-based normal generator.  Everything here is bandwidth- or
 // latency-bound; no tensor-core work.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/gmmvi_b200.h"
 #include <stdarg.h>
 #include <stdio.h>
@@ -33,6 +34,10 @@ int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
 size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
+bool stein_tc_supported(int N, int D);
+size_t stein_tc_workspace_floats(int N, int K, int D);
+int launch_stein_stats_tc(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
+                          const float* G, int K, float* M, float* ws, cudaStream_t st);
 
 // =================================================================================================
 // prepare_full: one CTA per component, fp64 arithmetic, thread-per-column forward substitution.
@@ -836,9 +841,22 @@ extern "C" int gvi_importance_weights_ext_f32(const float* lq, const float* bg, 
   return check_launch("importance_weights_ext_kernel");
 }
 
-extern "C" size_t gvi_stein_full_workspace(int K, int D) {
+static bool stein_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GMMVI_B200_TC_STEIN");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static size_t stein_base_floats(int K, int D) {
+  return ((size_t)2 * K * D * D + tc_gemm_workspace_floats(K, D, D, D) + 63) / 64 * 64;
+}
+extern "C" size_t gvi_stein_full_workspace(int N, int K, int D) {
   if (K <= 0) return 0;
-  return ((size_t)2 * K * D * D + tc_gemm_workspace_floats(K, D, D, D)) * sizeof(float);
+  size_t f = stein_base_floats(K, D);
+  if (N > 0 && stein_tc_supported(N, D)) f += stein_tc_workspace_floats(N, K, D);
+  return f * sizeof(float);
 }
 extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec,
                                   const float* W, const uint8_t* active, const float* G, int K, int symmetrize,
@@ -847,14 +865,18 @@ extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* mea
   if (K == 0) return GVI_OK;
   GVI_REQUIRE(X && means && prec && W && G && Hneg && gneg && ws, "gvi_stein_full_f32: null pointer");
   GVI_REQUIRE(K <= 65535, "gvi_stein_full_f32: K=%d exceeds 65535", K);
-  if (ws_bytes < gvi_stein_full_workspace(K, D)) {
-    set_last_error("gvi_stein_full_f32: workspace %zu < %zu", ws_bytes, gvi_stein_full_workspace(K, D));
+  if (ws_bytes < gvi_stein_full_workspace(N, K, D)) {
+    set_last_error("gvi_stein_full_f32: workspace %zu < %zu", ws_bytes, gvi_stein_full_workspace(N, K, D));
     return GVI_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* M = (float*)ws;
   float* T = M + (size_t)K * D * D;
-  int rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
+  int rc;
+  if (N > 0 && stein_tc_supported(N, D) && stein_tc_enabled())
+    rc = launch_stein_stats_tc(X, N, D, means, W, active, G, K, M, (float*)ws + stein_base_floats(K, D), st);
+  else
+    rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
   if (rc) return rc;
   {
     dim3 gg(ceil_div(D, 256), K);

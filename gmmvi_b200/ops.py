@@ -18,7 +18,7 @@ KERNELS = 0    # number of CUDA kernels those calls launched (bench.py's "gpu_la
 
 # kernels launched per C-ABI call (memsets are not counted)
 _KERNELS_PER_CALL = {
-    "gvi_stein_full_f32": 4,          # stein_stats + bgemm(gneg) + bgemm(P M) + finalize
+    "gvi_stein_full_f32": 12,         # absmax x2, rowmax x2, transposes x2, stein_tc, gsum, split x2 + bgemm(P M), finalize
 }
 
 
@@ -313,7 +313,7 @@ def stein_full(X, means, prec, W, active, G, symmetrize=True):
     K = means.shape[0]
     Hneg = torch.empty((K, D, D), device=X.device, dtype=torch.float32)
     gneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
-    nbytes = _lib.lib().gvi_stein_full_workspace(K, D)
+    nbytes = _lib.lib().gvi_stein_full_workspace(N, K, D)
     ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.float32)
     _call("gvi_stein_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), W.data_ptr(), _ptr(active),
           G.data_ptr(), K, int(bool(symmetrize)), Hneg.data_ptr(), gneg.data_ptr(), ws.data_ptr(), nbytes, _stream())

@@ -106,8 +106,10 @@ int gvi_importance_weights_ext_f32(const float* lq, const float* bg, int K, int 
 /* ---- Stein natural-gradient statistics ---------------------------------------------------------
  * M[k] = sum_n W[k,n] (x_n-mu_k) G[n,:]^T  (D x D),  gneg[k] = -sum_n W[k,n] G[n,:]
  * then Hneg[k] = -sym(prec_k M[k]) (symmetrize=1, ng_estimator.py:183-187) or -(prec_k M[k])^T
- * (symmetrize=0, :164-168).  `active` (nullable) is the block mask from gvi_importance_weights_f32. */
-size_t gvi_stein_full_workspace(int K, int D);
+ * (symmetrize=0, :164-168).  `active` (nullable) is the block mask from gvi_importance_weights_f32.
+ * For 16 <= D <= 256 the [D x N] . [N x D] reduction runs on the tcgen05 tensor cores (2 x fp16 split precision,
+ * weights and centring fused into the operand producer, accumulator drained with round-to-nearest adds). */
+size_t gvi_stein_full_workspace(int N, int K, int D);
 int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec, const float* W,
                        const uint8_t* active, const float* G, int K, int symmetrize, float* Hneg, float* gneg,
                        void* ws, size_t ws_bytes, void* stream);

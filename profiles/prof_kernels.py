@@ -40,6 +40,18 @@ elif which == "logdens_tf32":
     timed(lambda: ops.logdens_full(X, means, linv, cst, memo=False, tensor_cores="tf32"))
 elif which == "logdens_simt":
     timed(lambda: ops.logdens_full(X, means, linv, cst, memo=False, tensor_cores=False))
+elif which in ("stein", "stein_simt"):
+    if which == "stein_simt":
+        os.environ["GMMVI_B200_TC_STEIN"] = "0"
+    # dense case: every sample carries weight for every component
+    Nd = 16384
+    Wd = torch.rand((K, Nd), device="cuda", generator=g)
+    Wd = (Wd / Wd.sum(1, keepdim=True)).contiguous()
+    act = torch.ones((K, Nd // 128), device="cuda", dtype=torch.uint8)
+    Gd = torch.randn((Nd, D), device="cuda", generator=g).contiguous()
+    Xd = X[:Nd].contiguous()
+    timed(lambda: ops.stein_full(Xd, means, prec, Wd, act, Gd, True))
+    print("dense Stein: K=%d D=%d N=%d -> %.2f TFLOP algorithmic (2 D^2 per pair)" % (K, D, Nd, 2.0 * D * D * K * Nd / 1e12))
 elif which == "prepare":
     timed(lambda: ops.prepare_full(chol))
 elif which == "update":
