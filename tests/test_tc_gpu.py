@@ -106,3 +106,38 @@ def test_tc_bgemm(ta, tb, b, M, N, Kd):
     simt = ops.bgemm(dev(A), dev(B), ta, tb, 0.5, tensor_cores=False)
     assert rel_err(simt.cpu().numpy(), 0.5 * ref) < 1e-5
     assert rel_err(out.cpu().numpy(), 0.5 * ref) < 5e-6, rel_err(out.cpu().numpy(), 0.5 * ref)
+
+
+@pytest.mark.parametrize("K,D,N,dense", [(2, 256, 5000, True), (3, 100, 4500, True), (150, 64, 700, True),
+                                          (5, 48, 3000, False), (2, 200, 2600, False)])
+def test_tc_stein_stats(K, D, N, dense):
+    """tcgen05 Stein statistics against an fp64 einsum: several drains of the TMEM accumulator per component
+    (N > 2048 per work unit), split block ranges (K < #SMs), padded D, and skipped blocks (`dense=False`)."""
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(900 + D)
+    X = (rng.standard_normal((N, D)) * 3 + rng.standard_normal(D) * 20).astype(np.float32)
+    means = (rng.standard_normal((K, D)) * 20).astype(np.float32)
+    G = rng.standard_normal((N, D)).astype(np.float32)
+    W = rng.random((K, N)).astype(np.float32) ** 4
+    act = np.ones((K, (N + 127) // 128), np.uint8)
+    if not dense:          # zero the weight of whole 128-sample blocks and mark them inactive
+        for k in range(K):
+            off = rng.random(act.shape[1]) < 0.6
+            off[k % act.shape[1]] = False
+            act[k, off] = 0
+            for b in np.nonzero(off)[0]:
+                W[k, b * 128:(b + 1) * 128] = 0.0
+    W = (W / W.sum(1, keepdims=True)).astype(np.float32)
+    A = rng.standard_normal((K, D, D))
+    prec = (A @ A.transpose(0, 2, 1) / D + np.eye(D)).astype(np.float32)
+    Hneg, gneg = ops.stein_full(dev(X), dev(means), dev(prec), dev(W), dev(act, torch.uint8), dev(G), True)
+    X64, W64, G64 = X.astype(np.float64), W.astype(np.float64), G.astype(np.float64)
+    M = np.einsum("kn,knj,ni->kji", W64, X64[None] - means.astype(np.float64)[:, None], G64)
+    T = prec.astype(np.float64) @ M
+    Href = -0.5 * (T + T.transpose(0, 2, 1))
+    gref = -(W64 @ G64)
+    assert rel_err(Hneg.cpu().numpy(), Href) < 1e-4, rel_err(Hneg.cpu().numpy(), Href)
+    assert rel_err(gneg.cpu().numpy(), gref) < 1e-4
+    # bitwise reproducible
+    H2, _ = ops.stein_full(dev(X), dev(means), dev(prec), dev(W), dev(act, torch.uint8), dev(G), True)
+    assert torch.equal(Hneg, H2)
