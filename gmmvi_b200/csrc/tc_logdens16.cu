@@ -32,6 +32,8 @@
 // Register budget by setmaxnreg: control warps 48, epilogue 80, producers 88 (the pool is the launch allocation, 80 x 768).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace gvi {
 namespace h16 {
@@ -461,6 +463,362 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =====================================================================================================
+// Variant with the A operand in TENSOR MEMORY (default for Dp >= 128).
+//
+// ncu on the kernel above: the tensor pipe is active 54 % of the time and the shared-memory port is the limiter -- per
+// work item the MMAs fetch 192 KB of A and 209 KB of B from shared memory and the producers store another 128 KB, and
+// an SS MMA with N < 128 is bound by its operand fetch (4 KB of A + 32 N bytes of B at 128 B/clk; measured with
+// tools/probe_tmem.cu: 48 cycles at N = 64 where the math needs 32).  Here the producers write the split (x - mu) tile
+// straight into TMEM (tcgen05.st.16x256b: four lanes hold one row's 16 fp16 values, which is exactly one float4 of
+// the fp32 source per lane) and the MMAs take A from there, so shared memory only serves the resident factor.
+//
+// TMEM (512 columns): [0, 256) ring of 8 A stages (32 K-columns each; per 16-column K-step 8 columns of packed hi, 8 of lo);
+// [256, 384) and [384, 512) two accumulators of Dp/2 <= 128 columns.  A work item is issued as two sub-items so that
+// the accumulators stay double buffered: first the output columns [0, Dp/2) (K-steps j < Dp/2 only, triangular), then
+// [Dp/2, Dp) (all K-steps); the epilogue adds the two partial row sums.  An A stage is released after its second use.
+//
+// Producers: 16 warps = 4 groups of 4 warps (one per TMEM lane quadrant); group g converts the stages g, g + 4, ... of
+// the global stage sequence.  Thread t of a warp owns rows t/4 + 8 a (a = 0..3) of its quadrant and the float4 columns
+// t%4 and t%4 + 4 of the stage, i.e. a warp-wide load covers 8 rows x 64 contiguous bytes.
+namespace h16t {
+using namespace h16;
+
+constexpr int RING = 8;
+constexpr int ACC0 = 256, ACC1 = 384;
+
+struct BarriersT {
+  uint64_t full[RING];
+  uint64_t empty[RING];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t b_full;
+  uint64_t b_free;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 lanes x 16 columns: registers 4 i .. 4 i + 3 are the i-th 16x256b block (columns 8 i .. 8 i + 7); inside a block
+// thread t holds (row t/4, columns 2 (t%4), +1) in registers 0, 1 and (row t/4 + 8, same columns) in registers 2, 3
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// The tcgen05.mma of one sub-item (SUB = 0: output columns [0, Dp/2), SUB = 1: [Dp/2, Dp)) of one work item, fully
+// unrolled for NST = Dp / 32 stages so that every operand offset, N and accumulator column is an immediate.  The
+// issuing warp's instruction stream is the critical path of the kernel: the MMA queue is shallow (the issuing thread
+// blocks in UTCHMMA almost in lock step with the execution: tools/probe_tmem.cu T4), so whatever scalar work sits
+// between two stages is exposed whenever the queued MMAs are short.  Hence (a) immediates instead of ~150 dependent
+// scalar instructions per stage, and (b) one issuing warp per sub-item: the two accumulators are independent, which
+// also hides the ~40-cycle latency between dependent small MMAs on one accumulator.
+template <int NST, int SUB>
+__device__ __forceinline__ void mma_sub_item(uint32_t tmem_base, BarriersT* bars, uint32_t g0, uint32_t it,
+                                             uint64_t bhi_desc0, uint64_t blo_desc0, bool last_of_k) {
+  constexpr int Dp = 32 * NST, H = 16 * NST;
+  constexpr int ns = SUB == 0 ? NST / 2 : NST;
+  // keep the operand addresses of an item out of registers: they are re-derived (one add with an immediate each)
+  // instead of being hoisted out of the item loop
+  asm volatile("" : "+l"(bhi_desc0), "+l"(blo_desc0), "+r"(tmem_base));
+  mbar_wait_sleepy(&bars->acc_empty[SUB], (it & 1u) ^ 1u);
+  tc_fence_after();
+  const uint32_t acc = tmem_base + (uint32_t)(SUB == 0 ? ACC0 : ACC1);
+#pragma unroll
+  for (int si = 0; si < ns; ++si) {
+    const uint32_t g = g0 + (uint32_t)si;
+    const uint32_t slot = NST == RING ? (uint32_t)si : (g & (RING - 1));
+    const uint32_t par = NST == RING ? (it & 1u) : ((g >> 3) & 1u);
+    mbar_wait_fast(smem_u32(&bars->full[slot]), par);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t a0 = tmem_base + slot * 32u;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int c = 2 * si + ks;                 // K-step: columns 16 c .. 16 c + 15 of Linv
+        const int kb = c >> 2, kq = c & 3;
+        const int n = SUB == 0 ? H - 16 * c : (c < NST ? H : Dp - 16 * c);
+        const int i0 = SUB == 0 ? 16 * c : (c < NST ? H : 16 * c);
+        const int dcol = SUB == 0 ? 16 * c : (c < NST ? 0 : 16 * c - H);
+        const uint32_t idesc = make_idesc_f16(n);
+        const uint32_t d_tmem = acc + (uint32_t)dcol;
+        const uint32_t a_hi = a0 + (uint32_t)(ks * 16);
+        const uint32_t a_lo = a_hi + 8u;
+        // descriptor start-address fields are in 16-byte units (smem < 256 KB)
+        const uint64_t boffk = (uint64_t)((uint32_t)(block_row_offset(Dp, kb) + i0 - KB * kb) * 8u + (uint32_t)(kq * 2));
+        const uint64_t bd_hi = bhi_desc0 + boffk, bd_lo = blo_desc0 + boffk;
+        umma_f16_ts(d_tmem, a_hi, bd_hi, idesc, c != 0 ? 1u : 0u);
+        umma_f16_ts(d_tmem, a_lo, bd_hi, idesc, 1u);
+        umma_f16_ts(d_tmem, a_hi, bd_lo, idesc, 1u);
+      }
+      // a stage is free once both sub-items have read it; stages past the first half are only read by SUB 1
+      umma_commit(&bars->empty[slot]);
+      if (SUB == 1 && si >= NST / 2) umma_commit(&bars->empty[slot]);
+      if (si == ns - 1) {
+        umma_commit(&bars->acc_full[SUB]);
+        if (last_of_k) umma_commit(&bars->b_free);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int SUB>
+__device__ __forceinline__ void mma_issuer(uint32_t tmem_base, BarriersT* bars, int nst, int T, int w_begin, int w_end,
+                                           uint64_t bhi_desc0, uint64_t blo_desc0) {
+  int nload = 0;
+  uint32_t it = 0, g0 = 0;                       // g0: global stage counter of the item's first stage
+  int t = 0;
+  bool new_k = true;
+  if (w_end > w_begin) t = w_begin - (w_begin / T) * T;
+  for (int w = w_begin; w < w_end; ++w, ++it, g0 += (uint32_t)nst) {
+    if (new_k) {
+      mbar_wait_sleepy(&bars->b_full, (uint32_t)(nload & 1));
+      ++nload;
+    }
+    new_k = (t == T - 1);                        // the next item starts a new component
+    t = new_k ? 0 : t + 1;
+    const bool last_of_k = new_k && (w + 1 < w_end);
+    if (nst == 8) mma_sub_item<8, SUB>(tmem_base, bars, g0, it, bhi_desc0, blo_desc0, last_of_k);
+    else if (nst == 6) mma_sub_item<6, SUB>(tmem_base, bars, g0, it, bhi_desc0, blo_desc0, last_of_k);
+    else mma_sub_item<4, SUB>(tmem_base, bars, g0, it, bhi_desc0, blo_desc0, last_of_k);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const float* __restrict__ X, const float* __restrict__ tileinf, int N, int D, int Dp,
+                    const float* __restrict__ means, const float* __restrict__ minf,
+                    const float* __restrict__ tmax, const float* __restrict__ cst, int K, float* __restrict__ lq) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int brows = packed_rows(Dp);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + (size_t)brows * 128;
+  BarriersT* bars = reinterpret_cast<BarriersT*>(smem + (size_t)brows * 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ceil_div(N, TILE_M);
+  const long long total = (long long)T * K;      // < 2^31 (checked by the host)
+  const int nkb = Dp / KB;
+  const int nst = Dp / KA;               // A stages per work item: 4, 6 or 8
+  const int H = Dp / 2;                  // output columns per sub-item
+  const int w_begin = (int)(total * blockIdx.x / gridDim.x);
+  const int w_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(&bars->full[s], 4);          // one elected arrive per producer warp of the owning group
+      mbar_init(&bars->empty[s], 2);         // one commit per sub-item that reads the stage (see mma_sub_item)
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 4);     // one elected arrive per epilogue warp
+    }
+    mbar_init(&bars->b_full, 1);
+    mbar_init(&bars->b_free, 2);           // both issuers are done with the resident factor
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    reg_dec<56>();
+    if (warp == 0) {
+      // ---------------- TMA: Linv_k (hi, lo) becomes resident whenever the component changes ----------------
+      if (lane == 0 && w_end > w_begin) {
+        const int k_first = w_begin / T, k_last = (w_end - 1) / T;
+        int nload = 0;
+        for (int k = k_first; k <= k_last; ++k, ++nload) {
+          if (nload > 0) mbar_wait_sleepy(&bars->b_free, (uint32_t)((nload - 1) & 1));
+          mbar_arrive_expect_tx(&bars->b_full, 2u * (uint32_t)brows * 128u);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int row0 = block_row_offset(Dp, kb);
+            for (int r = 0; r < Dp - kb * KB; r += 64) {
+              tma_load_2d(b_hi + (size_t)(row0 + r) * 128, &map_hi, &bars->b_full, kb * KB, k * Dp + kb * KB + r);
+              tma_load_2d(b_lo + (size_t)(row0 + r) * 128, &map_lo, &bars->b_full, kb * KB, k * Dp + kb * KB + r);
+            }
+          }
+        }
+      }
+    } else if (warp == 1 || warp == 3) {
+      // ---------------- MMA issuers: warp 1 the sub-items 0, warp 3 the sub-items 1 of every work item ----------------
+      const uint64_t bhi_desc0 = make_desc(smem_u32(b_hi)), blo_desc0 = make_desc(smem_u32(b_lo));
+      if (warp == 1) mma_issuer<0>(tmem_base, bars, nst, T, w_begin, w_end, bhi_desc0, blo_desc0);
+      else mma_issuer<1>(tmem_base, bars, nst, T, w_begin, w_end, bhi_desc0, blo_desc0);
+    }
+  } else if (wg == 1) {
+    reg_dec<72>();
+    // ---------------- epilogue: row sums of squares of the two sub-items ----------------
+    const int q = warp - 4;
+    int it = 0;
+    const int ncol32 = H / 32;
+    for (int w = w_begin; w < w_end; ++w, ++it) {
+      const int k = w / T, t = w - k * T;
+      const int n = t * TILE_M + 32 * q + lane;
+      const float xi = __ldg(tileinf + t), mi = __ldg(minf + k), tm = __ldg(tmax + k), c = __ldg(cst + k);
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        mbar_wait_sleepy(&bars->acc_full[sub], (uint32_t)it & 1u);
+        tc_fence_after();
+        for (int cb = 0; cb < ncol32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((sub == 0 ? ACC0 : ACC1) + cb * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 a = make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            const float2 b = make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            s01 = ffma2v(a, a, s01);
+            s23 = ffma2v(b, b, s23);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[sub]);
+      }
+      const float s0 = s01.x + s23.x, s1 = s01.y + s23.y;
+      const float f = 1.0f / (pow2_scale(xi + mi) * pow2_scale(tm));
+      if (n < N) lq[(long long)k * N + n] = c - 0.5f * (((s0 + s1) * f) * f);
+    }
+  } else {
+    reg_inc<88>();
+    // ---------------- A producers ----------------
+    const int grp = (warp - 8) >> 2;                           // stage sequence g = grp, grp + 4, ...
+    const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+    const int c4 = lane & 3;
+    const int rsub = 32 * q + (lane >> 2);                     // my rows: rsub + 8 a, a = 0..3
+    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+    const float4* __restrict__ M4 = reinterpret_cast<const float4*>(means);
+    const int D4 = D >> 2;
+    const long long nstage_total = (long long)(w_end - w_begin) * nst;
+    // my half-stages: two per stage g = grp + 4 j
+    const int nunits = nstage_total > grp ? (int)((nstage_total - grp + 3) / 4) * 2 : 0;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16);
+
+    struct Half {
+      float4 x[4];                                             // [2 * (row a & 1) + b]: rows rsub + 16 h + 8 (a & 1)
+      float xi, mi;
+    };
+    // ---- load stream state: (stage s of item (k, t)), half h ----
+    int s_ld = grp, k_ld = 0, t_ld = 0, h_ld = 0;
+    if (w_end > w_begin) {
+      k_ld = w_begin / T;
+      t_ld = w_begin - k_ld * T;
+    }
+    while (s_ld >= nst) {                                      // nst = 4 with grp < 4 never enters; kept for safety
+      s_ld -= nst;
+      if (++t_ld == T) { t_ld = 0; ++k_ld; }
+    }
+    // ---- store stream state ----
+    int s_st = s_ld, k_st = k_ld, t_st = t_ld, h_st = 0;
+    uint32_t g_st = (uint32_t)grp;
+    float sc_cur = 0.f;
+
+    auto issue = [&](Half& R) {
+      const int col4 = s_ld * 8 + c4;
+      const int ca = min(col4, D4 - 1), cb = min(col4 + 4, D4 - 1);
+      const int row0 = t_ld * TILE_M + rsub + 16 * h_ld;
+      const int r0 = min(row0, N - 1), r1 = min(row0 + 8, N - 1);
+      R.x[0] = __ldg(X4 + (r0 * D4 + ca));
+      R.x[1] = __ldg(X4 + (r0 * D4 + cb));
+      R.x[2] = __ldg(X4 + (r1 * D4 + ca));
+      R.x[3] = __ldg(X4 + (r1 * D4 + cb));
+      if (h_ld == 0) {
+        R.xi = __ldg(tileinf + t_ld);
+        R.mi = __ldg(minf + k_ld);
+      }
+      h_ld ^= 1;
+      if (h_ld == 0) {
+        s_ld += 4;
+        if (s_ld >= nst) {
+          s_ld -= nst;
+          if (++t_ld == T) { t_ld = 0; ++k_ld; }
+        }
+      }
+    };
+    auto emit = [&](const Half& R) {
+      const uint32_t slot = g_st & (RING - 1);
+      if (h_st == 0) {
+        sc_cur = pow2_scale(R.xi + R.mi);
+        mbar_wait_fast(smem_u32(&bars->empty[slot]), ((g_st >> 3) & 1u) ^ 1u);
+        tc_fence_after();
+      }
+      const int col4 = s_st * 8 + c4;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {                            // K-step ks = b of the stage: float4 column col4 + 4 b
+        const float sc = col4 + 4 * b < D4 ? sc_cur : 0.f;
+        const float4 m = __ldg(M4 + (k_st * D4 + min(col4 + 4 * b, D4 - 1)));
+        // (x - m) sc == fma(x, sc, -(m sc)) bit for bit: scaling by a power of two commutes with rounding
+        const float2 nm01 = make_float2(-m.x * sc, -m.y * sc), nm23 = make_float2(-m.z * sc, -m.w * sc);
+        uint32_t r[8];                                         // blocks (hi, lo) x registers (row, row + 8) x 2
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const float4 x = R.x[2 * a + b];
+          const float2 v01 = ffma2(make_float2(x.x, x.y), sc, nm01);
+          const float2 v23 = ffma2(make_float2(x.z, x.w), sc, nm23);
+          const __half2 h01 = __floats2half2_rn(v01.x, v01.y), h23 = __floats2half2_rn(v23.x, v23.y);
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          const __half2 l01 = __floats2half2_rn(sub_f32_f16(v01.x, (unsigned short)(u01 & 0xffffu)),
+                                                sub_f32_f16(v01.y, (unsigned short)(u01 >> 16)));
+          const __half2 l23 = __floats2half2_rn(sub_f32_f16(v23.x, (unsigned short)(u23 & 0xffffu)),
+                                                sub_f32_f16(v23.y, (unsigned short)(u23 >> 16)));
+          r[2 * a] = u01;
+          r[2 * a + 1] = u23;
+          r[4 + 2 * a] = *reinterpret_cast<const uint32_t*>(&l01);
+          r[4 + 2 * a + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+        }
+        tmem_st_16x256b_x2(taddr0 + ((uint32_t)(16 * h_st) << 16) + slot * 32u + (uint32_t)(16 * b), r);
+      }
+      h_st ^= 1;
+      if (h_st == 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->full[slot]);
+        g_st += 4;
+        s_st += 4;
+        if (s_st >= nst) {
+          s_st -= nst;
+          if (++t_st == T) { t_st = 0; ++k_st; }
+        }
+      }
+    };
+    Half R0, R1;
+    if (nunits > 0) issue(R0);
+    for (int j = 0; j < nunits; j += 2) {
+      if (j + 1 < nunits) issue(R1);
+      emit(R0);
+      if (j + 1 < nunits) {
+        if (j + 2 < nunits) issue(R0);
+        emit(R1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static size_t smem_bytes_t(int Dp) { return (size_t)packed_rows(Dp) * 256 + 1024 /*alignment slack*/ + 256 /*barriers*/; }
+
+}  // namespace h16t
+
 // One CTA per component: t = max |Linv_k| -> scale 2^e with |Linv| 2^e < 2^14; write zero-padded fp16 hi / lo.
 __global__ void __launch_bounds__(256)
 split_h16_kernel(const float* __restrict__ linv, int D, int Dp, __half* __restrict__ hi, __half* __restrict__ lo,
@@ -573,20 +931,31 @@ extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, in
   rc = h16::make_map_h16(&map_lo, linv_lo, K, Dp);
   if (rc) return rc;
   static int num_sms = 0;
+  static int a_in_tmem = 1;      // GMMVI_B200_H16_A=smem selects the shared-memory A operand for every size
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(h16::logdens_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)h16::smem_bytes(256));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(h16::h16t::logdens_h16t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h16::h16t::smem_bytes_t(256));
     if (e != cudaSuccess) {
       set_last_error("gvi_logdens_full_h16_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       num_sms = 0;
       return GVI_ERR_CUDA;
     }
+    const char* env = getenv("GMMVI_B200_H16_A");
+    a_in_tmem = (env != nullptr && strcmp(env, "smem") == 0) ? 0 : 1;
   }
   const long long total = (long long)ceil_div(N, h16::TILE_M) * K;
   const int grid = (int)min((long long)num_sms, total);
+  if (a_in_tmem && Dp >= 128) {
+    h16::h16t::logdens_h16t_kernel<<<grid, h16::THREADS, h16::h16t::smem_bytes_t(Dp), (cudaStream_t)stream>>>(
+        map_hi, map_lo, X, tileinf, N, D, Dp, means, minf, tmax, cst, K, lq);
+    return check_launch("logdens_h16t_kernel");
+  }
   h16::logdens_h16_kernel<<<grid, h16::THREADS, h16::smem_bytes(Dp), (cudaStream_t)stream>>>(
       map_hi, map_lo, X, tileinf, N, D, Dp, means, minf, tmax, cst, K, lq);
   return check_launch("logdens_h16_kernel");
