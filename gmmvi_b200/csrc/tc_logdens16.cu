@@ -514,6 +514,11 @@ __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // The tcgen05.mma of one sub-item (SUB = 0: output columns [0, Dp/2), SUB = 1: [Dp/2, Dp)) of one work item, fully
@@ -606,6 +611,9 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   uint8_t* b_hi = smem;
   uint8_t* b_lo = smem + (size_t)brows * 128;
   BarriersT* bars = reinterpret_cast<BarriersT*>(smem + (size_t)brows * 256);
+  // mean rows of the components in this CTA's range (zero padded to Dp): the producers need one float4 of the mean per
+  // converted float4 and an L2 round trip for it would sit in front of every conversion
+  float* mean_sm = reinterpret_cast<float*>(smem + (size_t)brows * 256 + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = ceil_div(N, TILE_M);
   const long long total = (long long)T * K;      // < 2^31 (checked by the host)
@@ -629,6 +637,14 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  const int k_first_cta = w_end > w_begin ? w_begin / T : 0;
+  if (w_end > w_begin) {
+    const int ncomp = (w_end - 1) / T - k_first_cta + 1;
+    for (int i = threadIdx.x; i < ncomp * Dp; i += THREADS) {
+      const int kk = i / Dp, j = i - kk * Dp;
+      mean_sm[i] = j < D ? __ldg(means + (size_t)(k_first_cta + kk) * D + j) : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -703,7 +719,6 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const int c4 = lane & 3;
     const int rsub = 32 * q + (lane >> 2);                     // my rows: rsub + 8 a, a = 0..3
     const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
-    const float4* __restrict__ M4 = reinterpret_cast<const float4*>(means);
     const int D4 = D >> 2;
     const long long nstage_total = (long long)(w_end - w_begin) * nst;
     // my half-stages: two per stage g = grp + 4 j
@@ -725,7 +740,8 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       if (++t_ld == T) { t_ld = 0; ++k_ld; }
     }
     // ---- store stream state ----
-    int s_st = s_ld, k_st = k_ld, t_st = t_ld, h_st = 0;
+    int s_st = s_ld, t_st = t_ld, h_st = 0;
+    uint32_t mrow_st = smem_u32(mean_sm);                      // cached mean row of the store stream's component
     uint32_t g_st = (uint32_t)grp;
     float sc_cur = 0.f;
 
@@ -755,14 +771,14 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       const uint32_t slot = g_st & (RING - 1);
       if (h_st == 0) {
         sc_cur = pow2_scale(R.xi + R.mi);
-        mbar_wait_fast(smem_u32(&bars->empty[slot]), ((g_st >> 3) & 1u) ^ 1u);
+        mbar_wait_sleepy(&bars->empty[slot], ((g_st >> 3) & 1u) ^ 1u);
         tc_fence_after();
       }
       const int col4 = s_st * 8 + c4;
 #pragma unroll
       for (int b = 0; b < 2; ++b) {                            // K-step ks = b of the stage: float4 column col4 + 4 b
         const float sc = col4 + 4 * b < D4 ? sc_cur : 0.f;
-        const float4 m = __ldg(M4 + (k_st * D4 + min(col4 + 4 * b, D4 - 1)));
+        const float4 m = lds128(mrow_st + (uint32_t)(16 * (col4 + 4 * b)));   // zero padded to Dp columns
         // (x - m) sc == fma(x, sc, -(m sc)) bit for bit: scaling by a power of two commutes with rounding
         const float2 nm01 = make_float2(-m.x * sc, -m.y * sc), nm23 = make_float2(-m.z * sc, -m.w * sc);
         uint32_t r[8];                                         // blocks (hi, lo) x registers (row, row + 8) x 2
@@ -794,7 +810,7 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         s_st += 4;
         if (s_st >= nst) {
           s_st -= nst;
-          if (++t_st == T) { t_st = 0; ++k_st; }
+          if (++t_st == T) { t_st = 0; mrow_st += (uint32_t)(Dp * 4); }
         }
       }
     };
@@ -815,7 +831,10 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-static size_t smem_bytes_t(int Dp) { return (size_t)packed_rows(Dp) * 256 + 1024 /*alignment slack*/ + 256 /*barriers*/; }
+constexpr int MEANS_CACHED_MAX = 32;      // components whose mean rows are cached in shared memory (32 KB at Dp = 256)
+static size_t smem_bytes_t(int Dp) {
+  return (size_t)packed_rows(Dp) * 256 + 1024 /*alignment slack*/ + 256 /*barriers*/ + (size_t)MEANS_CACHED_MAX * Dp * 4;
+}
 
 }  // namespace h16t
 
@@ -951,7 +970,11 @@ extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, in
   }
   const long long total = (long long)ceil_div(N, h16::TILE_M) * K;
   const int grid = (int)min((long long)num_sms, total);
-  if (a_in_tmem && Dp >= 128) {
+  // the TMEM-A kernel caches the mean rows of a CTA's components in shared memory: a contiguous item range touches at
+  // most ceil(items / T) + 1 components
+  const int T = ceil_div(N, h16::TILE_M);
+  const bool means_fit = ((total + grid - 1) / grid + T - 1) / T + 1 <= h16::h16t::MEANS_CACHED_MAX;
+  if (a_in_tmem && Dp >= 128 && means_fit) {
     h16::h16t::logdens_h16t_kernel<<<grid, h16::THREADS, h16::h16t::smem_bytes_t(Dp), (cudaStream_t)stream>>>(
         map_hi, map_lo, X, tileinf, N, D, Dp, means, minf, tmax, cst, K, lq);
     return check_launch("logdens_h16t_kernel");
