@@ -32,7 +32,7 @@ K_COMP, DIM, PER_COMP = 512, 256, 128
 TARGET_COMPONENTS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
 # captures (profiles/r01_ncu_*.txt), keyed by (kernel kind, K, D, samples per launch); other shapes report null
-NCU_DRAM_TRAFFIC = {("h16", 512, 256, 65536): 1.847489e9 + 138.376448e6}
+NCU_DRAM_TRAFFIC = {("h16", 512, 256, 65536): 1.712667e9 + 138.592256e6}
 PRIOR_SCALE = 31.63          # configs/experiment_configs/gmm100.yml:11 (GMM-target experiments)
 
 
@@ -367,7 +367,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": achieved / tc_peak,
                      "traffic": NCU_DRAM_TRAFFIC.get((kind, K, D, int(X.shape[0]))),
-                     "traffic_source": "profiles/r01_ncu_h16_logdens.txt (bytes per launch)",
+                     "traffic_source": "profiles/r01_ncu_h16t_logdens.txt (bytes per launch)",
                      "algorithmic_bytes": 4.0 * (X.shape[0] * D + 2 * K * D * D // 2 + K * X.shape[0]),
                      "kernel": ops.logdens_kernel_name(D), "launch_ms": ld_ms,
                      "algorithmic_flop_per_pair": D * D + 4 * D,

@@ -44,7 +44,10 @@ def logdens_kernel_kind(D: int) -> str:
 
 
 def logdens_kernel_name(D: int = 256) -> str:
-    return {"h16": "gvi::h16::logdens_h16_kernel (tcgen05 kind::f16, 2 x fp16 split, resident Linv, TMA + TMEM)",
+    h16 = ("gvi::h16::h16t::logdens_h16t_kernel (tcgen05 kind::f16, 2 x fp16 split, A operand in TMEM via tcgen05.st, "
+           "resident Linv in shared memory by TMA)" if D > 64 and os.environ.get("GMMVI_B200_H16_A") != "smem" else
+           "gvi::h16::logdens_h16_kernel (tcgen05 kind::f16, 2 x fp16 split, resident Linv, TMA + TMEM)")
+    return {"h16": h16,
             "tf32": "gvi::tc::tc_logdens_kernel (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM)",
             "simt": "gvi::logdens_full_kernel (SIMT fp32 tile engine)"}[logdens_kernel_kind(int(D))]
 
