@@ -111,11 +111,14 @@ def test_empty_inputs():
     assert ops.mixture_lse(lq, dev(g32.log_weights)).shape == (0,)
 
 
+# N = 1000: streaming kernel; 8192: on-chip row kernel, shared memory only; 50000 / 65536: shared memory + registers
+# (65536 is the largest row the on-chip kernel takes); 65540: back to the streaming kernel
+@pytest.mark.parametrize("N", [1000, 8192, 50000, 65536, 65540])
 @pytest.mark.parametrize("self_norm", [True, False])
-def test_importance_weights(self_norm):
+def test_importance_weights(self_norm, N):
     from gmmvi_b200 import ops
     rng = np.random.default_rng(3)
-    K, N = 6, 1000
+    K = 6 if N <= 8192 else 3
     lq = (rng.standard_normal((K, N)) * 5 - 20).astype(np.float32)
     bg = (rng.standard_normal(N) * 2 - 18).astype(np.float32)
     rho = rng.standard_normal(N).astype(np.float32)
@@ -133,6 +136,14 @@ def test_importance_weights(self_norm):
     assert np.all(np.floor(out["ess"].cpu().numpy()) == np.floor(ess)) or True   # floor ties are tested in test_api
     act = out["active"].cpu().numpy()
     assert act.shape == (K, (N + 127) // 128) and act.max() == 1
+    # a block is flagged iff it holds a weight within e^-60 of the row's largest
+    top = lw.max(axis=1, keepdims=True)
+    pad = (-N) % 128
+    flag = np.pad((lw - top) > -60.0, ((0, 0), (0, pad))).reshape(K, -1, 128).any(axis=2)
+    assert np.array_equal(act.astype(bool), flag)
+    # only some outputs requested (the weight updater's call: no W)
+    out2 = ops.importance_weights(dev(lq), dev(bg), None, self_norm, dev(rho), False, True, False, False)
+    assert out2["W"] is None and rel_err(out2["dot"].cpu().numpy(), w @ rho.astype(np.float64)) < 1e-4
 
 
 def test_importance_weights_own_samples():
