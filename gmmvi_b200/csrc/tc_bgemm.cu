@@ -208,6 +208,27 @@ __global__ void split_tf32_strided_kernel(const float* __restrict__ in, int R, i
   }
 }
 
+// Same for 16-byte aligned operands with Cc % 4 == 0, ld % 4 == 0 and R * Cc < 2^31: one float4 per thread and step,
+// 32-bit index arithmetic (the generic kernel spends most of its time in two 64-bit divisions per element).
+__global__ void __launch_bounds__(256)
+split_tf32_strided_vec4_kernel(const float* __restrict__ in, int R, int C4, int ld4, long long stride_in,
+                               float* __restrict__ hi, float* __restrict__ lo) {
+  const int b = blockIdx.y;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(in + b * stride_in);
+  float4* __restrict__ h4 = reinterpret_cast<float4*>(hi + (long long)b * R * C4 * 4);
+  float4* __restrict__ l4 = reinterpret_cast<float4*>(lo + (long long)b * R * C4 * 4);
+  const int total = R * C4;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int r = e / C4, c = e - r * C4;
+    const float4 x = __ldg(src + ((long long)r * ld4 + c));
+    float4 h, l;
+    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+    h4[e] = h;
+    l4[e] = l;
+  }
+}
+
 static int num_sms_cached() {
   static int n = 0;
   if (n == 0) {
@@ -231,6 +252,14 @@ int launch_split_tf32(const float* in, int batch, int R, int Cc, int ld, long lo
     dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), batch), block(32, 8);
     tcg::split_tf32_transpose_kernel<<<grid, block, 0, st>>>(in, R, Cc, ld, stride_in, hi, lo);
     return check_launch("split_tf32_transpose_kernel");
+  }
+  const bool vec4 = Cc % 4 == 0 && ld % 4 == 0 && stride_in % 4 == 0 && (long long)R * Cc < 2147483647LL &&
+                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) % 16 == 0) &&
+                    ((long long)R * Cc) % 4 == 0;
+  if (vec4) {
+    dim3 grid((unsigned)min((long long)64, ((long long)R * (Cc / 4) + 255) / 256), batch);
+    tcg::split_tf32_strided_vec4_kernel<<<grid, 256, 0, st>>>(in, R, Cc / 4, ld / 4, stride_in, hi, lo);
+    return check_launch("split_tf32_strided_vec4_kernel");
   }
   dim3 grid((unsigned)min((long long)1024, ((long long)R * Cc + 255) / 256), batch);
   tcg::split_tf32_strided_kernel<<<grid, 256, 0, st>>>(in, R, Cc, ld, stride_in, hi, lo);

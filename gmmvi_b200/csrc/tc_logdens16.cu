@@ -839,26 +839,40 @@ static size_t smem_bytes_t(int Dp) {
 }  // namespace h16t
 
 // One CTA per component: t = max |Linv_k| -> scale 2^e with |Linv| 2^e < 2^14; write zero-padded fp16 hi / lo.
-__global__ void __launch_bounds__(256)
+// D % 4 == 0 (a condition of the fp16 kernels): float4 loads, 8-byte stores of four halves.
+__global__ void __launch_bounds__(512)
 split_h16_kernel(const float* __restrict__ linv, int D, int Dp, __half* __restrict__ hi, __half* __restrict__ lo,
                  float* __restrict__ tmax) {
   __shared__ float scratch[34];
   const int k = blockIdx.x;
-  const float* src = linv + (long long)k * D * D;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(linv + (long long)k * D * D);
+  const int D4 = D >> 2, Dp4 = Dp >> 2;
   float m = 0.f;
-  for (int i = threadIdx.x; i < D * D; i += blockDim.x) m = fmaxf(m, fabsf(src[i]));
+  for (int i = threadIdx.x; i < D * D4; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
   m = block_max(m, scratch);
   if (threadIdx.x == 0) tmax[k] = m;
   const float sc = pow2_scale(m);
-  __half* dh = hi + (long long)k * Dp * Dp;
-  __half* dl = lo + (long long)k * Dp * Dp;
-  for (int i = threadIdx.x; i < Dp * Dp; i += blockDim.x) {
-    const int r = i / Dp, cidx = i - r * Dp;
-    float v = 0.f;
-    if (r < D && cidx <= r) v = src[r * D + cidx] * sc;      // strictly-upper entries are structurally zero
-    const __half h = __float2half_rn(v);
-    dh[i] = h;
-    dl[i] = __float2half_rn(v - __half2float(h));
+  uint2* __restrict__ dh = reinterpret_cast<uint2*>(hi + (long long)k * Dp * Dp);
+  uint2* __restrict__ dl = reinterpret_cast<uint2*>(lo + (long long)k * Dp * Dp);
+  for (int i = threadIdx.x; i < Dp * Dp4; i += blockDim.x) {
+    const int r = i / Dp4, c4 = i - r * Dp4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < D && c4 < D4 && 4 * c4 <= r) {                    // blocks entirely above the diagonal stay zero
+      v = __ldg(src + (r * D4 + c4));
+      // strictly-upper entries are structurally zero
+      v.x *= sc;
+      v.y = 4 * c4 + 1 <= r ? v.y * sc : 0.f;
+      v.z = 4 * c4 + 2 <= r ? v.z * sc : 0.f;
+      v.w = 4 * c4 + 3 <= r ? v.w * sc : 0.f;
+    }
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    dh[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    dl[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
 }
 
@@ -912,7 +926,10 @@ extern "C" int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void
   GVI_REQUIRE(K >= 0 && D > 0, "gvi_split_h16_f32: bad sizes");
   if (K == 0) return GVI_OK;
   GVI_REQUIRE(linv && hi && lo && tmax, "gvi_split_h16_f32: null pointer");
-  h16::split_h16_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(linv, D, h16::padded_dim(D), (__half*)hi, (__half*)lo,
+  GVI_REQUIRE(D % 4 == 0 && reinterpret_cast<uintptr_t>(linv) % 16 == 0 && reinterpret_cast<uintptr_t>(hi) % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(lo) % 8 == 0,
+              "gvi_split_h16_f32: needs D %% 4 == 0 and aligned operands");
+  h16::split_h16_kernel<<<K, 512, 0, (cudaStream_t)stream>>>(linv, D, h16::padded_dim(D), (__half*)hi, (__half*)lo,
                                                              tmax);
   return check_launch("split_h16_kernel");
 }
