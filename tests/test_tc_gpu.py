@@ -32,12 +32,14 @@ def test_tc_logdens_matches_oracle(K, D, N, kind):
     assert err.max() < 5e-6, err.max()
 
 
-@pytest.mark.parametrize("kind", ["tf32", "h16"])
-def test_tc_logdens_many_tiles_and_components(kind):
+@pytest.mark.parametrize("kind,D", [("tf32", 64), ("h16", 64), ("h16", 128), ("h16", 192), ("h16", 256)])
+def test_tc_logdens_many_tiles_and_components(kind, D):
     """More work items than SMs: exercises the persistent loop, both TMEM buffers, the stage ring wrap and (h16) the
-    reload of the resident factor when a CTA's work range crosses a component boundary."""
+    reload of the resident factor when a CTA's work range crosses a component boundary.  D = 64 runs the kernel with the
+    A operand in shared memory, D >= 128 the one with A in tensor memory (4, 6 and 8 stages per work item: the ring of
+    8 A stages wraps differently for each) and its per-CTA cache of mean rows."""
     from gmmvi_b200 import ops
-    K, D, N = 40, 64, 128 * 12 + 5
+    K, N = 40, 128 * 12 + 5
     g, X = make_problem(K, D, N, seed=7, scale=10.0)
     g32 = gmm32_of(g)
     linv, prec, cst, ok = ops.prepare_full(dev(g32.chol_cov))
@@ -50,9 +52,12 @@ def test_tc_logdens_many_tiles_and_components(kind):
     assert torch.equal(a, a2)
 
 
-@pytest.mark.parametrize("K,D,N", [(3, 100, 700), (2, 200, 257), (6, 20, 300), (2, 12, 64), (300, 64, 130), (2, 36, 90)])
+@pytest.mark.parametrize("K,D,N", [(3, 100, 700), (2, 200, 257), (6, 20, 300), (2, 12, 64), (300, 64, 130), (2, 36, 90),
+                                   (4, 160, 400), (3, 192, 260), (300, 128, 130), (6000, 128, 100)])
 def test_h16_logdens_odd_dims(K, D, N):
-    """fp16 path on dimensions that are not multiples of 64 (zero-padded operand, clamped loads), and with more components than SMs (several factor reloads per CTA)."""
+    """fp16 path on dimensions that are not multiples of 64 (zero-padded operand, clamped loads), and with more components
+    than SMs (several factor reloads per CTA).  K = 6000 with one sample tile gives every CTA more components than the
+    TMEM-A kernel caches mean rows for: the entry point must fall back to the shared-memory-A kernel."""
     from gmmvi_b200 import ops
     g, X = make_problem(K, D, N, seed=300 + D, scale=30.0)
     g32 = gmm32_of(g)
@@ -141,3 +146,44 @@ def test_tc_stein_stats(K, D, N, dense):
     # bitwise reproducible
     H2, _ = ops.stein_full(dev(X), dev(means), dev(prec), dev(W), dev(act, torch.uint8), dev(G), True)
     assert torch.equal(Hneg, H2)
+
+
+def test_full_size_c5_properties():
+    """BASELINE's stress configuration at full size (K = 512, D = 256, N = 65536): the oracle cannot run it, so the tensor-core
+    pass is checked (a) against the exact-fp32 SIMT kernel on a slice of the components, (b) for exact scaling
+    invariance (x, mu, L -> 4 x, 4 mu, 4 L shifts every density by -D log 4 and nothing else), (c) through the
+    chi-square law of the samples' own components, (d) the importance weights of every component sum to one."""
+    from gmmvi_b200 import ops
+    K, D, N = 512, 256, 65536
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn((K, D, D), device="cuda", generator=g)
+    chol = torch.linalg.cholesky(A @ A.transpose(1, 2) / D + torch.eye(D, device="cuda")).contiguous()
+    del A
+    means = (torch.randn((K, D), device="cuda", generator=g) * 31.63).contiguous()
+    comp = torch.arange(N, device="cuda") // (N // K)
+    eps = torch.randn((N, D), device="cuda", generator=g)
+    X = (means[comp] + torch.einsum("nij,nj->ni", chol[comp], eps)).contiguous()
+    linv, prec, cst, ok = ops.prepare_full(chol)
+    assert bool(ok.all())
+    lq = ops.logdens_full(X, means, linv, cst, memo=False)
+    assert lq.shape == (K, N) and bool(torch.isfinite(lq).all())
+    # (a) exact fp32 kernel on 6 components spread over the range (all samples)
+    sel = torch.tensor([0, 1, 100, 255, 256, 511], device="cuda")
+    ref = ops.logdens_full(X, means[sel].contiguous(), linv[sel].contiguous(), cst[sel].contiguous(), memo=False,
+                           tensor_cores=False)
+    err = ((lq[sel] - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+    assert err < 5e-6, err
+    # (b) scaling by a power of two is exact in fp32: x, mu, L -> 4 x, 4 mu, 4 L changes every density by -D log 4 only
+    lq4 = ops.logdens_full((4.0 * X).contiguous(), (4.0 * means).contiguous(), (0.25 * linv).contiguous(),
+                           (cst - D * float(np.log(4.0))).contiguous(), memo=False)
+    err = ((lq4 + D * float(np.log(4.0)) - lq).abs() / lq.abs().clamp_min(1.0)).max().item()
+    assert err < 1e-6, err
+    # (c) own component: -2 (lq - cst) = |eps|^2 is chi-square with D degrees of freedom
+    own = lq[comp, torch.arange(N, device="cuda")]
+    maha = -2.0 * (own - cst[comp])
+    assert abs(maha.mean().item() - D) < 0.5 and abs(maha.var().item() - 2 * D) < 0.05 * 2 * D
+    assert ((maha - (eps * eps).sum(1)).abs() / D).max().item() < 1e-3
+    # (d) self-normalised importance weights
+    bg = ops.mixture_lse(lq, torch.full((K,), -float(np.log(K)), device="cuda"))
+    W = ops.importance_weights(lq, bg, None, True, None, True, False, False, False)["W"]
+    assert (W.sum(1) - 1.0).abs().max().item() < 1e-5 and bool((W >= 0).all())
