@@ -34,8 +34,10 @@ bool update_blocked_supported(int D);
 int launch_update_full_blocked(int mode, const float* means, const float* chols, const float* Bm, const float* B2,
                                const float* hv, const float* stepsizes, const float* last_etas,
                                const float* num_updates, int K, int D, float temperature, float* out_means,
-                               float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals,
+                               float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals, const float* tdiag, const float* toff, const float* thp,
                                cudaStream_t st);
+bool tridiag_supported(int D);
+int launch_tridiag(const float* Bm, const float* hv, int K, int D, float* d, float* e, float* hp, cudaStream_t st);
 
 constexpr int UPD_THREADS = 1024;
 
@@ -566,7 +568,7 @@ using namespace gvi;
 
 extern "C" size_t gvi_update_full_workspace(int K, int D) {
   if (K <= 0) return 0;
-  size_t f = (size_t)4 * K * D * D + (size_t)K * D + 64;
+  size_t f = (size_t)4 * K * D * D + (size_t)4 * K * D + 64;       // 3 K D: tridiagonal form (mode 0, D <= 256)
   if (upd_smem_bytes(D) > kMaxDynSmem) f += (size_t)K * D * (D + 1) / 2;
   f = (f + 63) / 64 * 64 + tc_gemm_workspace_floats(K, D, D, D);
   return f * sizeof(float);
@@ -596,8 +598,11 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
   float* Bm = T + (size_t)K * DD;
   float* B2 = Bm + (size_t)K * DD;
   float* hv = B2 + (size_t)K * DD;
-  float* gscr = hv + (size_t)K * D;
-  size_t used = (size_t)4 * K * DD + (size_t)K * D + 64;
+  float* tdg = hv + (size_t)K * D;               // tridiagonal form of B: diagonal, sub-diagonal, P^T h
+  float* tde = tdg + (size_t)K * D;
+  float* tdh = tde + (size_t)K * D;
+  float* gscr = tdh + (size_t)K * D;
+  size_t used = (size_t)4 * K * DD + (size_t)4 * K * D + 64;
   if (upd_smem_bytes(D) > kMaxDynSmem) used += (size_t)K * D * (D + 1) / 2;
   float* tcws = (float*)ws + (used + 63) / 64 * 64;
   const size_t tcws_floats = tc_gemm_workspace_floats(K, D, D, D);
@@ -617,9 +622,21 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
   update_vectors_kernel<<<K, 256, D * sizeof(float), st>>>(means, chols, Hneg, gneg, D, mode != 2, hv);
   rc = check_launch("update_vectors_kernel");
   if (rc) return rc;
-  if (update_blocked_supported(D) && !getenv("GMMVI_B200_UPDATE_PANEL"))
+  if (update_blocked_supported(D) && !getenv("GMMVI_B200_UPDATE_PANEL")) {
+    // mode 0, GMMVI_B200_UPDATE_TRIDIAG=1: the bisection evaluates KL(eta) from the tridiagonal form of B instead of
+    // factoring M(eta) for every eta.  Identical decisions and results (tests), and the update kernel itself drops
+    // from 3.99 to 1.48 ms at C5, but the Householder reduction (update_tridiag.cu) costs 6.4 ms there today, so the
+    // path is opt-in until that kernel is below ~2 ms.  (Read per call: the tests compare both paths.)
+    const char* td_env = getenv("GMMVI_B200_UPDATE_TRIDIAG");
+    const bool td = (td_env && td_env[0] == '1') && mode == 0 && tridiag_supported(D);
+    if (td) {
+      rc = launch_tridiag(Bm, hv, K, D, tdg, tde, tdh, st);
+      if (rc) return rc;
+    }
     return launch_update_full_blocked(mode, means, chols, Bm, B2, hv, stepsizes, last_etas, num_updates, K, D,
-                                      temperature, out_means, out_chols, success, etas, kls, evals, st);
+                                      temperature, out_means, out_chols, success, etas, kls, evals,
+                                      td ? tdg : nullptr, td ? tde : nullptr, td ? tdh : nullptr, st);
+  }
   const size_t full = upd_smem_bytes(D);
   const int use_global = full > kMaxDynSmem;
   const size_t smem = use_global ? (size_t)4 * D * sizeof(float) : full;

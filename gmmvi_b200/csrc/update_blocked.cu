@@ -414,6 +414,56 @@ __device__ __noinline__ KlTerms eval_whitened(const Smem s, const float* __restr
   return out;
 }
 
+// KL(new || old) for M = I + a1 T with T tridiagonal (diagonal d, sub-diagonal e) and h' = hp, evaluated by ONE
+// thread (update_tridiag.cu explains the change of basis).  With the pivots of the LDL^T factorisation from the top,
+// q_i = 1 + r_i, and from the bottom, q'_i = 1 + r'_i (both carried "minus one", like dm1 in the Cholesky path):
+//   log det M = sum log1p(r_i),   (M^-1)_ii = 1 / (q_i + q'_i - m_ii)  =>  tr M^-1 - D = sum -s_i / (1 + s_i) with
+//   s_i = r_i + r'_i - a1 d_i,    M x = h' by the same pivots (Thomas algorithm),   KL = 1/2 (logdet + tr + |x|^2 a1^2).
+// rq / ys: per-lane scratch, element i of lane l at [32 i + l].  Not positive definite (a pivot <= 0) -> FLT_MAX,
+// the value kl() returns for a failed Cholesky (:320-324).
+__device__ __noinline__ float kl_tridiag_lane(float a1, const float* __restrict__ d, const float* __restrict__ e,
+                                              const float* __restrict__ hp, int D, float* __restrict__ rq,
+                                              float* __restrict__ ys) {
+  const int lane = threadIdx.x & 31;
+  float r_prev = 0.f, y_prev = 0.f, ld = 0.f;
+  bool pd = true;
+  for (int i = 0; i < D; ++i) {
+    const float delta = a1 * d[i];
+    float r = delta, y = hp[i];
+    if (i > 0) {
+      const float b = a1 * e[i - 1];
+      const float l = b / (1.f + r_prev);
+      r = fmaf(-b, l, delta);
+      y = fmaf(-l, y_prev, y);
+    }
+    pd = pd && (1.f + r > 0.f);
+    ld += log1pf(r);
+    rq[32 * i + lane] = r;
+    ys[32 * i + lane] = y;
+    r_prev = r;
+    y_prev = y;
+  }
+  float rb_next = 0.f, x_next = 0.f, tr = 0.f, mh = 0.f;
+  for (int i = D - 1; i >= 0; --i) {
+    const float delta = a1 * d[i];
+    const float r = rq[32 * i + lane];
+    const float iq = 1.f / (1.f + r);
+    float rb = delta, x = ys[32 * i + lane] * iq;
+    if (i < D - 1) {
+      const float b = a1 * e[i];
+      rb = fmaf(-b, b / (1.f + rb_next), delta);
+      x = fmaf(-(b * iq), x_next, x);
+    }
+    const float sdev = r + rb - delta;
+    tr -= sdev / (1.f + sdev);
+    mh = fmaf(x, x, mh);
+    rb_next = rb;
+    x_next = x;
+  }
+  const float kl = 0.5f * (ld + tr + mh * a1 * a1);
+  return (pd && isfinite(kl)) ? kl : FLT_MAX;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 update_full_blocked_kernel(int mode, const float* __restrict__ means, const float* __restrict__ chols,
                            const float* __restrict__ Bmat, const float* __restrict__ B2mat,
@@ -421,8 +471,10 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
                            const float* __restrict__ last_etas, const float* __restrict__ num_updates, int D,
                            float temperature, float* __restrict__ out_means, float* __restrict__ out_chols,
                            int32_t* __restrict__ success, float* __restrict__ etas, float* __restrict__ kls,
-                           int32_t* __restrict__ evals) {
+                           int32_t* __restrict__ evals, const float* __restrict__ tdiag,
+                           const float* __restrict__ toff, const float* __restrict__ thp) {
   extern __shared__ __align__(16) float ub_smem[];
+  __shared__ float search_out[4];
   __shared__ float red[33];
   __shared__ float idiag[NB];
   __shared__ int flag;
@@ -464,6 +516,59 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
     else { lower = fmaxf(0.f, logf(last) - 3.f); upper = logf(last) + 3.f; }
     float leta = 0.5f * (upper + lower);
     bool feasible = false;
+    if (tdiag != nullptr) {
+      // ---- the same search with KL(eta) evaluated from the tridiagonal form: warp 0 evaluates the 31 candidate etas
+      // of the next five bisection levels at once (lane = node of the decision tree, heap numbering: left child =
+      // "feasible, upper = eta", right child = "lower = eta") and then walks the tree with the reference's rules ----
+      float* sd = s.A;
+      float* se = sd + Dp;
+      float* sh = se + Dp;
+      float* rq = sh + Dp;
+      float* ys = rq + 32 * Dp;
+      for (int i = tid; i < D; i += THREADS) {
+        sd[i] = tdiag[(long long)k * D + i];
+        se[i] = toff[(long long)k * D + i];
+        sh[i] = thp[(long long)k * D + i];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        bool done = false;
+        for (int round = 0; round < 200 && !done; ++round) {
+          float lo = lower, up = upper;
+          const int depth = 31 - __clz(max(lane, 1));
+          for (int b = depth - 1; b >= 0; --b) {
+            const float mid = 0.5f * (up + lo);
+            if ((lane >> b) & 1) lo = mid; else up = mid;
+          }
+          const float my_kl = kl_tridiag_lane(1.f / expf(0.5f * (up + lo)), sd, se, sh, D, rq, ys);
+          int node = 1;
+          for (int lvl = 0; lvl < 5; ++lvl) {
+            leta = 0.5f * (upper + lower);
+            const float diff = fminf(expf(upper) - expf(leta), expf(leta) - expf(lower));
+            if (diff < 1e-1f) { done = true; break; }
+            const float klv = __shfl_sync(0xffffffffu, my_kl, node);
+            ++n_evals;
+            if (fabsf(step - klv) < 1e-1f * step) { lower = upper = leta; done = true; break; }
+            if (step > klv) { upper = leta; feasible = true; node = 2 * node; }
+            else { lower = leta; node = 2 * node + 1; }
+          }
+        }
+        if (lane == 0) {
+          search_out[0] = lower;
+          search_out[1] = upper;
+          search_out[2] = feasible ? 1.f : 0.f;
+          search_out[3] = (float)n_evals;
+        }
+      }
+      __syncthreads();
+      lower = search_out[0];
+      upper = search_out[1];
+      feasible = search_out[2] != 0.f;
+      n_evals = (int)search_out[3];
+      // the scratch of the search may reach into the vectors behind the blocks when D <= 64: restore h~
+      for (int i = tid; i < Dp; i += THREADS) s.hrev[i] = i < D ? hvec[(long long)k * D + (D - 1 - i)] : 0.f;
+      __syncthreads();
+    } else
     for (int it = 0; it < 1000; ++it) {
       const float diff = fminf(expf(upper) - expf(leta), expf(leta) - expf(lower));
       if (diff < 1e-1f) break;
@@ -637,7 +742,7 @@ int launch_update_full_blocked(int mode, const float* means, const float* chols,
                                const float* hv, const float* stepsizes, const float* last_etas,
                                const float* num_updates, int K, int D, float temperature, float* out_means,
                                float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals,
-                               cudaStream_t st) {
+                               const float* tdiag, const float* toff, const float* thp, cudaStream_t st) {
   const size_t smem = ub::blocked_smem_bytes(D);
   static bool attr_set = false;
   if (!attr_set) {
@@ -651,7 +756,7 @@ int launch_update_full_blocked(int mode, const float* means, const float* chols,
   }
   ub::update_full_blocked_kernel<<<K, ub::THREADS, smem, st>>>(mode, means, chols, Bm, B2, hv, stepsizes, last_etas,
                                                                num_updates, D, temperature, out_means, out_chols,
-                                                               success, etas, kls, evals);
+                                                               success, etas, kls, evals, tdiag, toff, thp);
   return check_launch("update_full_blocked_kernel");
 }
 

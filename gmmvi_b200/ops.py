@@ -395,6 +395,16 @@ def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, steps
     return om, oc, succ, etas, kls
 
 
+def tridiag(B, h):
+    """Householder tridiagonalisation of the symmetric matrices S[i][j] = B[k][min(i,j)][max(i,j)] (D <= 256):
+    -> (d[K,D], e[K,D] with e[:, D-1] = 0, hp[K,D] = P^T h)."""
+    B, h = _chk(B, "B"), _chk(h, "h")
+    K, D = h.shape
+    d, e, hp = (torch.empty((K, D), device=B.device, dtype=torch.float32) for _ in range(3))
+    _call("gvi_tridiag_f32", B.data_ptr(), h.data_ptr(), K, D, d.data_ptr(), e.data_ptr(), hp.data_ptr(), _stream())
+    return d, e, hp
+
+
 def weight_update(trust_region: bool, logw, elr, stepsize, temperature: float = 1.0):
     """stepsize: device scalar tensor (or python float).  -> (new_log_weights (un-normalised result of the
     reference's search), info[2] = (kl, eta))."""

@@ -135,6 +135,10 @@ int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const flo
  * num_updates[K] (mode 2: no mean step on a component's first update).
  * Outputs: new means/chols (old ones when success[k]==0), etas[k] / kls[k] (mode 0; -1 on failure). */
 size_t gvi_update_full_workspace(int K, int D);
+/* Householder tridiagonalisation T = P^T S P, hp = P^T h of S[i][j] = S[j][i] = B[min(i,j)][max(i,j)] (D <= 256): the
+ * mode-0 update evaluates KL(eta) of its bisection (:244-333, :335-429) from (d, e, hp) in O(D) per eta.  d[K,D]
+ * diagonal, e[K,D] sub-diagonal (e[k][D-1] = 0). */
+int gvi_tridiag_f32(const float* B, const float* h, int K, int D, float* d, float* e, float* hp, void* stream);
 int gvi_update_full_f32(int mode, const float* means, const float* chols, const float* Hneg, const float* gneg,
                         const float* stepsizes, const float* last_etas, const float* num_updates, int K, int D,
                         float temperature, float* out_means, float* out_chols, int32_t* success, float* etas,

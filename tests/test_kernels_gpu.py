@@ -270,6 +270,55 @@ def test_kl_update_full(K, D, warm):
                 assert np.isclose(kls.cpu().numpy()[k], info["kls"][k], rtol=2e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("D", [1, 2, 3, 5, 33, 100, 256])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_tridiag(D, symmetric):
+    """Householder tridiagonalisation used by the KL-constrained update: T = P^T S P and h' = P^T h for the symmetric
+    matrix S built from the UPPER triangle of B (the triangle the update kernel reads).  Orthogonal invariants: the
+    spectrum, |h| and the Krylov moments h^T S^j h."""
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(50 + D)
+    K = 3
+    A = rng.standard_normal((K, D, D))
+    B = A @ A.transpose(0, 2, 1) / D - 0.3 * np.eye(D) if symmetric else A
+    h = rng.standard_normal((K, D))
+    d, e, hp = (t.cpu().numpy().astype(np.float64) for t in ops.tridiag(dev(B.astype(np.float32)), dev(h.astype(np.float32))))
+    for k in range(K):
+        Bk = B[k].astype(np.float32).astype(np.float64)
+        S = np.triu(Bk) + np.triu(Bk, 1).T
+        T = np.diag(d[k]) + np.diag(e[k][:-1], 1) + np.diag(e[k][:-1], -1)
+        scale = max(np.abs(np.linalg.eigvalsh(S)).max(), 1e-30)
+        assert np.abs(np.linalg.eigvalsh(T) - np.linalg.eigvalsh(S)).max() < 2e-5 * scale
+        hk = h[k].astype(np.float32).astype(np.float64)
+        assert abs(np.linalg.norm(hp[k]) - np.linalg.norm(hk)) < 1e-5 * np.linalg.norm(hk)
+        for j in (1, 2, 3):
+            ref = hk @ np.linalg.matrix_power(S, j) @ hk
+            got = hp[k] @ np.linalg.matrix_power(T, j) @ hp[k]
+            assert abs(got - ref) < 5e-5 * scale ** j * (hk @ hk)
+
+
+@pytest.mark.parametrize("K,D,warm", [(6, 10, False), (4, 64, True), (3, 100, False), (3, 256, True), (2, 256, False)])
+def test_kl_update_tridiagonal_search_matches_cholesky_search(K, D, warm, monkeypatch):
+    """The bisection with KL(eta) from the tridiagonal form must take the decisions of the bisection that factors
+    M(eta) for every eta: same eta (a discrete outcome), same evaluation count, same success flags, and new parameters
+    equal to rounding (the final factorisation is the same code in both)."""
+    from gmmvi_b200 import ops
+    last = np.full(K, 30.0) if warm else None
+    g32, H, gn = _update_problem(K, D, seed=91 + D, last_eta=last)
+    args = ("trust-region", False, dev(g32.means), dev(g32.chol_cov), dev(H), dev(gn), dev(g32.stepsizes),
+            dev(g32.last_log_etas), None, 1.0)
+    monkeypatch.setenv("GMMVI_B200_UPDATE_TRIDIAG", "0")
+    ref = [t.clone() for t in ops.update_components(*args)]
+    ref_evals = ops.last_update_evals.clone()
+    monkeypatch.setenv("GMMVI_B200_UPDATE_TRIDIAG", "1")
+    new = ops.update_components(*args)
+    assert torch.equal(ref[2], new[2])
+    assert torch.equal(ref_evals, ops.last_update_evals)
+    assert torch.equal(ref[3], new[3])                                  # etas
+    assert torch.equal(ref[0], new[0]) and torch.equal(ref[1], new[1])  # same final factorisation -> same bits
+    assert torch.allclose(ref[4], new[4], rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("mode", ["direct", "iBLR"])
 @pytest.mark.parametrize("K,D", [(5, 10), (3, 100), (2, 200)])
 @pytest.mark.parametrize("first", [True, False])
