@@ -1,6 +1,6 @@
 """GmmviRunner (mirror of gmmvi_runner.py:24-200): seeds the generators, builds target + model + GMMVI from one
 config dict, times `train_iter`, returns the reference's metric dict and dumps the GMM as .npz.
-MMD evaluation and matplotlib figures are out of scope."""
+matplotlib figures are out of scope."""
 from __future__ import annotations
 
 import os
@@ -26,8 +26,14 @@ class GmmviRunner:
         target_distribution, initial_model = init_experiment(self.config, device=device)
         self.gmmvi = GMMVI.build_from_config(self.config, target_distribution, initial_model)
         if "mmd_evaluation_config" in config.keys():
-            raise NotImplementedError("MMD evaluation is outside the scope of gmmvi_b200")
-        self.mmd = None
+            # gmmvi_runner.py:45-54; `sample_dir` is looked up next to this file like in the reference, then as given
+            from .experiments.evaluation.mmd import MMD
+            rel = config["mmd_evaluation_config"]["sample_dir"]
+            path = os.path.join(os.path.dirname(os.path.realpath(__file__)), rel)
+            samples = np.load(path if os.path.exists(path) else rel)
+            self.mmd = MMD(samples, config["mmd_evaluation_config"]["alpha"], device=device)
+        else:
+            self.mmd = None
         if "dump_gmm_path" not in self.config:
             self.dump_gmms = False
         else:
@@ -64,6 +70,8 @@ class GmmviRunner:
         out = {"-elbo": float(-elbo.item()), "entropy": float(entropy.item()),
                "target_density": float(mean_reward.item()), "algo_time": float(np.sum(self.wall_times))}
         out.update(g.sample_selector.target_distribution.expensive_metrics(g.model, test_samples))
+        if self.mmd is not None:
+            out.update({"MMD:": float(self.mmd.compute_MMD(test_samples).item())})      # key as in the reference (:142)
         return out
 
     def iterate_and_log(self, n: int) -> dict:

@@ -395,6 +395,17 @@ def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, steps
     return om, oc, succ, etas, kls
 
 
+def gauss_kernel_sum(X, Y, w):
+    """sum_{i,j} exp(-sum_d w[d] (X[i,d] - Y[j,d])^2) -> 0-d float32 tensor (MMD evaluation, mmd.py:38-56)."""
+    X, Y, w = _chk(X, "X"), _chk(Y, "Y"), _chk(w, "w")
+    n1, D = X.shape
+    n2 = Y.shape[0]
+    npart = _lib.lib().gvi_gauss_kernel_sum_partials(n1, n2)
+    partial = torch.zeros(max(npart, 1), device=X.device, dtype=torch.float64)
+    _call("gvi_gauss_kernel_sum_f32", X.data_ptr(), n1, Y.data_ptr(), n2, D, w.data_ptr(), partial.data_ptr(), _stream())
+    return partial.sum().to(torch.float32)
+
+
 def tridiag(B, h):
     """Householder tridiagonalisation of the symmetric matrices S[i][j] = B[k][min(i,j)][max(i,j)] (D <= 256):
     -> (d[K,D], e[K,D] with e[:, D-1] = 0, hp[K,D] = P^T h)."""

@@ -181,6 +181,13 @@ int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- MMD evaluation (experiments/evaluation/mmd.py:41-60) -------------------------------------------------
+ * sum_{i<n1, j<n2} exp(-sum_d w[d] (X[i,d] - Y[j,d])^2): compute_ustat (Y = X) and kernel_mix of the reference with
+ * the diagonal bandwidth w = 1 / (alpha sigma).  The result is the sum of partial[0 .. gvi_gauss_kernel_sum_partials). */
+size_t gvi_gauss_kernel_sum_partials(int n1, int n2);
+int gvi_gauss_kernel_sum_f32(const float* X, int n1, const float* Y, int n2, int D, const float* w, double* partial,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -891,4 +891,41 @@ def train_iter(gmm: OracleGMM, db: OracleSampleDB, target: Callable, cfg: Iterat
                 elr=elr, update=info)
 
 
+# =====================================================================================================
+# MMD evaluation (experiments/evaluation/mmd.py:4-78)
+# =====================================================================================================
+def mmd_sigma(groundtruth, max_points_for_median=1000, dtype=np.float32):
+    """mmd.py:26-36 -> diagonal of the bandwidth matrix: per-dimension median of the squared differences of all pairs
+    i <= j (i == j included) among the first `max_points_for_median` points.  tfp.stats.percentile(x, 50, axis=0)
+    (tensorflow-probability 0.20.1, stats/quantiles.py, default interpolation 'nearest') sorts DESCENDING and takes
+    element tf.round((d - 1) * (1 - q / 100)); tf.round rounds halves to even."""
+    G = np.asarray(groundtruth, dtype)[:int(min(max_points_for_median, len(groundtruth)))]
+    iu, ju = np.triu_indices(len(G))
+    diff = (G[iu] - G[ju]) ** 2
+    d = diff.shape[0]
+    k_desc = int(np.round((d - 1) * 0.5))          # np.round: half to even
+    return np.sort(diff, axis=0)[::-1][k_desc].astype(dtype)
+
+
+def mmd_kernel_sum(X, Y, sigma_diag, alpha, dtype=np.float32):
+    """mmd.py:38-56 (compute_ustat: Y = X; kernel_mix: X = ground truth): row by row like the reference,
+    sum_i sum_j exp(-(x_i - y_j) K (x_i - y_j)) with K = inv(alpha * diag(sigma))."""
+    X, Y = np.asarray(X, dtype), np.asarray(Y, dtype)
+    kern = (1.0 / (dtype(alpha) * np.asarray(sigma_diag, dtype))).astype(dtype)
+    total = dtype(0.0)
+    for i in range(X.shape[0]):
+        diff = X[i] - Y
+        total = total + np.sum(np.exp(-np.sum(diff * kern * diff, axis=1)), dtype=dtype)
+    return total
+
+
+def mmd(groundtruth, model_sample, alpha, dtype=np.float32):
+    """mmd.py:62-78."""
+    sig = mmd_sigma(groundtruth, dtype=dtype)
+    n1, n2 = len(groundtruth), len(model_sample)
+    return (mmd_kernel_sum(groundtruth, groundtruth, sig, alpha, dtype) / n1 ** 2
+            + mmd_kernel_sum(model_sample, model_sample, sig, alpha, dtype) / n2 ** 2
+            - 2 * mmd_kernel_sum(groundtruth, model_sample, sig, alpha, dtype) / (n1 * n2))
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

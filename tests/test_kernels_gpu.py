@@ -470,3 +470,30 @@ def test_more_estimator(K, D, N, self_norm):
     gneg = (quad @ dev(g32.means).unsqueeze(2)).squeeze(2) - lin
     assert rel_err(quad.cpu().numpy(), Href) < 5e-4, rel_err(quad.cpu().numpy(), Href)
     assert rel_err(gneg.cpu().numpy(), gref) < 5e-4
+
+
+@pytest.mark.parametrize("n1,n2,D", [(1, 1, 1), (70, 33, 5), (300, 257, 20), (1100, 500, 40)])
+def test_mmd_matches_oracle(n1, n2, D):
+    """experiments/evaluation/mmd.py on device: bandwidth (an element of the data: exact), U-statistics and MMD against
+    the restatement; n1 = 1100 exercises the 1000-point cap of the median trick and several CTA tiles."""
+    from gmmvi_b200.experiments.evaluation.mmd import MMD
+    rng = np.random.default_rng(n1 + D)
+    G = (rng.standard_normal((n1, D)) * 2 + 1).astype(np.float32)
+    S = (rng.standard_normal((n2, D)) * 2.2 + 1.3).astype(np.float32)
+    if n1 == 1:
+        G[:] = 0.5                                   # a single point: sigma = 0 -> inf bandwidth like the reference
+        m = MMD(G, 3.0)
+        assert float(torch.diagonal(m.sigma)[0]) == 0.0
+        return
+    alpha = 20.0
+    m = MMD(G, alpha)
+    sig = O.mmd_sigma(G, dtype=np.float32)
+    assert np.array_equal(torch.diagonal(m.sigma).cpu().numpy(), sig)
+    assert m.sigma.shape == (D, D)
+    ref_u = O.mmd_kernel_sum(S, S, sig, alpha, np.float64)
+    ref_mix = O.mmd_kernel_sum(G, S, sig, alpha, np.float64)
+    assert np.isclose(float(m.compute_ustat(dev(S), alpha)), ref_u, rtol=2e-5)
+    assert np.isclose(float(m.kernel_mix(dev(S), alpha)), ref_mix, rtol=2e-5, atol=1e-12)
+    ref = O.mmd(G, S, alpha, np.float64)
+    assert np.isclose(float(m.compute_MMD(dev(S))), ref, rtol=1e-3, atol=1e-6)
+    assert abs(float(m.compute_MMD(dev(G)))) < 1e-6

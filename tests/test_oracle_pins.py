@@ -277,3 +277,25 @@ def test_full_iteration_improves_elbo_and_golden_fixture():
     for key in ref.files:
         assert np.allclose(out[key], ref[key], rtol=1e-9, atol=1e-12), key
     assert out["elbo"][-1] > out["elbo"][0]
+
+
+def test_mmd_restatement():
+    """MMD (mmd.py): the median trick picks an ELEMENT of the data ('nearest' percentile, descending sort, halves rounded
+    to even) -- checked against numpy's own 'nearest' percentile where the two conventions coincide and by hand where they
+    do not; the U-statistics against a direct double loop in fp64; MMD(X, X) = 0 and MMD >= 0."""
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((40, 3))
+    sig = O.mmd_sigma(G, dtype=np.float64)
+    iu, ju = np.triu_indices(40)
+    diff = (G[iu] - G[ju]) ** 2                      # d = 820 rows: (d - 1) / 2 = 409.5 -> index 410 of the descending sort
+    for j in range(3):
+        assert sig[j] == np.sort(diff[:, j])[::-1][410]
+    G5 = G[:5]                                       # d = 15: (d - 1) / 2 = 7 exactly, the plain median
+    assert np.allclose(O.mmd_sigma(G5, dtype=np.float64), np.median(((G5[np.triu_indices(5)[0]] - G5[np.triu_indices(5)[1]]) ** 2), axis=0))
+    S = rng.standard_normal((25, 3)) + 0.5
+    w = 1.0 / (2.0 * sig)
+    direct = sum(np.exp(-np.sum(w * (G[i] - S[j]) ** 2)) for i in range(40) for j in range(25))
+    assert np.isclose(O.mmd_kernel_sum(G, S, sig, 2.0, np.float64), direct, rtol=1e-12)
+    assert abs(O.mmd(G, G, 2.0, np.float64)) < 1e-15
+    assert O.mmd(G, S, 2.0, np.float64) > 0.0
+    assert np.isclose(O.mmd(G, S, 2.0, np.float32), O.mmd(G, S, 2.0, np.float64), rtol=1e-4)
