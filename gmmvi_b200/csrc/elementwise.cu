@@ -170,24 +170,51 @@ __device__ __forceinline__ void pb_load_T(double* Lt, const float* __restrict__ 
   }
 }
 
-// inverse of a diagonal block: Dt[m * PP + r] = inv(L_bb)[r][m], from Lt[m * PP + r] = L_bb[r][m]
-__device__ __forceinline__ void pb_diag_inverse(const double* Lt, double* Dt) {
-  if (threadIdx.x < PB) {
-    const int c = threadIdx.x;                     // column c of the inverse = row c of Dt
-    double* y = Dt + c * PP;
-    for (int r = 0; r < c; ++r) y[r] = 0.0;
-    y[c] = 1.0 / Lt[c * PP + c];
-    for (int r = c + 1; r < PB; ++r) {
-      double sacc = 0.0;
-      for (int m = c; m < r; ++m) sacc = fma(Lt[m * PP + r], y[m], sacc);
-      y[r] = -sacc / Lt[r * PP + r];
-    }
+// inverse of a diagonal block by ONE WARP (lane = column c of the inverse = row c of Dt):
+// Dt[m * PP + r] = inv(L_bb)[r][m], from Lt[m * PP + r] = L_bb[r][m]
+__device__ __forceinline__ void pb_diag_inverse_warp(const double* Lt, double* Dt) {
+  const int c = threadIdx.x & 31;
+  double* y = Dt + c * PP;
+  for (int r = 0; r < c; ++r) y[r] = 0.0;
+  y[c] = 1.0 / Lt[c * PP + c];
+  for (int r = c + 1; r < PB; ++r) {
+    double sacc = 0.0;
+    for (int m = c; m < r; ++m) sacc = fma(Lt[m * PP + r], y[m], sacc);
+    y[r] = -sacc / Lt[r * PP + r];
   }
 }
 
+// Inverses of all diagonal 32 x 32 blocks, one warp per block: dinv[b][m * 32 + r] = inv(L_ii)[r][m] for b = k * nb + i.
+// Every column-block CTA of prepare_blocked_kernel needs inv(L_ii) for all i >= j; computing them there (one warp busy
+// for ~7 k cycles, seven idle, once per (i, j) pair) was most of that kernel's critical path.
+constexpr int PD_WARPS = 4;
+__global__ void __launch_bounds__(32 * PD_WARPS)
+prepare_diag_kernel(const float* __restrict__ chol, int D, int nb, int nblocks, double* __restrict__ dinv) {
+  extern __shared__ __align__(16) double pd_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * PD_WARPS + warp;
+  if (b >= nblocks) return;
+  double* Lt = pd_sm + (size_t)warp * 2 * PB * PP;
+  double* Dt = Lt + PB * PP;
+  const int k = b / nb, i = b - k * nb;
+  const float* L = chol + (long long)k * D * D;
+  for (int e = lane; e < PB * PB; e += 32) {
+    const int r = e >> 5, m = e & 31;
+    const int gr = i * PB + r, gc = i * PB + m;
+    double v = (gr == gc) ? 1.0 : 0.0;
+    if (gr < D && gc < D) v = (double)L[(long long)gr * D + gc];
+    Lt[m * PP + r] = v;
+  }
+  __syncwarp();
+  pb_diag_inverse_warp(Lt, Dt);
+  __syncwarp();
+  double* out = dinv + (size_t)b * PB * PB;
+  for (int e = lane; e < PB * PB; e += 32) out[e] = Dt[(e >> 5) * PP + (e & 31)];
+}
+
 __global__ void __launch_bounds__(256)
-prepare_blocked_kernel(const float* __restrict__ chol, int D, int nb, float* __restrict__ linv, float* __restrict__ cst,
-                       int32_t* __restrict__ ok) {
+prepare_blocked_kernel(const float* __restrict__ chol, int D, int nb, const double* __restrict__ dinv,
+                       float* __restrict__ linv, float* __restrict__ cst, int32_t* __restrict__ ok) {
   extern __shared__ __align__(16) double pb_sm[];
   constexpr int BLK = PB * PP;                      // doubles per padded 32 x 32 block
   double* Xs = pb_sm;                               // [nb] blocks: the column block of X being built
@@ -217,24 +244,44 @@ prepare_blocked_kernel(const float* __restrict__ chol, int D, int nb, float* __r
     }
     __syncthreads();
   }
+  const double* dk = dinv + (size_t)k * nb * PB * PB;
 
-  // ---- X_jj ----
-  pb_load_T(Lt, L, D, j, j);
-  __syncthreads();
-  pb_diag_inverse(Lt, Dt);
-  __syncthreads();
+  // ---- X_jj = inv(L_jj): dinv holds it transposed ----
   for (int e = threadIdx.x; e < PB * PB; e += blockDim.x) {
-    const int r = e >> 5, c = e & 31;
-    Xs[r * PP + c] = Dt[c * PP + r];
+    const int c = e >> 5, r = e & 31;
+    Xs[r * PP + c] = dk[(size_t)j * PB * PB + e];
   }
   __syncthreads();
 
-  // ---- X_ij, i > j ----
+  // ---- X_ij, i > j.  The blocks L_ik of the running sum are loaded one step ahead into registers (four elements per
+  // thread), so the L2 latency of a block overlaps the product with the previous one. ----
+  float pre[4];
+  auto fetch = [&](int bi, int bj) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int r = e >> 5, m = e & 31;
+      const int gr = bi * PB + r, gc = bj * PB + m;
+      float v = (gr == gc) ? 1.f : 0.f;
+      if (gr < D && gc < D) v = __ldg(L + (long long)gr * D + gc);
+      pre[q] = v;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      Lt[(e & 31) * PP + (e >> 5)] = (double)pre[q];
+    }
+  };
+  if (j + 1 < nb) fetch(j + 1, j);
   for (int i = j + 1; i < nb; ++i) {
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     for (int kk = j; kk < i; ++kk) {
-      pb_load_T(Lt, L, D, i, kk);
+      stash();
       __syncthreads();
+      if (kk + 1 < i) fetch(i, kk + 1);
+      else if (i + 1 < nb) fetch(i + 1, j);
       pb_acc(acc, Lt, Xs + (size_t)(kk - j) * BLK, ty, tx, 0, PB);
       __syncthreads();
     }
@@ -242,9 +289,7 @@ prepare_blocked_kernel(const float* __restrict__ chol, int D, int nb, float* __r
     Ts[(2 * ty) * PP + 2 * tx + 1] = acc[0][1];
     Ts[(2 * ty + 1) * PP + 2 * tx] = acc[1][0];
     Ts[(2 * ty + 1) * PP + 2 * tx + 1] = acc[1][1];
-    pb_load_T(Lt, L, D, i, i);
-    __syncthreads();
-    pb_diag_inverse(Lt, Dt);
+    for (int e = threadIdx.x; e < PB * PB; e += blockDim.x) Dt[(e >> 5) * PP + (e & 31)] = dk[(size_t)i * PB * PB + e];
     __syncthreads();
     double out[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     pb_acc(out, Dt, Ts, ty, tx, 0, 2 * ty + 2);      // inv(L_ii) is lower triangular: m <= row
@@ -810,7 +855,11 @@ extern "C" const char* gvi_last_error(void) { return g_last_error; }
 
 extern "C" size_t gvi_prepare_full_workspace(int K, int D) {
   if (K <= 0) return 0;
-  if (D <= 256) return tc_gemm_workspace_floats(K, D, D, D) * sizeof(float) + 16;      // blocked path: only the GEMM scratch
+  if (D <= 256) {   // blocked path: the inverses of the diagonal blocks, then (same memory) the GEMM scratch
+    const size_t gemm = tc_gemm_workspace_floats(K, D, D, D) * sizeof(float);
+    const size_t diag = (size_t)K * ceil_div(D, PB) * PB * PB * sizeof(double);
+    return (gemm > diag ? gemm : diag) + 16;
+  }
   return (size_t)K * D * D * sizeof(double);
 }
 extern "C" int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv, float* prec, float* cst,
@@ -838,8 +887,22 @@ extern "C" int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv
     }
     attr_set = true;
   }
-  prepare_blocked_kernel<<<K * nb, 256, smem, (cudaStream_t)stream>>>(chol, D, nb, linv, cst, ok);
-  int rc = check_launch("prepare_blocked_kernel");
+  static bool attr2_set = false;
+  const size_t smem_diag = (size_t)PD_WARPS * 2 * PB * PP * sizeof(double);
+  if (!attr2_set) {
+    cudaError_t e = cudaFuncSetAttribute(prepare_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag);
+    if (e != cudaSuccess) {
+      set_last_error("gvi_prepare_full_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return GVI_ERR_CUDA;
+    }
+    attr2_set = true;
+  }
+  double* dinv = (double*)ws;
+  prepare_diag_kernel<<<ceil_div(K * nb, PD_WARPS), 32 * PD_WARPS, smem_diag, (cudaStream_t)stream>>>(chol, D, nb, K * nb, dinv);
+  int rc = check_launch("prepare_diag_kernel");
+  if (rc) return rc;
+  prepare_blocked_kernel<<<K * nb, 256, smem, (cudaStream_t)stream>>>(chol, D, nb, dinv, linv, cst, ok);
+  rc = check_launch("prepare_blocked_kernel");
   if (rc || prec == nullptr) return rc;
   // prec = linv^T linv (batched, tensor cores in 3xTF32 when the shape allows)
   return launch_gemm_auto(1, 0, K, D, D, D, 1.0f, linv, D, (long long)D * D, linv, D, (long long)D * D, prec, D,
