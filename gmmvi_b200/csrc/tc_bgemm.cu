@@ -229,6 +229,36 @@ split_tf32_strided_vec4_kernel(const float* __restrict__ in, int R, int C4, int 
   }
 }
 
+// hi / lo split of the symmetric matrix read from the LOWER triangle of `in`: out[b][r][c] = in[b][max(r,c)][min(r,c)]
+// (what tf.linalg.cholesky sees of a not exactly symmetric input).  32 x 32 tiles through shared memory so that both
+// the direct and the mirrored reads are coalesced.
+__global__ void split_tf32_symlower_kernel(const float* __restrict__ in, int D, float* __restrict__ hi,
+                                           float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* src = in + (long long)b * D * D;
+  const long long ob = (long long)b * D * D;
+  const bool upper = c0 > r0;                    // tile strictly above the diagonal: read the mirrored tile, transposed
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int rr = (upper ? c0 : r0) + i, cc = (upper ? r0 : c0) + threadIdx.x;
+    tile[i][threadIdx.x] = (rr < D && cc < D) ? src[(long long)rr * D + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < D && c < D) {
+      float x;
+      if (upper) x = tile[threadIdx.x][i];
+      else if (c0 == r0 && c > r) x = tile[threadIdx.x][i];      // diagonal tile: mirror inside the tile
+      else x = tile[i][threadIdx.x];
+      const float h = to_tf32(x);
+      hi[ob + (long long)r * D + c] = h;
+      lo[ob + (long long)r * D + c] = to_tf32(x - h);
+    }
+  }
+}
+
 static int num_sms_cached() {
   static int n = 0;
   if (n == 0) {
@@ -315,9 +345,14 @@ int launch_tc_gemm(int transA, int transB, int batch, int M, int N, int Kd, floa
   else        rc = launch_split_tf32(A, batch, M, Kd, lda, strideA, 0, Ah, Al, st);
   if (rc) return rc;
   // B operand must be [N][Kd]: transB == 0 -> B is [Kd][N], transpose it; transB == 1 -> B is [N][Kd] already
-  if (transB) rc = launch_split_tf32(B, batch, N, Kd, ldb, strideB, 0, Bh, Bl, st);
-  else        rc = launch_split_tf32(B, batch, Kd, N, ldb, strideB, 1, Bh, Bl, st);
-  if (rc) return rc;
+  if (A == B && lda == ldb && strideA == strideB && M == N && (transA != 0) != (transB != 0)) {
+    Bh = Ah;          // X^T X or X X^T: both operands are the same split
+    Bl = Al;
+  } else {
+    if (transB) rc = launch_split_tf32(B, batch, N, Kd, ldb, strideB, 0, Bh, Bl, st);
+    else        rc = launch_split_tf32(B, batch, Kd, N, ldb, strideB, 1, Bh, Bl, st);
+    if (rc) return rc;
+  }
   return launch_tc_bgemm(batch, M, N, Kd, alpha, Ah, Al, Bh, Bl, C, ldc, strideC, st);
 }
 
@@ -343,6 +378,30 @@ int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, fl
     return launch_tc_gemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, ws,
                           st);
   return launch_bgemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, st);
+}
+
+// The two D^3 products of the whitened update, T = Rlow L and B = L^T T with Rlow = the symmetric matrix in the lower
+// triangle of R (update.cu), on the tensor cores with the operand splits shared: the mirror of R is folded into its
+// split, and the transposed split of L serves as B operand of the first and as A operand of the second product
+// (5 kernels instead of mirror + 4 splits + 2 GEMMs).  ws: 6 K D^2 floats.  Returns 1 when the shape / workspace does
+// not allow the tensor-core path (the caller then uses the generic route), 0 on success, < 0 on error.
+size_t tc_update_products_workspace_floats(int K, int D) { return (size_t)6 * K * D * D + 256; }
+int launch_update_products_tc(const float* R, const float* L, int K, int D, float* T, float* Bm, float* ws,
+                              size_t ws_floats, cudaStream_t st) {
+  if (!(tc_gemm_enabled() && ws != nullptr && tc_gemm_supported(D, D, D) && D >= 64 &&
+        ws_floats >= tc_update_products_workspace_floats(K, D) && (reinterpret_cast<uintptr_t>(ws) % 16 == 0)))
+    return 1;
+  const size_t n = (size_t)K * D * D;
+  const long long DD = (long long)D * D;
+  float *Rh = ws, *Rl = ws + n, *Lth = ws + 2 * n, *Ltl = ws + 3 * n, *Tth = ws + 4 * n, *Ttl = ws + 5 * n;
+  dim3 grid(ceil_div(D, 32), ceil_div(D, 32), K), block(32, 8);
+  tcg::split_tf32_symlower_kernel<<<grid, block, 0, st>>>(R, D, Rh, Rl);
+  int rc = check_launch("split_tf32_symlower_kernel");
+  if (rc) return rc;
+  if ((rc = launch_split_tf32(L, K, D, D, D, DD, 1, Lth, Ltl, st))) return rc;            // L^T, [c][r]
+  if ((rc = launch_tc_bgemm(K, D, D, D, 1.f, Rh, Rl, Lth, Ltl, T, D, DD, st))) return rc;     // T = Rlow L
+  if ((rc = launch_split_tf32(T, K, D, D, D, DD, 1, Tth, Ttl, st))) return rc;            // T^T
+  return launch_tc_bgemm(K, D, D, D, 1.f, Lth, Ltl, Tth, Ttl, Bm, D, DD, st);             // B = L^T T
 }
 
 }  // namespace gvi

@@ -29,6 +29,9 @@ int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
 size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
+size_t tc_update_products_workspace_floats(int K, int D);
+int launch_update_products_tc(const float* R, const float* L, int K, int D, float* T, float* Bm, float* ws,
+                              size_t ws_floats, cudaStream_t st);
 
 bool update_blocked_supported(int D);
 int launch_update_full_blocked(int mode, const float* means, const float* chols, const float* Bm, const float* B2,
@@ -570,7 +573,7 @@ extern "C" size_t gvi_update_full_workspace(int K, int D) {
   if (K <= 0) return 0;
   size_t f = (size_t)4 * K * D * D + (size_t)4 * K * D + 64;       // 3 K D: tridiagonal form (mode 0, D <= 256)
   if (upd_smem_bytes(D) > kMaxDynSmem) f += (size_t)K * D * (D + 1) / 2;
-  f = (f + 63) / 64 * 64 + tc_gemm_workspace_floats(K, D, D, D);
+  f = (f + 63) / 64 * 64 + tc_update_products_workspace_floats(K, D);      // >= tc_gemm_workspace_floats(K, D, D, D)
   return f * sizeof(float);
 }
 
@@ -605,16 +608,20 @@ extern "C" int gvi_update_full_f32(int mode, const float* means, const float* ch
   size_t used = (size_t)4 * K * DD + (size_t)4 * K * D + 64;
   if (upd_smem_bytes(D) > kMaxDynSmem) used += (size_t)K * D * (D + 1) / 2;
   float* tcws = (float*)ws + (used + 63) / 64 * 64;
-  const size_t tcws_floats = tc_gemm_workspace_floats(K, D, D, D);
-  dim3 g1(min(ceil_div(D * D, 256), 1024), K);
-  mirror_lower_kernel<<<g1, 256, 0, st>>>(Hneg, D, Rlow);
-  int rc = check_launch("mirror_lower_kernel");
-  if (rc) return rc;
-  // T = Rlow L ;  B = L^T T
-  rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, Rlow, D, DD, chols, D, DD, T, D, DD, tcws, tcws_floats, st);
-  if (rc) return rc;
-  rc = launch_gemm_auto(1, 0, K, D, D, D, 1.f, chols, D, DD, T, D, DD, Bm, D, DD, tcws, tcws_floats, st);
-  if (rc) return rc;
+  const size_t tcws_floats = tc_update_products_workspace_floats(K, D);
+  // T = Rlow L ;  B = L^T T  (Rlow = R mirrored from its lower triangle)
+  int rc = launch_update_products_tc(Hneg, chols, K, D, T, Bm, tcws, tcws_floats, st);
+  if (rc < 0) return rc;
+  if (rc == 1) {      // shapes the tensor-core path does not take
+    dim3 g1(min(ceil_div(D * D, 256), 1024), K);
+    mirror_lower_kernel<<<g1, 256, 0, st>>>(Hneg, D, Rlow);
+    rc = check_launch("mirror_lower_kernel");
+    if (rc) return rc;
+    rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, Rlow, D, DD, chols, D, DD, T, D, DD, tcws, tcws_floats, st);
+    if (rc) return rc;
+    rc = launch_gemm_auto(1, 0, K, D, D, D, 1.f, chols, D, DD, T, D, DD, Bm, D, DD, tcws, tcws_floats, st);
+    if (rc) return rc;
+  }
   if (mode == 2) {
     rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, Bm, D, DD, Bm, D, DD, B2, D, DD, tcws, tcws_floats, st);
     if (rc) return rc;

@@ -47,7 +47,7 @@ if rank == 0:
     ev = [e for e in prof.key_averages() if e.device_time_total > 0]
     tot = sum(e.self_device_time_total for e in ev)
     print(f"sum of device time per iteration: {tot / steps / 1e3:.3f} ms")
-    for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:22]:
+    for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:70]:
         print(f"{e.self_device_time_total / steps / 1e3:8.3f} ms  n={e.count / steps:5.1f}  {e.key[:90]}")
 if world > 1:
     dist.destroy_process_group()
