@@ -6,10 +6,48 @@ import torch
 from .. import ops
 
 
+class _Growable:
+    """Row-appendable device tensor: `view` is buf[:n]; appending copies only the new rows (capacity doubles when it
+    runs out), where torch.cat re-copies -- and re-allocates -- the whole database every iteration (the reference's
+    tf.concat does the same: SURVEY.md section 8, N2)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.buf, self.n = t, int(t.shape[0])
+
+    @property
+    def view(self) -> torch.Tensor:
+        return self.buf[:self.n]
+
+    def append(self, x: torch.Tensor):
+        m = int(x.shape[0])
+        if self.n + m > self.buf.shape[0]:
+            cap = max(2 * int(self.buf.shape[0]), self.n + m, 1024)
+            nb = torch.empty((cap,) + tuple(self.buf.shape[1:]), device=self.buf.device, dtype=self.buf.dtype)
+            nb[:self.n].copy_(self.buf[:self.n])
+            self.buf = nb
+        self.buf[self.n:self.n + m].copy_(x)
+        self.n += m
+
+
+def _stored(name):
+    def get(self):
+        return self._store[name].view
+
+    def set_(self, value):
+        self._store[name] = _Growable(value)
+    return property(get, set_)
+
+
 class SampleDB:
+    # every stored array is a growable buffer behind a plain tensor attribute (reads see the filled rows)
+    samples, means, chols, inv_chols = _stored("samples"), _stored("means"), _stored("chols"), _stored("inv_chols")
+    consts, target_lnpdfs, target_grads, mapping = (_stored("consts"), _stored("target_lnpdfs"),
+                                                    _stored("target_grads"), _stored("mapping"))
+
     def __init__(self, dim, diagonal_covariances, keep_samples, max_samples=None, device="cuda"):
         """optimization/sample_db.py:30-46."""
         self._dim = dim
+        self._store = {}
         self.diagonal_covariances = diagonal_covariances
         self.keep_samples = keep_samples
         self.max_samples = max_samples
@@ -66,15 +104,16 @@ class SampleDB:
         inv, cst = self._invert(chols, prepared)
         mapping = mapping.to(torch.int32)
         if self.keep_samples:
-            self.mapping = torch.cat((self.mapping, mapping + self.chols.shape[0]))
-            self.means = torch.cat((self.means, means), 0)
-            self.chols = torch.cat((self.chols, chols), 0)
-            self.inv_chols = torch.cat((self.inv_chols, inv), 0)
+            st = self._store
+            st["mapping"].append(mapping + int(self.chols.shape[0]))
+            st["means"].append(means)
+            st["chols"].append(chols)
+            st["inv_chols"].append(inv)
             if cst is not None:
-                self.consts = torch.cat((self.consts, cst), 0)
-            self.samples = torch.cat((self.samples, samples), 0)
-            self.target_lnpdfs = torch.cat((self.target_lnpdfs, target_lnpdfs), 0)
-            self.target_grads = torch.cat((self.target_grads, target_grads), 0)
+                st["consts"].append(cst)
+            st["samples"].append(samples)
+            st["target_lnpdfs"].append(target_lnpdfs)
+            st["target_grads"].append(target_grads)
         else:
             self.mapping, self.means, self.chols, self.inv_chols = mapping, means, chols, inv
             self.consts = cst if cst is not None else self.consts
