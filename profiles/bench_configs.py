@@ -45,3 +45,33 @@ timed("C2 SAMTRON planar_robot_4 (ex.6)", runner_for("planar_robot_4", "SAMTRON"
     "num_component_adapter_config": {"del_iters": 10, "add_iters": 1},
     "sample_selector_config": {"desired_samples_per_component": 100, "ratio_reused_samples_to_desired": 0.0},
     "model_initialization": {"num_initial_components": 100}}))
+
+
+def direct_runner(name, D, K, target, codeword, overrides, diag=False, prior_scale=31.63, initial_cov=1.0):
+    """C3 / C4: synthetic fixed-K configurations of BASELINE.json built through the same runner (target passed as
+    config['target_fn'], setup_experiment.py:14-16)."""
+    algo = update_config(get_default_algorithm_config(codeword), overrides)
+    config = update_config({"start_seed": 1, "use_sample_database": False, "max_database_size": 10000000, "temperature": 1.0,
+                            "model_initialization": {"use_diagonal_covs": diag, "num_initial_components": K,
+                                                     "prior_mean": 0.0, "prior_scale": prior_scale,
+                                                     "initial_cov": initial_cov},
+                            "gmmvi_runner_config": {"log_metrics_interval": 10 ** 9}}, algo)
+    config["target_fn"] = target
+    timed(name, GmmviRunner.build_from_config(config))
+
+
+from gmmvi_b200.experiments.target_distributions.gmm import make_target as make_gmm_target  # noqa: E402
+from gmmvi_b200.experiments.target_distributions.student_t_mixture import make_target as make_stm_target  # noqa: E402
+
+# C3: 100-D 10-mode GMM target, 50 full-covariance components, 4096 samples per iteration (mixture-based selector:
+# desired_samples_per_component is the TOTAL, sample_selector.py:322), MORE + trust-region weights
+direct_runner("C3 GMM100 target, K=50, N=4096, MORE + TR weights", 100, 50, make_gmm_target(100), "ZEPTFOX", {
+    "sample_selector_config": {"desired_samples_per_component": 4096, "ratio_reused_samples_to_desired": 0.0},
+    "component_stepsize_adapter_config": {"initial_stepsize": 0.01}})
+# C4: 200-D Student-T mixture, 256 components, 64 samples per component (16384 per iteration), Stein + iBLR, fixed
+# stepsize 1e-4 (examples/3: guidance for iBLR), diagonal and full covariances
+for diag in (True, False):
+    direct_runner(f"C4 STM200 target, K=256, N=16384, Stein + iBLR, {'diagonal' if diag else 'full'} cov", 200, 256,
+                  make_stm_target(200, False, device="cuda"), "SEMYFUX", {
+        "sample_selector_config": {"desired_samples_per_component": 64, "ratio_reused_samples_to_desired": 0.0},
+        "component_stepsize_adapter_config": {"initial_stepsize": 1e-4}}, diag=diag, prior_scale=100.0, initial_cov=300.0)
