@@ -50,6 +50,10 @@ _SIGNATURES = {
     "gvi_more_fit_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_i,
                                    c_vp, C.c_size_t, c_vp]),
     "gvi_update_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_mixture_grad_full_h16_supported": (C.c_int, [C.c_int]),
+    "gvi_split_h16_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_vp, c_vp, c_f, c_vp]),
+    "gvi_mixture_grad_full_h16_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_vp, c_vp, c_f, c_f, c_f, c_f,
+                                                C.c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "gvi_gauss_kernel_sum_partials": (C.c_size_t, [C.c_int, C.c_int]),
     "gvi_gauss_kernel_sum_f32": (C.c_int, [c_f, C.c_int, c_f, C.c_int, C.c_int, c_f, c_vp, c_vp]),
     "gvi_tridiag_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_vp]),

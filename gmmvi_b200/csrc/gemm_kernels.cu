@@ -499,6 +499,13 @@ extern "C" int gvi_logdens_full_f32(const float* X, int N, int D, const float* m
   return launch_logdens_full(X, N, D, means, linv, cst, K, lq, (cudaStream_t)stream);
 }
 
+namespace gvi {
+int launch_resp_mask(const float* lq, const float* logw, const float* logq, int K, int N, uint32_t* mask, cudaStream_t st) {
+  resp_mask_kernel<<<ceil_div(N, BM), 128, ceil_div(K, 32) * sizeof(uint32_t), st>>>(lq, logw, logq, K, N, mask);
+  return check_launch("resp_mask_kernel");
+}
+}  // namespace gvi
+
 extern "C" size_t gvi_mixture_grad_full_workspace(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   return (size_t)ceil_div(N, BM) * ceil_div(K, 32) * sizeof(uint32_t);

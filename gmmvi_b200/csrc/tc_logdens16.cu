@@ -838,11 +838,337 @@ static size_t smem_bytes_t(int Dp) {
 
 }  // namespace h16t
 
+// =====================================================================================================
+// Mixture gradient on the same structure:  grad[n, :] = - sum_k r_kn P_k (x_n - mu_k)      (models/gmm.py:274-300)
+//
+// Work item = (128-sample tile t, component k) with some responsibility r_kn > e^-60 in the tile (bit mask from
+// resp_mask_kernel); every role of the CTA walks the mask of its tiles in the same order.  Per item the producers
+// write A = r_kn (x_n - mu_k) s (fp16 hi / lo, tensor memory, exactly like the log-density kernel plus the row
+// factor), and the item is issued in two phases h = 0, 1 for the output columns [h Dp/2, (h + 1) Dp/2): the TMA warp
+// loads that half of the fp16-split precision matrix P_k (rows = output columns; 128 KB at D = 256) into shared
+// memory, the MMAs run over all K-steps into the half accumulator h, the epilogue adds -Z / (s t_k) into grad
+// (vector reductions performed in L2: all items of a tile belong to the same CTA and are retired in order by the same
+// threads, so the sum is deterministic).  The A stages stay in TMEM for both phases.  P_k is used once per item, so the
+// load of the next half is exposed (single buffer); at C5 that is 1.5 items per tile and irrelevant, and in the dense
+// worst case the kernel is still several times faster than the SIMT tile engine it replaces.
+namespace mg {
+using namespace h16t;
+
+struct BarriersM {
+  uint64_t full[RING];
+  uint64_t empty[RING];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t b_full;
+  uint64_t b_free;
+  uint32_t tmem_base;
+};
+
+// Fire-and-forget vector add into global memory (performed in L2).  A read-modify-write in the epilogue costs an L2
+// round trip per 32-column chunk (~10 us per item, 9 % tensor activity); the reduction does not wait.  Every address is
+// only ever updated by one thread, in program order, so the sum stays deterministic.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// the (tile, component) items of tiles [tile, tile_end) in mask order
+struct Walker {
+  const uint32_t* mask;
+  int words, tile, tile_end, wd;
+  uint32_t bits;
+  __device__ __forceinline__ void init(const uint32_t* m, int w, int t0, int t1) {
+    mask = m; words = w; tile = t0; tile_end = t1; wd = 0;
+    bits = t0 < t1 ? __ldg(m + (long long)t0 * w) : 0u;
+  }
+  __device__ __forceinline__ bool next(int& t, int& k) {
+    while (true) {
+      if (bits) {
+        k = wd * 32 + (__ffs(bits) - 1);
+        bits &= bits - 1;
+        t = tile;
+        return true;
+      }
+      if (++wd == words) { wd = 0; ++tile; }
+      if (tile >= tile_end) return false;
+      bits = __ldg(mask + (long long)tile * words + wd);
+    }
+  }
+};
+
+template <int NST>
+__global__ void __launch_bounds__(THREADS, 1)
+mixgrad_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                   const float* __restrict__ X, const float* __restrict__ tileinf, int N, int D,
+                   const float* __restrict__ means, const float* __restrict__ minf, const float* __restrict__ tmaxp,
+                   const float* __restrict__ lq, const float* __restrict__ logw, const float* __restrict__ logq, int K,
+                   const uint32_t* __restrict__ mask, int words, float* __restrict__ grad) {
+  constexpr int Dp = 32 * NST, Hh = 16 * NST, NKB = Dp / KB;
+  constexpr uint32_t HALF_BYTES = (uint32_t)NKB * Hh * 128;        // one split half of the resident P rows
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + HALF_BYTES;
+  BarriersM* bars = reinterpret_cast<BarriersM*>(smem + 2 * HALF_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ceil_div(N, TILE_M);
+  const int t_begin = (int)((long long)T * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(&bars->full[s], 4);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->acc_full[b], 1);
+      mbar_init(&bars->acc_empty[b], 4);
+    }
+    mbar_init(&bars->b_full, 1);
+    mbar_init(&bars->b_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    reg_dec<56>();
+    if (warp == 0) {
+      // ---------------- TMA: the half h of P_k (hi, lo) for every (item, h) ----------------
+      if (lane == 0) {
+        Walker wk;
+        wk.init(mask, words, t_begin, t_end);
+        int t, k;
+        uint32_t p = 0;                                          // phase counter: (item, h) pairs
+        while (wk.next(t, k)) {
+          for (int h = 0; h < 2; ++h, ++p) {
+            if (p > 0) mbar_wait_sleepy(&bars->b_free, (p - 1) & 1u);
+            mbar_arrive_expect_tx(&bars->b_full, 2u * HALF_BYTES);
+            for (int kb = 0; kb < NKB; ++kb)
+              for (int r = 0; r < Hh; r += 64) {
+                tma_load_2d(b_hi + (size_t)(kb * Hh + r) * 128, &map_hi, &bars->b_full, kb * KB, k * Dp + h * Hh + r);
+                tma_load_2d(b_lo + (size_t)(kb * Hh + r) * 128, &map_lo, &bars->b_full, kb * KB, k * Dp + h * Hh + r);
+              }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer: both phases of every item ----------------
+      Walker wk;
+      wk.init(mask, words, t_begin, t_end);
+      int t, k;
+      uint32_t it = 0, p = 0, g0 = 0;
+      uint64_t bhi_desc0 = make_desc(smem_u32(b_hi)), blo_desc0 = make_desc(smem_u32(b_lo));
+      while (wk.next(t, k)) {
+        uint32_t tb = tmem_base;
+        asm volatile("" : "+l"(bhi_desc0), "+l"(blo_desc0), "+r"(tb));      // re-derive operand addresses per item
+#pragma unroll
+        for (int h = 0; h < 2; ++h, ++p) {
+          mbar_wait_sleepy(&bars->b_full, p & 1u);
+          mbar_wait_sleepy(&bars->acc_empty[h], (it & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t acc = tb + (uint32_t)(h == 0 ? ACC0 : ACC1);
+          const uint32_t idesc = make_idesc_f16(Hh);
+#pragma unroll
+          for (int si = 0; si < NST; ++si) {
+            const uint32_t g = g0 + (uint32_t)si;
+            const uint32_t slot = NST == RING ? (uint32_t)si : (g & (RING - 1));
+            if (h == 0) {
+              mbar_wait_fast(smem_u32(&bars->full[slot]), NST == RING ? (it & 1u) : ((g >> 3) & 1u));
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint32_t a0 = tb + slot * 32u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const int c = 2 * si + ks;
+                const uint64_t boffk = (uint64_t)((uint32_t)((c >> 2) * Hh * 8) + (uint32_t)((c & 3) * 2));
+                const uint64_t bd_hi = bhi_desc0 + boffk, bd_lo = blo_desc0 + boffk;
+                const uint32_t a_hi = a0 + (uint32_t)(ks * 16), a_lo = a_hi + 8u;
+                umma_f16_ts(acc, a_hi, bd_hi, idesc, c != 0 ? 1u : 0u);
+                umma_f16_ts(acc, a_lo, bd_hi, idesc, 1u);
+                umma_f16_ts(acc, a_hi, bd_lo, idesc, 1u);
+              }
+              if (h == 1) umma_commit(&bars->empty[slot]);
+              if (si == NST - 1) {
+                umma_commit(&bars->acc_full[h]);
+                umma_commit(&bars->b_free);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        ++it;
+        g0 += NST;
+      }
+    }
+  } else if (wg == 1) {
+    reg_dec<72>();
+    // ---------------- epilogue: grad[n, h Hh + c] -= Z[n, c] / (s t_k) ----------------
+    const int q = warp - 4;
+    Walker wk;
+    wk.init(mask, words, t_begin, t_end);
+    int t, k;
+    uint32_t it = 0;
+    while (wk.next(t, k)) {
+      const int n = t * TILE_M + 32 * q + lane;
+      const float f = -1.0f / (pow2_scale(__ldg(tileinf + t) + __ldg(minf + k)) * pow2_scale(__ldg(tmaxp + k)));
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait_sleepy(&bars->acc_full[h], it & 1u);
+        tc_fence_after();
+        for (int cb = 0; cb < Hh / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((h == 0 ? ACC0 : ACC1) + cb * 32), v);
+          tmem_ld_wait();
+          const int col0 = h * Hh + cb * 32;
+          if (n < N) {
+            float* gp = grad + (long long)n * D + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < D)                                    // D % 4 == 0: the whole float4 is inside
+                red_add_v4(gp + i, f * __uint_as_float(v[i]), f * __uint_as_float(v[i + 1]),
+                           f * __uint_as_float(v[i + 2]), f * __uint_as_float(v[i + 3]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[h]);
+      }
+      ++it;
+    }
+  } else {
+    reg_inc<88>();
+    // ---------------- A producers: r_kn (x_n - mu_k) s, fp16 hi / lo, into tensor memory ----------------
+    const int grp = (warp - 8) >> 2;
+    const int q = warp & 3;
+    const int c4 = lane & 3;
+    const int rsub = 32 * q + (lane >> 2);
+    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+    const float4* __restrict__ M4 = reinterpret_cast<const float4*>(means);
+    const int D4 = D >> 2;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16);
+    struct Half {
+      float4 x[4];
+      float a0, a1;                                            // log responsibilities of my two rows
+      float bound;                                             // tileinf + minf of the item
+    };
+    // load stream: stage s_ld of item (t_ld, k_ld), half h_ld; store stream likewise (two walkers over the same items)
+    Walker wl, ws_;
+    wl.init(mask, words, t_begin, t_end);
+    ws_.init(mask, words, t_begin, t_end);
+    int t_ld = 0, k_ld = 0, t_st = 0, k_st = 0;
+    bool ld_ok = wl.next(t_ld, k_ld);
+    ws_.next(t_st, k_st);
+    int s_ld = grp, h_ld = 0, s_st = grp, h_st = 0;
+    while (ld_ok && s_ld >= NST) {                             // NST = 4, grp < 4: never; kept for symmetry
+      s_ld -= NST;
+      ld_ok = wl.next(t_ld, k_ld);
+    }
+    uint32_t g_st = (uint32_t)grp;
+    float sc_cur = 0.f;
+    auto issue = [&](Half& R) -> bool {
+      if (!ld_ok) return false;
+      const int col4 = s_ld * 8 + c4;
+      const int ca = min(col4, D4 - 1), cb = min(col4 + 4, D4 - 1);
+      const int row0 = t_ld * TILE_M + rsub + 16 * h_ld;
+      const int r0 = min(row0, N - 1), r1 = min(row0 + 8, N - 1);
+      R.x[0] = __ldg(X4 + (r0 * D4 + ca));
+      R.x[1] = __ldg(X4 + (r0 * D4 + cb));
+      R.x[2] = __ldg(X4 + (r1 * D4 + ca));
+      R.x[3] = __ldg(X4 + (r1 * D4 + cb));
+      const float lw = __ldg(logw + k_ld);
+      R.a0 = row0 < N ? __ldg(lq + (long long)k_ld * N + r0) + lw - __ldg(logq + r0) : -INFINITY;
+      R.a1 = row0 + 8 < N ? __ldg(lq + (long long)k_ld * N + r1) + lw - __ldg(logq + r1) : -INFINITY;
+      R.bound = __ldg(tileinf + t_ld) + __ldg(minf + k_ld);
+      h_ld ^= 1;
+      if (h_ld == 0) {
+        s_ld += 4;
+        if (s_ld >= NST) {
+          s_ld -= NST;
+          ld_ok = wl.next(t_ld, k_ld);
+        }
+      }
+      return true;
+    };
+    auto emit = [&](const Half& R) {
+      const uint32_t slot = g_st & (RING - 1);
+      if (h_st == 0) {
+        sc_cur = pow2_scale(R.bound);
+        mbar_wait_sleepy(&bars->empty[slot], ((g_st >> 3) & 1u) ^ 1u);
+        tc_fence_after();
+      }
+      const float scr0 = R.a0 > -60.f ? expf(R.a0) * sc_cur : 0.f;
+      const float scr1 = R.a1 > -60.f ? expf(R.a1) * sc_cur : 0.f;
+      const int col4 = s_st * 8 + c4;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const bool colok = col4 + 4 * b < D4;
+        const float4 m = __ldg(M4 + (k_st * D4 + min(col4 + 4 * b, D4 - 1)));
+        uint32_t r[8];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const float sc = colok ? (a ? scr1 : scr0) : 0.f;
+          const float4 x = R.x[2 * a + b];
+          const float2 v01 = ffma2(make_float2(x.x, x.y), sc, make_float2(-m.x * sc, -m.y * sc));
+          const float2 v23 = ffma2(make_float2(x.z, x.w), sc, make_float2(-m.z * sc, -m.w * sc));
+          const __half2 h01 = __floats2half2_rn(v01.x, v01.y), h23 = __floats2half2_rn(v23.x, v23.y);
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          const __half2 l01 = __floats2half2_rn(sub_f32_f16(v01.x, (unsigned short)(u01 & 0xffffu)),
+                                                sub_f32_f16(v01.y, (unsigned short)(u01 >> 16)));
+          const __half2 l23 = __floats2half2_rn(sub_f32_f16(v23.x, (unsigned short)(u23 & 0xffffu)),
+                                                sub_f32_f16(v23.y, (unsigned short)(u23 >> 16)));
+          r[2 * a] = u01;
+          r[2 * a + 1] = u23;
+          r[4 + 2 * a] = *reinterpret_cast<const uint32_t*>(&l01);
+          r[4 + 2 * a + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+        }
+        tmem_st_16x256b_x2(taddr0 + ((uint32_t)(16 * h_st) << 16) + slot * 32u + (uint32_t)(16 * b), r);
+      }
+      h_st ^= 1;
+      if (h_st == 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->full[slot]);
+        g_st += 4;
+        s_st += 4;
+        if (s_st >= NST) {
+          s_st -= NST;
+          ws_.next(t_st, k_st);
+        }
+      }
+    };
+    Half R0, R1;
+    bool v0 = issue(R0);
+    while (v0) {
+      const bool v1 = issue(R1);
+      emit(R0);
+      if (!v1) break;
+      v0 = issue(R0);
+      emit(R1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int NST>
+static size_t smem_bytes_m() { return (size_t)2 * (32 * NST / KB) * (16 * NST) * 128 + 1024 + 256; }
+
+}  // namespace mg
+
 // One CTA per component: t = max |Linv_k| -> scale 2^e with |Linv| 2^e < 2^14; write zero-padded fp16 hi / lo.
 // D % 4 == 0 (a condition of the fp16 kernels): float4 loads, 8-byte stores of four halves.
 __global__ void __launch_bounds__(512)
 split_h16_kernel(const float* __restrict__ linv, int D, int Dp, __half* __restrict__ hi, __half* __restrict__ lo,
-                 float* __restrict__ tmax) {
+                 float* __restrict__ tmax, int full) {
   __shared__ float scratch[34];
   const int k = blockIdx.x;
   const float4* __restrict__ src = reinterpret_cast<const float4*>(linv + (long long)k * D * D);
@@ -860,13 +1186,13 @@ split_h16_kernel(const float* __restrict__ linv, int D, int Dp, __half* __restri
   for (int i = threadIdx.x; i < Dp * Dp4; i += blockDim.x) {
     const int r = i / Dp4, c4 = i - r * Dp4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < D && c4 < D4 && 4 * c4 <= r) {                    // blocks entirely above the diagonal stay zero
+    if (r < D && c4 < D4 && (full || 4 * c4 <= r)) {          // triangular input: blocks above the diagonal stay zero
       v = __ldg(src + (r * D4 + c4));
-      // strictly-upper entries are structurally zero
+      // triangular input: strictly-upper entries are structurally zero
       v.x *= sc;
-      v.y = 4 * c4 + 1 <= r ? v.y * sc : 0.f;
-      v.z = 4 * c4 + 2 <= r ? v.z * sc : 0.f;
-      v.w = 4 * c4 + 3 <= r ? v.w * sc : 0.f;
+      v.y = (full || 4 * c4 + 1 <= r) ? v.y * sc : 0.f;
+      v.z = (full || 4 * c4 + 2 <= r) ? v.z * sc : 0.f;
+      v.w = (full || 4 * c4 + 3 <= r) ? v.w * sc : 0.f;
     }
     const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -930,8 +1256,91 @@ extern "C" int gvi_split_h16_f32(const float* linv, int K, int D, void* hi, void
                   reinterpret_cast<uintptr_t>(lo) % 8 == 0,
               "gvi_split_h16_f32: needs D %% 4 == 0 and aligned operands");
   h16::split_h16_kernel<<<K, 512, 0, (cudaStream_t)stream>>>(linv, D, h16::padded_dim(D), (__half*)hi, (__half*)lo,
-                                                             tmax);
+                                                             tmax, 0);
   return check_launch("split_h16_kernel");
+}
+
+// The same split for a FULL matrix per component (the precision matrices of the tensor-core mixture gradient).
+extern "C" int gvi_split_h16_full_f32(const float* mat, int K, int D, void* hi, void* lo, float* tmax, void* stream) {
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_split_h16_full_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(mat && hi && lo && tmax, "gvi_split_h16_full_f32: null pointer");
+  GVI_REQUIRE(D % 4 == 0 && reinterpret_cast<uintptr_t>(mat) % 16 == 0 && reinterpret_cast<uintptr_t>(hi) % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(lo) % 8 == 0,
+              "gvi_split_h16_full_f32: needs D %% 4 == 0 and aligned operands");
+  h16::split_h16_kernel<<<K, 512, 0, (cudaStream_t)stream>>>(mat, D, h16::padded_dim(D), (__half*)hi, (__half*)lo, tmax,
+                                                             1);
+  return check_launch("split_h16_kernel");
+}
+
+namespace gvi {
+int launch_resp_mask(const float* lq, const float* logw, const float* logq, int K, int N, uint32_t* mask, cudaStream_t st);
+}
+
+extern "C" int gvi_mixture_grad_full_h16_supported(int D) {
+  return (D % 4 == 0 && ((D > 64 && D <= 128) || (D > 192 && D <= 256))) ? 1 : 0;      // Dp = 128 or 256
+}
+
+// grad[N, D] = - sum_k r_kn P_k (x_n - mu_k) on the tensor cores (mg::mixgrad_h16_kernel).  p_hi / p_lo / tmaxp: the
+// fp16 split of prec[K, D, D] from gvi_split_h16_full_f32; tileinf / minf as for gvi_logdens_full_h16_f32; ws: the
+// block mask, gvi_mixture_grad_full_workspace(N, K) bytes.
+extern "C" int gvi_mixture_grad_full_h16_f32(const float* X, const float* tileinf, int N, int D, const float* means,
+                                             const float* minf, const void* p_hi, const void* p_lo, const float* tmaxp,
+                                             const float* lq, const float* logw, const float* logq, int K, float* grad,
+                                             void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_mixture_grad_full_h16_f32: bad sizes");
+  if (!gvi_mixture_grad_full_h16_supported(D)) {
+    set_last_error("gvi_mixture_grad_full_h16_f32: D=%d unsupported (D %% 4 == 0 and 64 < D <= 128 or 192 < D <= 256)", D);
+    return GVI_ERR_UNSUPPORTED;
+  }
+  if (N == 0) return GVI_OK;
+  GVI_REQUIRE(X && tileinf && means && minf && p_hi && p_lo && tmaxp && lq && logw && logq && grad && ws,
+              "gvi_mixture_grad_full_h16_f32: null pointer");
+  GVI_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(means) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(grad) % 16 == 0 && reinterpret_cast<uintptr_t>(p_hi) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(p_lo) % 16 == 0,
+              "gvi_mixture_grad_full_h16_f32: operands must be 16-byte aligned");
+  const int T = ceil_div(N, h16::TILE_M), words = ceil_div(K, 32);
+  GVI_REQUIRE(ws_bytes >= (size_t)T * words * sizeof(uint32_t), "gvi_mixture_grad_full_h16_f32: workspace too small");
+  const int Dp = h16::padded_dim(D);
+  GVI_REQUIRE((long long)K * Dp < 2147483647LL && (long long)N * D < 2147483647LL,
+              "gvi_mixture_grad_full_h16_f32: K*D or N*D too large (32-bit offsets)");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* mask = (uint32_t*)ws;
+  int rc = launch_resp_mask(lq, logw, logq, K, N, mask, st);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(grad, 0, (size_t)N * D * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_last_error("gvi_mixture_grad_full_h16_f32: memset: %s", cudaGetErrorString(e));
+    return GVI_ERR_CUDA;
+  }
+  CUtensorMap map_hi, map_lo;
+  if ((rc = h16::make_map_h16(&map_hi, p_hi, K, Dp))) return rc;
+  if ((rc = h16::make_map_h16(&map_lo, p_lo, K, Dp))) return rc;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaFuncSetAttribute(h16::mg::mixgrad_h16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)h16::mg::smem_bytes_m<8>());
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(h16::mg::mixgrad_h16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)h16::mg::smem_bytes_m<4>());
+    if (e != cudaSuccess) {
+      set_last_error("gvi_mixture_grad_full_h16_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      num_sms = 0;
+      return GVI_ERR_CUDA;
+    }
+  }
+  const int grid = min(num_sms, T);
+  if (Dp == 256)
+    h16::mg::mixgrad_h16_kernel<8><<<grid, h16::THREADS, h16::mg::smem_bytes_m<8>(), st>>>(
+        map_hi, map_lo, X, tileinf, N, D, means, minf, tmaxp, lq, logw, logq, K, mask, words, grad);
+  else
+    h16::mg::mixgrad_h16_kernel<4><<<grid, h16::THREADS, h16::mg::smem_bytes_m<4>(), st>>>(
+        map_hi, map_lo, X, tileinf, N, D, means, minf, tmaxp, lq, logw, logq, K, mask, words, grad);
+  return check_launch("mixgrad_h16_kernel");
 }
 
 extern "C" int gvi_group_absmax_f32(const float* in, long long rows, int cols, int group, float* out, void* stream) {

@@ -211,7 +211,28 @@ def mixture_lse(lq, logw):
     return out
 
 
-def mixture_grad_full(X, means, prec, lq, logw, logq):
+_P16_CACHE = []         # [(key, prec, hi, lo, tmax)]
+TC_MIXGRAD = os.environ.get("GMMVI_B200_TC_MIXGRAD", "1") != "0"
+
+
+def split_h16_full(prec):
+    """Zero-padded, power-of-two scaled fp16 (hi, lo) copies of full matrices [K, D, D] (the precisions) + tmax[K]."""
+    key = (prec.data_ptr(), prec._version, tuple(prec.shape))
+    for k_, _, hi, lo, tmax in _P16_CACHE:
+        if k_ == key:
+            return hi, lo, tmax
+    K, D, _ = prec.shape
+    Dp = _lib.lib().gvi_h16_padded_dim(D)
+    hi = torch.empty((K, Dp, Dp), device=prec.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    tmax = torch.empty(K, device=prec.device, dtype=torch.float32)
+    _call("gvi_split_h16_full_f32", prec.data_ptr(), K, D, hi.data_ptr(), lo.data_ptr(), tmax.data_ptr(), _stream())
+    _P16_CACHE.insert(0, (key, prec, hi, lo, tmax))
+    del _P16_CACHE[3:]
+    return hi, lo, tmax
+
+
+def mixture_grad_full(X, means, prec, lq, logw, logq, tensor_cores=None):
     X, means, prec = _chk(X, "X"), _chk(means, "means"), _chk(prec, "prec")
     lq, logw, logq = _chk(lq, "lq"), _chk(logw, "logw"), _chk(logq, "logq")
     N, D = X.shape
@@ -219,6 +240,13 @@ def mixture_grad_full(X, means, prec, lq, logw, logq):
     grad = torch.empty_like(X)
     nbytes = _lib.lib().gvi_mixture_grad_full_workspace(N, K)
     ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.int32)
+    use_tc = (USE_TENSOR_CORES and TC_MIXGRAD) if tensor_cores is None else bool(tensor_cores)
+    if use_tc and N > 0 and K > 0 and _lib.lib().gvi_mixture_grad_full_h16_supported(int(D)):
+        hi, lo, tmaxp = split_h16_full(prec)
+        _call("gvi_mixture_grad_full_h16_f32", X.data_ptr(), group_absmax(X, 128).data_ptr(), N, D, means.data_ptr(),
+              group_absmax(means, 1).data_ptr(), hi.data_ptr(), lo.data_ptr(), tmaxp.data_ptr(), lq.data_ptr(),
+              logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), ws.data_ptr(), nbytes, _stream(), kernels=2)
+        return grad
     _call("gvi_mixture_grad_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), lq.data_ptr(),
           logw.data_ptr(), logq.data_ptr(), K, grad.data_ptr(), ws.data_ptr(), nbytes, _stream(), kernels=2)
     return grad

@@ -181,6 +181,17 @@ int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- tensor-core mixture gradient (same contraction as gvi_mixture_grad_full_f32) ------------------------------
+ * grad[n, :] = -sum_k r_kn P_k (x_n - mu_k) with tcgen05 MMAs in the 2 x fp16 split precision of the log-density kernel.
+ * p_hi / p_lo / tmaxp: gvi_split_h16_full_f32(prec); tileinf[ceil(N/128)] / minf[K]: gvi_group_absmax_f32 of X (groups of
+ * 128 rows) and of means; ws: gvi_mixture_grad_full_workspace(N, K) bytes.  D % 4 == 0, 64 < D <= 128 or 192 < D <= 256. */
+int gvi_mixture_grad_full_h16_supported(int D);
+int gvi_split_h16_full_f32(const float* mat, int K, int D, void* hi, void* lo, float* tmax, void* stream);
+int gvi_mixture_grad_full_h16_f32(const float* X, const float* tileinf, int N, int D, const float* means,
+                                  const float* minf, const void* p_hi, const void* p_lo, const float* tmaxp,
+                                  const float* lq, const float* logw, const float* logq, int K, float* grad, void* ws,
+                                  size_t ws_bytes, void* stream);
+
 /* ---- MMD evaluation (experiments/evaluation/mmd.py:41-60) -------------------------------------------------
  * sum_{i<n1, j<n2} exp(-sum_d w[d] (X[i,d] - Y[j,d])^2): compute_ustat (Y = X) and kernel_mix of the reference with
  * the diagonal bandwidth w = 1 / (alpha sigma).  The result is the sum of partial[0 .. gvi_gauss_kernel_sum_partials). */
