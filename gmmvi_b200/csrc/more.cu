@@ -12,8 +12,16 @@
 //   Q_z = -(T + T^T) with T = upper-triangular scatter of theta, r_z, then the un-whitening of :184-189.
 // The reference solves the (symmetric positive definite) system with an LU (tf.linalg.solve); a Cholesky factorisation
 // gives the same solution and reports a non-positive pivot through ok[k] instead of returning garbage.
+//
+// Tensor-core route (default, gvi_more_tensor_cores()): the two O(F^2 N) / O(F^3) products run on tcgen05 in 3xTF32
+// (tc_bgemm.cu).  The feature kernel writes S = sqrt(w) Phi directly as the operand the MMA wants - transposed
+// [F+1][N] (reduction dimension contiguous) and split into TF32 hi / lo - so A' = S^T S needs one operand; the
+// reduction over the samples is cut into 512-sample segments added with round-to-nearest adds; only tiles of the
+// lower triangle are computed.  The trailing update A22 -= T21 T21^T of the blocked Cholesky takes the hi / lo
+// split of the panel from the kernel that copies the panel back.
 #include "common.cuh"
 #include "../../include/gmmvi_b200.h"
+#include <stdlib.h>
 
 namespace gvi {
 
@@ -21,6 +29,10 @@ int launch_bgemm_ex(int transA, int transB, int batch, int M, int N, int Kd, flo
                     long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                     long long strideC, const float* scaleK, long long strideScale, float beta, int lower_only,
                     cudaStream_t st);
+int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
+                       const float* Bl, float* C, int ldc, long long strideC, float beta, int kseg_kblocks,
+                       int lower_only, cudaStream_t st);
+bool tc_gemm_enabled();
 
 namespace more {
 
@@ -76,9 +88,65 @@ features_kernel(const float* __restrict__ Z, const float* __restrict__ y, int N,
   }
 }
 
-__global__ void ridge_kernel(float* __restrict__ A, int Fa, int F, const float* __restrict__ l2, int k0) {
+// Tensor-core operand: S[kc][f][n] = sqrt(w_kn) Phi[n][f] as TF32 hi / lo, [Fa][Np] with the samples contiguous
+// (Np = N rounded up to 4, the padding is zero).  One CTA = 32 samples, a warp walks the features (lane = sample),
+// so every store instruction writes 128 contiguous bytes.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256)
+features_split_kernel(const float* __restrict__ Z, const float* __restrict__ y, const float* __restrict__ W, int N,
+                      int Np, int D, int F, int k0, float* __restrict__ Sh, float* __restrict__ Sl) {
+  extern __shared__ float zs[];      // [32][D + 1]
+  __shared__ float sw[32], sy[32];
   const int kc = blockIdx.y;
-  float* Ak = A + (long long)kc * Fa * Fa;
+  const int n0 = blockIdx.x * 32;
+  const int Dp = D + 1;
+  const float* Zk = Z + (long long)kc * N * D;
+  for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {
+    const int r = e / D, d = e % D;
+    zs[r * Dp + d] = (n0 + r < N) ? Zk[(long long)(n0 + r) * D + d] : 0.f;
+  }
+  if (threadIdx.x < 32) {
+    const int n = n0 + threadIdx.x;
+    sw[threadIdx.x] = n < N ? sqrtf(fmaxf(W[(long long)(k0 + kc) * N + n], 0.f)) : 0.f;
+    sy[threadIdx.x] = n < N ? y[n] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nq = D * (D + 1) / 2, Fa = F + 1;
+  const float* zr = zs + lane * Dp;
+  const float w = sw[lane];
+  const bool live = n0 + lane < Np;
+  float* oh = Sh + (long long)kc * Fa * Np + n0 + lane;
+  float* ol = Sl + (long long)kc * Fa * Np + n0 + lane;
+  // (i, j) of quadratic feature f = warp, advanced by nwarps per step
+  int i = 0, j = warp;
+  while (i < D && j >= D) { j = j - D + i + 1; ++i; }
+  for (int f = warp; f < Fa; f += nwarps) {
+    float v;
+    if (f < nq) {
+      v = zr[i] * zr[j];
+      j += nwarps;
+      while (i < D && j >= D) { j = j - D + i + 1; ++i; }
+    } else if (f < nq + D) v = zr[f - nq];
+    else if (f == F - 1) v = 1.f;
+    else v = sy[lane];
+    v *= w;
+    const float h = tf32_rna(v);
+    if (live) {
+      oh[(long long)f * Np] = h;
+      ol[(long long)f * Np] = tf32_rna(v - h);
+    }
+  }
+}
+
+// (Fa = row pitch of A, sA = distance between the matrices of two components, here and below)
+__global__ void ridge_kernel(float* __restrict__ A, int Fa, long long sA, int F, const float* __restrict__ l2, int k0) {
+  const int kc = blockIdx.y;
+  float* Ak = A + kc * sA;
   const float lam = l2[k0 + kc];
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F - 1; f += gridDim.x * blockDim.x)
     Ak[(long long)f * Fa + f] += lam;
@@ -86,13 +154,13 @@ __global__ void ridge_kernel(float* __restrict__ A, int Fa, int F, const float* 
 
 // Diagonal block [nb x nb] at (p, p): in-place Cholesky (fp64 accumulation) and its inverse into Sinv[kc][NB][NB].
 __global__ void __launch_bounds__(256)
-potrf_inv_kernel(float* __restrict__ A, int Fa, int p, int nb, float* __restrict__ Sinv, int32_t* __restrict__ ok,
-                 int k0) {
+potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, float* __restrict__ Sinv,
+                 int32_t* __restrict__ ok, int k0) {
   extern __shared__ float sm[];          // L[nb][NB+1], Y[nb][NB+1]
   float* L = sm;
   float* Y = sm + NB * (NB + 1);
   const int kc = blockIdx.x;
-  float* Ak = A + (long long)kc * Fa * Fa + (long long)p * Fa + p;
+  float* Ak = A + kc * sA + (long long)p * Fa + p;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int e = tid; e < nb * nb; e += nt) {
     const int i = e / nb, j = e % nb;
@@ -101,12 +169,26 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, int p, int nb, float* __restrict
   __syncthreads();
   __shared__ int bad;
   if (tid == 0) bad = 0;
+  // Two threads per row (even / odd columns of the dot product, two accumulators each: the fp64 chain and the
+  // fp32 -> fp64 conversions bound this kernel), combined with a shuffle inside the pair.
+  const int half = tid & 1, pr = tid >> 1;
   for (int j = 0; j < nb; ++j) {
     __syncthreads();
-    for (int i = j + tid; i < nb; i += nt) {
-      double s = (double)L[i * (NB + 1) + j];
-      for (int m = 0; m < j; ++m) s -= (double)L[i * (NB + 1) + m] * (double)L[j * (NB + 1) + m];
-      L[i * (NB + 1) + j] = (float)s;     // unscaled
+    {
+      const int i = j + pr;                       // blockDim = 256 covers the nb <= 128 rows below the diagonal
+      const float* Li = L + min(i, nb - 1) * (NB + 1);
+      const float* Lj = L + j * (NB + 1);
+      double s0 = 0.0, s1 = 0.0;
+      int m = half;
+      for (; m + 2 < j; m += 4) {
+        s0 += (double)Li[m] * (double)Lj[m];
+        s1 += (double)Li[m + 2] * (double)Lj[m + 2];
+      }
+      if (m < j) s0 += (double)Li[m] * (double)Lj[m];
+      double s = s0 + s1;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      __syncwarp();
+      if (half == 0 && i < nb) L[i * (NB + 1) + j] = (float)((double)Li[j] - s);     // unscaled
     }
     __syncthreads();
     float piv = L[j * (NB + 1) + j];
@@ -119,14 +201,27 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, int p, int nb, float* __restrict
     for (int i = j + tid; i < nb; i += nt) L[i * (NB + 1) + j] = (i == j) ? c : L[i * (NB + 1) + j] / c;
   }
   __syncthreads();
-  // inverse, thread per column
-  for (int c = tid; c < nb; c += nt) {
-    for (int i = 0; i < c; ++i) Y[i * (NB + 1) + c] = 0.f;
-    Y[c * (NB + 1) + c] = 1.f / L[c * (NB + 1) + c];
+  // inverse: a thread pair per column
+  for (int c = pr; c < nb; c += nt / 2) {
+    const unsigned pm = 3u << ((tid & 31) & ~1);
+    if (half == 0) {
+      for (int i = 0; i < c; ++i) Y[i * (NB + 1) + c] = 0.f;
+      Y[c * (NB + 1) + c] = 1.f / L[c * (NB + 1) + c];
+    }
+    __syncwarp(pm);
     for (int i = c + 1; i < nb; ++i) {
-      double s = 0.0;
-      for (int m = c; m < i; ++m) s += (double)L[i * (NB + 1) + m] * (double)Y[m * (NB + 1) + c];
-      Y[i * (NB + 1) + c] = (float)(-s / (double)L[i * (NB + 1) + i]);
+      const float* Li = L + i * (NB + 1);
+      double s0 = 0.0, s1 = 0.0;
+      int m = c + half;
+      for (; m + 2 < i; m += 4) {
+        s0 += (double)Li[m] * (double)Y[m * (NB + 1) + c];
+        s1 += (double)Li[m + 2] * (double)Y[(m + 2) * (NB + 1) + c];
+      }
+      if (m < i) s0 += (double)Li[m] * (double)Y[m * (NB + 1) + c];
+      double s = s0 + s1;
+      s += __shfl_xor_sync(pm, s, 1);
+      if (half == 0) Y[i * (NB + 1) + c] = (float)(-s / (double)Li[i]);
+      __syncwarp(pm);
     }
   }
   __syncthreads();
@@ -139,43 +234,77 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, int p, int nb, float* __restrict
   if (tid == 0 && bad && ok) ok[k0 + kc] = 0;
 }
 
-// A[kc][r0 + r][p + c] = T[kc][r][c]
+// A[kc][r0 + r][p + c] = T[kc][r][c]; with Th / Tl also the dense TF32 hi / lo split [kc][rows][nb] of the panel
 __global__ void copy_panel_kernel(const float* __restrict__ T, int ldt, long long strideT, float* __restrict__ A, int Fa,
-                                  int r0, int p, int rows, int nb) {
+                                  long long strideA, int r0, int p, int rows, int nb, float* __restrict__ Th,
+                                  float* __restrict__ Tl) {
   const int kc = blockIdx.y;
   const float* Tk = T + kc * strideT;
-  float* Ak = A + (long long)kc * Fa * Fa;
+  float* Ak = A + kc * strideA;
+  const long long ob = (long long)kc * rows * nb;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)rows * nb;
        e += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(e / nb), c = (int)(e % nb);
-    Ak[(long long)(r0 + r) * Fa + p + c] = Tk[(long long)r * ldt + c];
+    const float v = Tk[(long long)r * ldt + c];
+    Ak[(long long)(r0 + r) * Fa + p + c] = v;
+    if (Th) {
+      const float h = tf32_rna(v);
+      Th[ob + e] = h;
+      Tl[ob + e] = tf32_rna(v - h);
+    }
   }
 }
 
 // Back substitution L^T theta = v (v = row F of the factored augmented matrix), then the coefficients are unpacked:
-// Qz = -(T + T^T), rz.  One CTA per component.
+// Qz = -(T + T^T), rz.  One CTA per component.  Blocked by BS rows from the bottom: warp 0 solves the BS x BS diagonal
+// block held in shared memory (lane = two unknowns, theta broadcast by shuffle), then all threads subtract the block's
+// contribution from the remaining right-hand side, thread = column, rows of L read coalesced.
+constexpr int BS = 64;
 __global__ void __launch_bounds__(1024)
-backsolve_unpack_kernel(const float* __restrict__ A, int Fa, int F, int D, float* __restrict__ theta_ws,
+backsolve_unpack_kernel(const float* __restrict__ A, int Fa, long long sA, int F, int D, float* __restrict__ theta_ws,
                         float* __restrict__ Qz, float* __restrict__ rz) {
   extern __shared__ float v[];       // [F]
-  __shared__ float ts;
+  __shared__ float Ld[BS][BS + 1];
+  __shared__ float th[BS];
   const int kc = blockIdx.x;
-  const float* Ak = A + (long long)kc * Fa * Fa;
+  const float* Ak = A + kc * sA;
   float* theta = theta_ws + (long long)kc * F;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   for (int f = tid; f < F; f += nt) v[f] = Ak[(long long)F * Fa + f];
-  __syncthreads();
-  for (int i = F - 1; i >= 0; --i) {
-    const float* Li = Ak + (long long)i * Fa;
-    if (tid == 0) {
-      ts = v[i] / Li[i];
-      theta[i] = ts;
+  for (int p = ((F - 1) / BS) * BS; p >= 0; p -= BS) {
+    const int nb = min(BS, F - p);
+    for (int e = tid; e < nb * nb; e += nt) {
+      const int i = e / nb, j = e % nb;
+      Ld[i][j] = Ak[(long long)(p + i) * Fa + p + j];
+    }
+    __syncthreads();        // also orders the v updates of the previous block
+    if (tid < 32) {
+      float v0 = lane < nb ? v[p + lane] : 0.f, v1 = lane + 32 < nb ? v[p + lane + 32] : 0.f;
+      for (int i = nb - 1; i >= 0; --i) {
+        const float vi = __shfl_sync(0xffffffffu, i < 32 ? v0 : v1, i & 31);
+        const float t = vi / Ld[i][i];
+        if (lane == 0) th[i] = t;
+        if (lane < i) v0 = fmaf(-Ld[i][lane], t, v0);
+        if (lane + 32 < i) v1 = fmaf(-Ld[i][lane + 32], t, v1);
+      }
     }
     __syncthreads();
-    const float t = ts;
-    for (int m = tid; m < i; m += nt) v[m] = fmaf(-Li[m], t, v[m]);
-    __syncthreads();
+    for (int i = tid; i < nb; i += nt) theta[p + i] = th[i];
+    for (int m = tid; m < p; m += nt) {
+      const float* col = Ak + (long long)p * Fa + m;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int i = 0;
+      for (; i + 3 < nb; i += 4) {
+        a0 = fmaf(col[(long long)i * Fa], th[i], a0);
+        a1 = fmaf(col[(long long)(i + 1) * Fa], th[i + 1], a1);
+        a2 = fmaf(col[(long long)(i + 2) * Fa], th[i + 2], a2);
+        a3 = fmaf(col[(long long)(i + 3) * Fa], th[i + 3], a3);
+      }
+      for (; i < nb; ++i) a0 = fmaf(col[(long long)i * Fa], th[i], a0);
+      v[m] -= (a0 + a1) + (a2 + a3);
+    }
   }
+  __syncthreads();
   const int nq = D * (D + 1) / 2;
   float* Q = Qz + (long long)kc * D * D;
   for (int e = tid; e < D * D; e += nt) {
@@ -204,19 +333,24 @@ unwhiten_lin_kernel(const float* __restrict__ linv, const float* __restrict__ me
 }
 
 struct Layout {
-  size_t xc, z, phi, a, sinv, t21, theta, qz, rz, t1, total;
+  size_t xc, z, phi, sh, sl, a, sinv, t21, t21h, t21l, theta, qz, rz, t1, total;
 };
-static Layout layout(int Kc, int N, int D) {
-  const size_t F = (size_t)D * (D + 1) / 2 + D + 1, Fa = F + 1;
+static inline int pitch_of(int Fa) { return (Fa + 3) & ~3; }      // 16-byte aligned rows of the normal matrix
+static Layout layout(int Kc, int N, int D, bool tc) {
+  const size_t F = (size_t)D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = pitch_of((int)Fa), Np = ((size_t)N + 3) & ~(size_t)3;
   Layout l;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
   l.xc = take((size_t)Kc * N * D);
   l.z = take((size_t)Kc * N * D);
-  l.phi = take((size_t)Kc * N * Fa);
-  l.a = take((size_t)Kc * Fa * Fa);
+  l.phi = take(tc ? 0 : (size_t)Kc * N * Fa);
+  l.sh = take(tc ? (size_t)Kc * Fa * Np : 0);
+  l.sl = take(tc ? (size_t)Kc * Fa * Np : 0);
+  l.a = take((size_t)Kc * Fa * ld);
   l.sinv = take((size_t)Kc * NB * NB);
   l.t21 = take((size_t)Kc * Fa * NB);
+  l.t21h = take(tc ? (size_t)Kc * Fa * NB : 0);
+  l.t21l = take(tc ? (size_t)Kc * Fa * NB : 0);
   l.theta = take((size_t)Kc * F);
   l.qz = take((size_t)Kc * D * D);
   l.rz = take((size_t)Kc * D);
@@ -225,14 +359,23 @@ static Layout layout(int Kc, int N, int D) {
   return l;
 }
 
+static bool more_tc() {      // read per call: the tests switch routes inside one process
+  const char* e = getenv("GMMVI_B200_MORE_TC");
+  return !(e != nullptr && e[0] == '0') && tc_gemm_enabled();
+}
+
+constexpr int KSEG = 16;      // 16 k-blocks of 32 = 512 samples per accumulator segment of the normal-equation build
+
 }  // namespace more
 }  // namespace gvi
 
 using namespace gvi;
 
+extern "C" int gvi_more_tensor_cores(void) { return more::more_tc() ? 1 : 0; }
+
 extern "C" size_t gvi_more_workspace(int chunk, int N, int D) {
   if (chunk <= 0 || N <= 0 || D <= 0) return 0;
-  return more::layout(chunk, N, D).total * sizeof(float);
+  return more::layout(chunk, N, D, more::more_tc()).total * sizeof(float);
 }
 
 extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const float* linv, const float* W,
@@ -246,17 +389,25 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     return GVI_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int F = D * (D + 1) / 2 + D + 1, Fa = F + 1;
-  const more::Layout l = more::layout(chunk, N, D);
+  const bool tc = more::more_tc() && (reinterpret_cast<uintptr_t>(ws) % 16 == 0);
+  if (more::more_tc() && !tc) {
+    set_last_error("gvi_more_fit_f32: workspace must be 16-byte aligned for the tensor-core route");
+    return GVI_ERR_INVALID;
+  }
+  const int F = D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = more::pitch_of(Fa), Np = (N + 3) & ~3;
+  const long long sA = (long long)Fa * ld;
+  const more::Layout l = more::layout(chunk, N, D, tc);
   float* base = (float*)ws;
-  float *Xc = base + l.xc, *Z = base + l.z, *Phi = base + l.phi, *A = base + l.a, *Sinv = base + l.sinv,
-        *T21 = base + l.t21, *theta = base + l.theta, *Qz = base + l.qz, *rz = base + l.rz, *T1 = base + l.t1;
+  float *Xc = base + l.xc, *Z = base + l.z, *Phi = base + l.phi, *Sh = base + l.sh, *Sl = base + l.sl, *A = base + l.a,
+        *Sinv = base + l.sinv, *T21 = base + l.t21, *T21h = base + l.t21h, *T21l = base + l.t21l,
+        *theta = base + l.theta, *Qz = base + l.qz, *rz = base + l.rz, *T1 = base + l.t1;
   const long long DD = (long long)D * D, ND = (long long)N * D;
   static bool attr_done = false;
   const size_t potrf_smem = (size_t)2 * more::NB * (more::NB + 1) * sizeof(float);
   if (!attr_done) {
     cudaFuncSetAttribute(more::potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
     cudaFuncSetAttribute(more::backsolve_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(more::features_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   if ((size_t)F * sizeof(float) > 200 * 1024) {
@@ -273,38 +424,53 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     rc = launch_bgemm_ex(0, 1, Kc, N, D, D, 1.f, Xc, D, ND, linv + (long long)k0 * DD, D, DD, Z, D, ND, nullptr, 0, 0.f,
                          0, st);
     if (rc) return rc;
-    dim3 g2(ceil_div(N, 8), Kc);
-    more::features_kernel<<<g2, 256, 8 * D * sizeof(float), st>>>(Z, y, N, D, F, Phi);
-    if ((rc = check_launch("more::features_kernel"))) return rc;
-    // A' = Phi^T diag(w) Phi (lower triangle)
-    rc = launch_bgemm_ex(1, 0, Kc, Fa, Fa, N, 1.f, Phi, Fa, (long long)N * Fa, Phi, Fa, (long long)N * Fa, A, Fa,
-                         (long long)Fa * Fa, W + (long long)k0 * N, N, 0.f, 1, st);
-    if (rc) return rc;
+    if (tc) {
+      // S = sqrt(w) Phi, transposed and split; A' = S^T S (lower triangle)
+      dim3 g2(ceil_div(Np, 32), Kc);
+      more::features_split_kernel<<<g2, 256, (size_t)32 * (D + 1) * sizeof(float), st>>>(Z, y, W, N, Np, D, F, k0, Sh, Sl);
+      if ((rc = check_launch("more::features_split_kernel"))) return rc;
+      rc = launch_tc_bgemm_ex(Kc, Fa, Fa, Np, 1.f, Sh, Sl, Sh, Sl, A, ld, sA, 0.f, more::KSEG, 1, st);
+      if (rc) return rc;
+    } else {
+      dim3 g2(ceil_div(N, 8), Kc);
+      more::features_kernel<<<g2, 256, 8 * D * sizeof(float), st>>>(Z, y, N, D, F, Phi);
+      if ((rc = check_launch("more::features_kernel"))) return rc;
+      // A' = Phi^T diag(w) Phi (lower triangle)
+      rc = launch_bgemm_ex(1, 0, Kc, Fa, Fa, N, 1.f, Phi, Fa, (long long)N * Fa, Phi, Fa, (long long)N * Fa, A, ld, sA,
+                           W + (long long)k0 * N, N, 0.f, 1, st);
+      if (rc) return rc;
+    }
     dim3 g3(ceil_div(F, 256), Kc);
-    more::ridge_kernel<<<g3, 256, 0, st>>>(A, Fa, F, l2reg, k0);
+    more::ridge_kernel<<<g3, 256, 0, st>>>(A, ld, sA, F, l2reg, k0);
     if ((rc = check_launch("more::ridge_kernel"))) return rc;
     // blocked Cholesky of A[:F,:F], carried through row F
     for (int p = 0; p < F; p += more::NB) {
       const int nb = min(more::NB, F - p);
-      more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, Fa, p, nb, Sinv, ok, k0);
+      more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, nb, Sinv, ok, k0);
       if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
       const int r0 = p + nb, rows = Fa - r0;
       if (rows <= 0) continue;
       // T21 = A21 Linv11^T
-      rc = launch_bgemm_ex(0, 1, Kc, rows, nb, nb, 1.f, A + (long long)r0 * Fa + p, Fa, (long long)Fa * Fa, Sinv,
-                           more::NB, (long long)more::NB * more::NB, T21, more::NB, (long long)Fa * more::NB, nullptr, 0,
-                           0.f, 0, st);
+      rc = launch_bgemm_ex(0, 1, Kc, rows, nb, nb, 1.f, A + (long long)r0 * ld + p, ld, sA, Sinv, more::NB,
+                           (long long)more::NB * more::NB, T21, more::NB, (long long)Fa * more::NB, nullptr, 0, 0.f, 0,
+                           st);
       if (rc) return rc;
+      // the tensor-core trailing update wants a reduction length that is a multiple of 4 and enough rows to fill a tile
+      const bool tc_trail = tc && nb % 4 == 0 && rows >= 64;
       dim3 g4((unsigned)min((long long)1024, ((long long)rows * nb + 255) / 256), Kc);
-      more::copy_panel_kernel<<<g4, 256, 0, st>>>(T21, more::NB, (long long)Fa * more::NB, A, Fa, r0, p, rows, nb);
+      more::copy_panel_kernel<<<g4, 256, 0, st>>>(T21, more::NB, (long long)Fa * more::NB, A, ld, sA, r0, p, rows, nb,
+                                                  tc_trail ? T21h : nullptr, tc_trail ? T21l : nullptr);
       if ((rc = check_launch("more::copy_panel_kernel"))) return rc;
       // A22 -= T21 T21^T (lower triangle)
-      rc = launch_bgemm_ex(0, 1, Kc, rows, rows, nb, -1.f, T21, more::NB, (long long)Fa * more::NB, T21, more::NB,
-                           (long long)Fa * more::NB, A + (long long)r0 * Fa + r0, Fa, (long long)Fa * Fa, nullptr, 0,
-                           1.f, 1, st);
+      if (tc_trail)
+        rc = launch_tc_bgemm_ex(Kc, rows, rows, nb, -1.f, T21h, T21l, T21h, T21l, A + (long long)r0 * ld + r0, ld, sA,
+                                1.f, 0, 1, st);
+      else
+        rc = launch_bgemm_ex(0, 1, Kc, rows, rows, nb, -1.f, T21, more::NB, (long long)Fa * more::NB, T21, more::NB,
+                             (long long)Fa * more::NB, A + (long long)r0 * ld + r0, ld, sA, nullptr, 0, 1.f, 1, st);
       if (rc) return rc;
     }
-    more::backsolve_unpack_kernel<<<Kc, 1024, F * sizeof(float), st>>>(A, Fa, F, D, theta, Qz, rz);
+    more::backsolve_unpack_kernel<<<Kc, 1024, F * sizeof(float), st>>>(A, ld, sA, F, D, theta, Qz, rz);
     if ((rc = check_launch("more::backsolve_unpack_kernel"))) return rc;
     // quad = Linv^T Qz Linv
     rc = launch_bgemm_ex(0, 0, Kc, D, D, D, 1.f, Qz, D, DD, linv + (long long)k0 * DD, D, DD, T1, D, DD, nullptr, 0, 0.f,

@@ -8,8 +8,15 @@
 // Persistent, warp-specialised: warp 0 = TMA producer (A hi/lo 128 x 32, B hi/lo NT x 32 per k-block, 128B swizzle,
 // 2-stage ring), warp 1 = MMA issuer (3 tcgen05.mma per 8-wide k-step, fp32 accumulators in TMEM, double buffered),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> alpha -> global).
+//
+// Long reductions (the MORE normal equations Phi^T W Phi reduce over thousands of samples, least_squares.py:60-75) are
+// cut into segments of `kseg` k-blocks: the tensor core's fp32 accumulator truncates, so every segment starts a fresh
+// accumulator (the two TMEM buffers alternate) and the epilogue adds it to C in global memory with round-to-nearest
+// adds, the old values of C prefetched one 32-column chunk ahead.  `beta` = 1 adds to the existing C (trailing update of
+// the blocked Cholesky), `lower_only` enumerates only the tiles that touch the lower triangle.
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace gvi {
 namespace tcg {
@@ -37,14 +44,16 @@ struct Barriers {
 __global__ void __launch_bounds__(THREADS, 1)
 tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, int batch, int M,
-                int N, int Kd, float alpha, float* __restrict__ C, int ldc, long long strideC) {
+                int N, int Kd, float alpha, float* __restrict__ C, int ldc, long long strideC, float beta, int kseg,
+                int lower_only, int tiles_per_batch) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt_n = ceil_div(M, TILE_M), nt_n = ceil_div(N, ACC_COLS);
-  const long long total = (long long)batch * mt_n * nt_n;
+  const long long total = (long long)batch * tiles_per_batch;
   const int nkb = ceil_div(Kd, KBLK);
+  const int nseg = ceil_div(nkb, kseg);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -64,10 +73,22 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
   const uint32_t tmem_base = bars->tmem_base;
 
   auto decode = [&](long long w, int& b, int& m0, int& n0, int& nt) {
-    b = (int)(w / (mt_n * nt_n));
-    const int r = (int)(w % (mt_n * nt_n));
-    m0 = (r / nt_n) * TILE_M;
-    n0 = (r % nt_n) * ACC_COLS;
+    b = (int)(w / tiles_per_batch);
+    int r = (int)(w % tiles_per_batch);
+    if (lower_only) {
+      // row mt of the tile grid keeps the column tiles with n0 <= m0 + TILE_M - 1: min(nt_n, mt / 2 + 1) of them
+      int mt = 0;
+      for (;; ++mt) {
+        const int cnt = min(nt_n, (mt * TILE_M + TILE_M - 1) / ACC_COLS + 1);
+        if (r < cnt) break;
+        r -= cnt;
+      }
+      m0 = mt * TILE_M;
+      n0 = r * ACC_COLS;
+    } else {
+      m0 = (r / nt_n) * TILE_M;
+      n0 = (r % nt_n) * ACC_COLS;
+    }
     nt = min(ACC_COLS, (N - n0 + 15) & ~15);      // MMA N: multiple of 16, rows beyond N are zero-filled by TMA
   };
 
@@ -98,69 +119,133 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       long long it = 0;
-      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (long long w = blockIdx.x; w < total; w += gridDim.x) {
         int b, m0, n0, nt;
         decode(w, b, m0, n0, nt);
-        const int buf = (int)(it & 1);
-        const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&bars->acc_empty[buf], (use & 1) ^ 1);
-        tc_fence_after();
         const uint32_t idesc = make_idesc(nt);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&bars->full[s], ph);
+        for (int seg = 0; seg < nseg; ++seg, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t use = (uint32_t)(it >> 1);
+          mbar_wait(&bars->acc_empty[buf], (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+          const int kb_end = min(nkb, (seg + 1) * kseg);
+          for (int kb = seg * kseg; kb < kb_end; ++kb) {
+            mbar_wait(&bars->full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+            const int first = kb == seg * kseg;
 #pragma unroll
-          for (int ks = 0; ks < KBLK / 8; ++ks) {
-            const uint64_t a_hi = make_desc(st + ks * 32);
-            const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
-            const uint64_t b_hi = make_desc(st + 2 * A_BYTES + ks * 32);
-            const uint64_t b_lo = make_desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            for (int ks = 0; ks < KBLK / 8; ++ks) {
+              const uint64_t a_hi = make_desc(st + ks * 32);
+              const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
+              const uint64_t b_hi = make_desc(st + 2 * A_BYTES + ks * 32);
+              const uint64_t b_lo = make_desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            }
+            umma_commit(&bars->empty[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-          umma_commit(&bars->empty[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          umma_commit(&bars->acc_full[buf]);
         }
-        umma_commit(&bars->acc_full[buf]);
       }
     }
   } else if (warp >= 4) {
     const int q = warp - 4;
     long long it = 0;
     const bool vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && (strideC % 4 == 0);
-    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
       int b, m0, n0, nt;
       decode(w, b, m0, n0, nt);
-      const int buf = (int)(it & 1);
-      const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&bars->acc_full[buf], use & 1);
-      tc_fence_after();
       const int m = m0 + 32 * q + lane;
       float* crow = C + b * strideC + (long long)m * ldc + n0;
-      for (int c = 0; c * 32 < nt; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + c * 32), v);
-        tmem_ld_wait();
-        if (m < M) {
-          const int ncol = min(32, N - (n0 + c * 32));
-          if (vec && ncol == 32) {
+      for (int seg = 0; seg < nseg; ++seg, ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t use = (uint32_t)(it >> 1);
+        const bool add = seg > 0 || beta != 0.f;       // C (+)= alpha * acc
+        if (!add) {
+          mbar_wait(&bars->acc_full[buf], use & 1);
+          tc_fence_after();
+          for (int c = 0; c * 32 < nt; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + c * 32), v);
+            tmem_ld_wait();
+            if (m < M) {
+              const int ncol = min(32, N - (n0 + c * 32));
+              if (vec && ncol == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(crow + c * 32 + i) =
-                  make_float4(alpha * __uint_as_float(v[i]), alpha * __uint_as_float(v[i + 1]),
-                              alpha * __uint_as_float(v[i + 2]), alpha * __uint_as_float(v[i + 3]));
-          } else {
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(crow + c * 32 + i) =
+                      make_float4(alpha * __uint_as_float(v[i]), alpha * __uint_as_float(v[i + 1]),
+                                  alpha * __uint_as_float(v[i + 2]), alpha * __uint_as_float(v[i + 3]));
+              } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncol) crow[c * 32 + i] = alpha * __uint_as_float(v[i]);
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncol) crow[c * 32 + i] = alpha * __uint_as_float(v[i]);
+              }
+            }
+          }
+        } else {
+          // read-modify-write with the old values of C fetched one chunk ahead (the first chunk before the wait for the
+          // accumulator); this thread wrote them itself in the previous segment, or a previous kernel did (beta)
+          const float bscale = seg > 0 ? 1.f : beta;
+          float4 old[2][8];
+          auto fetch = [&](int c, float4 (&o)[8]) {
+            if (m < M && c * 32 < nt) {
+              const int ncol = min(32, N - (n0 + c * 32));
+              if (vec && ncol == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = *reinterpret_cast<const float4*>(crow + c * 32 + 4 * i);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  o[i].x = 4 * i + 0 < ncol ? crow[c * 32 + 4 * i + 0] : 0.f;
+                  o[i].y = 4 * i + 1 < ncol ? crow[c * 32 + 4 * i + 1] : 0.f;
+                  o[i].z = 4 * i + 2 < ncol ? crow[c * 32 + 4 * i + 2] : 0.f;
+                  o[i].w = 4 * i + 3 < ncol ? crow[c * 32 + 4 * i + 3] : 0.f;
+                }
+              }
+            }
+          };
+          fetch(0, old[0]);
+          mbar_wait(&bars->acc_full[buf], use & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < ACC_COLS / 32; ++c) {
+            if (c * 32 < nt) {
+              fetch(c + 1, old[(c + 1) & 1]);
+              uint32_t v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + c * 32), v);
+              tmem_ld_wait();
+              if (m < M) {
+                const float4(&o)[8] = old[c & 1];
+                const int ncol = min(32, N - (n0 + c * 32));
+                if (vec && ncol == 32) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(crow + c * 32 + 4 * i) =
+                        make_float4(fmaf(alpha, __uint_as_float(v[4 * i]), bscale * o[i].x),
+                                    fmaf(alpha, __uint_as_float(v[4 * i + 1]), bscale * o[i].y),
+                                    fmaf(alpha, __uint_as_float(v[4 * i + 2]), bscale * o[i].z),
+                                    fmaf(alpha, __uint_as_float(v[4 * i + 3]), bscale * o[i].w));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (4 * i + 0 < ncol) crow[c * 32 + 4 * i + 0] = fmaf(alpha, __uint_as_float(v[4 * i + 0]), bscale * o[i].x);
+                    if (4 * i + 1 < ncol) crow[c * 32 + 4 * i + 1] = fmaf(alpha, __uint_as_float(v[4 * i + 1]), bscale * o[i].y);
+                    if (4 * i + 2 < ncol) crow[c * 32 + 4 * i + 2] = fmaf(alpha, __uint_as_float(v[4 * i + 2]), bscale * o[i].z);
+                    if (4 * i + 3 < ncol) crow[c * 32 + 4 * i + 3] = fmaf(alpha, __uint_as_float(v[4 * i + 3]), bscale * o[i].w);
+                  }
+                }
+              }
+            }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&bars->acc_empty[buf]);
       }
-      tc_fence_before();
-      mbar_arrive(&bars->acc_empty[buf]);
     }
   }
   tc_fence_before();
@@ -296,9 +381,17 @@ int launch_split_tf32(const float* in, int batch, int R, int Cc, int ld, long lo
   return check_launch("split_tf32_strided_kernel");
 }
 
-// C[b] = alpha * A[b] B[b]^T with A [b][M][Kd], B [b][N][Kd] densely packed hi / lo operands
-int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
-                    const float* Bl, float* C, int ldc, long long strideC, cudaStream_t st) {
+// C[b] = alpha * A[b] B[b]^T + beta * C[b] with A [b][M][Kd], B [b][N][Kd] densely packed hi / lo operands.
+//   kseg_kblocks > 0: the reduction is cut into segments of that many 32-wide k-blocks, added to C with round-to-nearest
+//                     adds (0 = one segment);  beta is 0 or 1;  lower_only: tiles strictly above the diagonal are skipped.
+static int tiles_lower(int mt_n, int nt_n) {
+  int t = 0;
+  for (int mt = 0; mt < mt_n; ++mt) t += std::min(nt_n, (mt * tcg::TILE_M + tcg::TILE_M - 1) / tcg::ACC_COLS + 1);
+  return t;
+}
+int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
+                       const float* Bl, float* C, int ldc, long long strideC, float beta, int kseg_kblocks,
+                       int lower_only, cudaStream_t st) {
   if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
   if (!tc_gemm_supported(M, N, Kd)) {
     set_last_error("tc_bgemm: unsupported shape M=%d N=%d K=%d", M, N, Kd);
@@ -320,11 +413,19 @@ int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* A
     }
     attr = true;
   }
-  const long long total = (long long)batch * ceil_div(M, tcg::TILE_M) * ceil_div(N, tcg::ACC_COLS);
+  const int mt_n = ceil_div(M, tcg::TILE_M), nt_n = ceil_div(N, tcg::ACC_COLS);
+  const int tpb = lower_only ? tiles_lower(mt_n, nt_n) : mt_n * nt_n;
+  const int nkb = ceil_div(Kd, tcg::KBLK);
+  const int kseg = (kseg_kblocks > 0 && kseg_kblocks < nkb) ? kseg_kblocks : nkb;
+  const long long total = (long long)batch * tpb;
   const int grid = (int)min((long long)tcg::num_sms_cached(), total);
   tcg::tc_bgemm_kernel<<<grid, tcg::THREADS, tcg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, batch, M, N, Kd, alpha, C, ldc,
-                                                                   strideC);
+                                                                   strideC, beta, kseg, lower_only ? 1 : 0, tpb);
   return check_launch("tc_bgemm_kernel");
+}
+int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
+                    const float* Bl, float* C, int ldc, long long strideC, cudaStream_t st) {
+  return launch_tc_bgemm_ex(batch, M, N, Kd, alpha, Ah, Al, Bh, Bl, C, ldc, strideC, 0.f, 0, 0, st);
 }
 
 // C[b] = alpha * opA(A[b]) opB(B[b]) for row-major fp32 inputs, like launch_bgemm; ws holds the split operands:
@@ -332,9 +433,9 @@ int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* A
 size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd) {
   return (size_t)2 * batch * ((size_t)M * Kd + (size_t)N * Kd) + 256;
 }
-int launch_tc_gemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
-                   long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
-                   long long strideC, float* ws, cudaStream_t st) {
+int launch_tc_gemm_ex(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                      long long strideC, float beta, int kseg_kblocks, int lower_only, float* ws, cudaStream_t st) {
   float* Ah = ws;
   float* Al = Ah + (size_t)batch * M * Kd;
   float* Bh = Al + (size_t)batch * M * Kd;
@@ -353,14 +454,21 @@ int launch_tc_gemm(int transA, int transB, int batch, int M, int N, int Kd, floa
     else        rc = launch_split_tf32(B, batch, Kd, N, ldb, strideB, 1, Bh, Bl, st);
     if (rc) return rc;
   }
-  return launch_tc_bgemm(batch, M, N, Kd, alpha, Ah, Al, Bh, Bl, C, ldc, strideC, st);
+  return launch_tc_bgemm_ex(batch, M, N, Kd, alpha, Ah, Al, Bh, Bl, C, ldc, strideC, beta, kseg_kblocks, lower_only,
+                            st);
+}
+int launch_tc_gemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                   long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                   long long strideC, float* ws, cudaStream_t st) {
+  return launch_tc_gemm_ex(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
+                           0.f, 0, 0, ws, st);
 }
 
 int launch_bgemm(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
                  long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                  long long strideC, cudaStream_t st);
 
-static bool tc_gemm_enabled() {
+bool tc_gemm_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GMMVI_B200_TC_GEMM");
@@ -412,6 +520,26 @@ extern "C" int gvi_tc_bgemm_supported(int M, int N, int Kd) { return tc_gemm_sup
 
 extern "C" size_t gvi_tc_bgemm_workspace(int batch, int M, int N, int Kd) {
   return tc_gemm_workspace_floats(batch, M, N, Kd) * sizeof(float);
+}
+
+extern "C" int gvi_tc_bgemm_ex_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha,
+                                   const float* A, int lda, long long strideA, const float* B, int ldb,
+                                   long long strideB, float* C, int ldc, long long strideC, float beta,
+                                   int kseg_kblocks, int lower_only, void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(batch >= 0 && M >= 0 && N >= 0 && Kd >= 0 && kseg_kblocks >= 0, "gvi_tc_bgemm_ex_f32: bad sizes");
+  GVI_REQUIRE(beta == 0.f || beta == 1.f, "gvi_tc_bgemm_ex_f32: beta must be 0 or 1");
+  if (batch == 0 || M == 0 || N == 0) return GVI_OK;
+  GVI_REQUIRE(A && B && C && ws, "gvi_tc_bgemm_ex_f32: null pointer");
+  if (!tc_gemm_supported(M, N, Kd)) {
+    set_last_error("gvi_tc_bgemm_ex_f32: unsupported shape (K must be a positive multiple of 4)");
+    return GVI_ERR_UNSUPPORTED;
+  }
+  if (ws_bytes < gvi_tc_bgemm_workspace(batch, M, N, Kd)) {
+    set_last_error("gvi_tc_bgemm_ex_f32: workspace %zu < %zu", ws_bytes, gvi_tc_bgemm_workspace(batch, M, N, Kd));
+    return GVI_ERR_WORKSPACE;
+  }
+  return launch_tc_gemm_ex(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
+                           beta, kseg_kblocks, lower_only, (float*)ws, (cudaStream_t)stream);
 }
 
 extern "C" int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A,

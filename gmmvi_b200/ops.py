@@ -362,8 +362,9 @@ def stein_diag(X, means, stds, W, G):
     return Hneg, gneg
 
 
-def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=4 << 30):
-    """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32)."""
+def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=32 << 30):
+    """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32).
+    Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.28 GB per component)."""
     X, y, W = _chk(samples, "samples"), _chk(rewards, "rewards"), _chk(weights, "weights")
     means, linv, l2 = _chk(means, "means"), _chk(linv, "linv"), _chk(regularizers, "regularizers")
     N, D = X.shape
@@ -382,6 +383,24 @@ def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget
           l2.data_ptr(), K, chunk, quad.data_ptr(), lin.data_ptr(), ok.data_ptr(), ws.data_ptr(), nbytes, _stream(),
           kernels=((K + chunk - 1) // chunk) * (9 + 4 * panels))
     return quad, lin, ok
+
+
+def bgemm_ex(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, kseg_kblocks=0, lower_only=False):
+    """In place C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b] on the tcgen05 tensor cores (3xTF32) with the reduction
+    cut into round-to-nearest accumulated segments of `kseg_kblocks` x 32 and, with lower_only, only the tiles that
+    touch the lower triangle written (gvi_tc_bgemm_ex_f32; the MORE normal equations and Cholesky trailing updates)."""
+    A, B, C = _chk(A, "A"), _chk(B, "B"), _chk(C, "C")
+    batch = A.shape[0]
+    M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
+    N = B.shape[1] if transB else B.shape[2]
+    if tuple(C.shape) != (batch, M, N):
+        raise ValueError(f"bgemm_ex: C has shape {tuple(C.shape)}, expected {(batch, M, N)}")
+    nbytes = _lib.lib().gvi_tc_bgemm_workspace(batch, M, N, Kd)
+    ws = torch.empty(nbytes // 4 + 4, device=A.device, dtype=torch.float32)
+    _call("gvi_tc_bgemm_ex_f32", int(transA), int(transB), batch, M, N, Kd, float(alpha), A.data_ptr(), A.shape[2],
+          A.shape[1] * A.shape[2], B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], C.data_ptr(), N, M * N,
+          float(beta), int(kseg_kblocks), int(bool(lower_only)), ws.data_ptr(), nbytes, _stream(), kernels=3)
+    return C
 
 
 UPDATE_MODES = {"trust-region": 0, "direct": 1, "iBLR": 2}

@@ -122,7 +122,11 @@ int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const f
  * least_squares.py:34-191): quad[k] = reward_quad (= expected_hessian_neg), lin[k] = reward_lin.
  * W[K,N] importance weights, y[N] = target_lnpdf - log q, l2reg[K]; linv from gvi_prepare_full_f32.
  * Components are processed `chunk` at a time (workspace grows with chunk); ok[k] (caller-initialised to 1) is
- * cleared when the normal matrix of component k is not positive definite. */
+ * cleared when the normal matrix of component k is not positive definite.
+ * gvi_more_tensor_cores() != 0: the normal matrix and the trailing updates of its blocked Cholesky run on the tcgen05
+ * tensor cores (3xTF32, features written pre-split and transposed); GMMVI_B200_MORE_TC=0 selects the SIMT fp32 engine.
+ * The workspace size depends on that switch. */
+int gvi_more_tensor_cores(void);
 size_t gvi_more_workspace(int chunk, int N, int D);
 int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const float* linv, const float* W,
                      const float* y, const float* l2reg, int K, int chunk, float* quad, float* lin, int32_t* ok,
@@ -180,6 +184,15 @@ size_t gvi_tc_bgemm_workspace(int batch, int M, int N, int Kd);
 int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
                      long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                      long long strideC, void* ws, size_t ws_bytes, void* stream);
+/* C[b] = alpha * opA(A[b]) opB(B[b]) + beta * C[b] (beta 0 or 1) with the reduction cut into segments of
+ * `kseg_kblocks` blocks of 32 that are added to C with round-to-nearest adds (the tensor core's accumulator
+ * truncates; 0 = one segment), and with `lower_only` != 0 only the 128 x 256 tiles that touch the lower triangle
+ * written: the normal-equation build Phi^T W Phi and the trailing updates of the blocked Cholesky of the MORE
+ * estimator (least_squares.py:60-75). */
+int gvi_tc_bgemm_ex_f32(int transA, int transB, int batch, int M, int N, int Kd, float alpha, const float* A, int lda,
+                        long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
+                        long long strideC, float beta, int kseg_kblocks, int lower_only, void* ws, size_t ws_bytes,
+                        void* stream);
 
 /* ---- tensor-core mixture gradient (same contraction as gvi_mixture_grad_full_f32) ------------------------------
  * grad[n, :] = -sum_k r_kn P_k (x_n - mu_k) with tcgen05 MMAs in the 2 x fp16 split precision of the log-density kernel.

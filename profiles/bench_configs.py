@@ -1,5 +1,6 @@
 """Iteration times of the BASELINE.json configurations C1-C4 through the reference-facing runner / module API
-(C5 is bench.py).  usage: python profiles/bench_configs.py [iterations]"""
+(C5 is bench.py).  usage: python profiles/bench_configs.py [iterations] [C1,C3,...] [--kernels]
+--kernels adds the per-kernel device time of the timed iterations (torch.profiler, a second pass)."""
 import os
 import sys
 import time
@@ -12,10 +13,16 @@ sys.path.insert(0, ROOT)
 from gmmvi_b200.configs import get_default_algorithm_config, get_default_experiment_config, update_config  # noqa: E402
 from gmmvi_b200.gmmvi_runner import GmmviRunner  # noqa: E402
 
-iters = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+iters = int(args[0]) if len(args) > 0 else 60
+only = set(args[1].split(",")) if len(args) > 1 else None
+kernels = "--kernels" in sys.argv
 
 
-def timed(name, runner, warm=10):
+def timed(name, make_runner, warm=10):
+    if only is not None and name.split()[0] not in only:
+        return
+    runner = make_runner()
     for n in range(warm):
         runner.iterate_and_log(n)
     torch.cuda.synchronize()
@@ -26,6 +33,14 @@ def timed(name, runner, warm=10):
     dt = (time.perf_counter() - t0) / iters
     m = runner.gmmvi.model
     print(f"{name:58s} {dt * 1e3:8.2f} ms/iter  K={m.num_components:4d}  finite={bool(torch.isfinite(m.means).all())}", flush=True)
+    if kernels:
+        n_prof = min(iters, 5)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            for n in range(warm + iters, warm + iters + n_prof):
+                runner.iterate_and_log(n)
+            torch.cuda.synchronize()
+        for e in sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)[:10]:
+            print(f"    {e.self_device_time_total / n_prof / 1e3:9.3f} ms  n={e.count / n_prof:7.1f}  {e.key[:100]}", flush=True)
 
 
 def runner_for(experiment, codeword, overrides):
@@ -37,11 +52,11 @@ def runner_for(experiment, codeword, overrides):
 
 
 # C1: examples/5_samtron_20D_student-T.py (D=20, 45 initial components, 200 samples per component)
-timed("C1 SAMTRON stm20 (ex.5)", runner_for("stm20", "SAMTRON", {
+timed("C1 SAMTRON stm20 (ex.5)", lambda: runner_for("stm20", "SAMTRON", {
     "sample_selector_config": {"desired_samples_per_component": 200, "ratio_reused_samples_to_desired": 0.0},
     "model_initialization": {"num_initial_components": 45}}))
 # C2: examples/6_samtron_planar4.py (D=10, 100 initial components, 100 samples per component)
-timed("C2 SAMTRON planar_robot_4 (ex.6)", runner_for("planar_robot_4", "SAMTRON", {
+timed("C2 SAMTRON planar_robot_4 (ex.6)", lambda: runner_for("planar_robot_4", "SAMTRON", {
     "num_component_adapter_config": {"del_iters": 10, "add_iters": 1},
     "sample_selector_config": {"desired_samples_per_component": 100, "ratio_reused_samples_to_desired": 0.0},
     "model_initialization": {"num_initial_components": 100}}))
@@ -57,7 +72,7 @@ def direct_runner(name, D, K, target, codeword, overrides, diag=False, prior_sca
                                                      "initial_cov": initial_cov},
                             "gmmvi_runner_config": {"log_metrics_interval": 10 ** 9}}, algo)
     config["target_fn"] = target
-    timed(name, GmmviRunner.build_from_config(config))
+    timed(name, lambda: GmmviRunner.build_from_config(config))
 
 
 from gmmvi_b200.experiments.target_distributions.gmm import make_target as make_gmm_target  # noqa: E402

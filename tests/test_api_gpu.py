@@ -224,7 +224,13 @@ def test_more_iteration_matches_oracle():
         assert rel_err(gmmvi.model.chol_cov.cpu().numpy(), og.chol_cov) < 2e-3
 
 
-def test_more_c3_shape():
+@pytest.mark.parametrize("route", ["tensor", "simt"])
+def test_more_c3_shape(route, monkeypatch):
+    monkeypatch.setenv("GMMVI_B200_MORE_TC", "1" if route == "tensor" else "0")
+    _more_c3_shape()
+
+
+def _more_c3_shape():
     """BASELINE config C3 shape (D=100 -> F=5151 features): the blocked Cholesky path over 41 panels.  The normal
     matrix is only well conditioned in fp32 when N is a few times F (SURVEY.md "Hard parts": C3 with N=4096 < F is
     rank deficient in the reference too), hence N = 12000 here."""

@@ -440,10 +440,53 @@ def test_bgemm(ta, tb):
     assert rel_err(out.cpu().numpy(), 0.5 * ref) < 1e-5
 
 
+@pytest.mark.parametrize("b,M,N,Kd,kseg,beta,lower", [
+    (2, 300, 300, 1000, 4, 0.0, True),       # several segments, ragged tiles, lower triangle only
+    (1, 517, 517, 128, 0, 1.0, True),        # trailing update of the blocked Cholesky: C -= T T^T
+    (3, 130, 70, 260, 3, 1.0, False),        # rectangular, last segment shorter, K not a multiple of 32
+    (1, 1030, 1030, 2052, 16, 0.0, True),    # more tiles than one wave of lower tiles per row
+])
+def test_tc_bgemm_segments_beta_lower(b, M, N, Kd, kseg, beta, lower):
+    """gvi_tc_bgemm_ex_f32: round-to-nearest accumulated reduction segments, beta = 1, lower-triangle tile enumeration."""
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(M + Kd)
+    same = M == N
+    A = rng.standard_normal((b, M, Kd)).astype(np.float32)
+    B = A if same else rng.standard_normal((b, N, Kd)).astype(np.float32)
+    C0 = rng.standard_normal((b, M, N)).astype(np.float32)
+    alpha = -1.0 if beta else 0.5
+    ref = alpha * (A.astype(np.float64) @ B.astype(np.float64).transpose(0, 2, 1)) + beta * C0
+    C = dev(C0.copy())
+    ops.bgemm_ex(dev(A), dev(B), C, False, True, alpha, beta, kseg, lower)
+    out = C.cpu().numpy()
+    rows, cols = np.arange(M)[:, None], np.arange(N)[None, :]
+    written = np.ones((M, N), bool) if not lower else (cols // 256) * 256 <= (rows // 128) * 128 + 127
+    assert written[np.tril_indices(M, 0, N)].all()
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref)[:, written].max() < 2e-6 * scale * max(1.0, np.sqrt(Kd / 256))
+    assert np.array_equal(out[:, ~written], C0[:, ~written])        # skipped tiles are not touched
+    # A^T B through the transposing split as well (the form the estimator's normal equations have)
+    if not beta:
+        C2 = dev(C0.copy())
+        At = np.ascontiguousarray(A.transpose(0, 2, 1))
+        ops.bgemm_ex(dev(At), dev(np.ascontiguousarray(B.transpose(0, 2, 1))), C2, True, False, alpha, 0.0, kseg, lower)
+        assert np.array_equal(C2.cpu().numpy()[:, written], out[:, written])
+
+
+@pytest.fixture(params=["tensor", "simt"])
+def more_route(request, monkeypatch):
+    monkeypatch.setenv("GMMVI_B200_MORE_TC", "1" if request.param == "tensor" else "0")
+    from gmmvi_b200 import _lib
+    assert bool(_lib.lib().gvi_more_tensor_cores()) == (request.param == "tensor")
+    return request.param
+
+
 @pytest.mark.parametrize("K,D,N,self_norm", [(3, 4, 300, True), (4, 12, 1500, True), (2, 20, 2000, False),
-                                              (2, 40, 4000, True)])
-def test_more_estimator(K, D, N, self_norm):
-    """MORE against the oracle (ng_estimator.py:296-376): needs N >= F = D(D+1)/2 + D + 1 samples."""
+                                              (2, 40, 4000, True), (3, 30, 2501, True)])
+def test_more_estimator(K, D, N, self_norm, more_route):
+    """MORE against the oracle (ng_estimator.py:296-376): needs N >= F = D(D+1)/2 + D + 1 samples.  Both routes: the
+    normal equations / Cholesky trailing updates on the tensor cores (3xTF32, pre-split transposed features) and in the
+    SIMT fp32 engine; N = 2501 is not a multiple of 4 (zero-padded reduction), D = 30 gives F + 1 = 497 (pitch 500)."""
     from gmmvi_b200 import ops
     g, X = make_problem(K, D, N, seed=80 + D, scale=1.0)
     g32 = gmm32_of(g)
