@@ -73,6 +73,9 @@ _SIGNATURES = {
                                       C.c_longlong, c_f, C.c_int, C.c_longlong, c_f, C.c_int, C.c_longlong, C.c_float,
                                       C.c_int, C.c_int, c_vp, C.c_size_t, c_vp]),
     "gvi_more_tensor_cores": (C.c_int, []),
+    "gvi_tc_bgemm_h16_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gvi_tc_bgemm_h16_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_f, c_f, c_f, C.c_float, C.c_int,
+                                       C.c_int, c_vp, C.c_size_t, c_vp]),
     "gvi_bgemm_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_f, C.c_int,
                                 C.c_longlong, c_f, C.c_int, C.c_longlong, c_f, C.c_int, C.c_longlong, c_vp]),
 }

@@ -13,15 +13,19 @@
 // The reference solves the (symmetric positive definite) system with an LU (tf.linalg.solve); a Cholesky factorisation
 // gives the same solution and reports a non-positive pivot through ok[k] instead of returning garbage.
 //
-// Tensor-core route (default, gvi_more_tensor_cores()): the two O(F^2 N) / O(F^3) products run on tcgen05 in 3xTF32
-// (tc_bgemm.cu).  The feature kernel writes S = sqrt(w) Phi directly as the operand the MMA wants - transposed
-// [F+1][N] (reduction dimension contiguous) and split into TF32 hi / lo - so A' = S^T S needs one operand; the
-// reduction over the samples is cut into 512-sample segments added with round-to-nearest adds; only tiles of the
-// lower triangle are computed.  The trailing update A22 -= T21 T21^T of the blocked Cholesky takes the hi / lo
-// split of the panel from the kernel that copies the panel back.
-#include "common.cuh"
+// Tensor-core route (default, gvi_more_tensor_cores()): the two O(F^2 N) / O(F^3) products run on tcgen05
+// (tc_bgemm.cu) in split precision, 2 x fp16 by default (3xTF32 with GMMVI_B200_MORE_TC=tf32).  The feature kernel
+// writes S = sqrt(w) Phi directly as the operand the MMA wants - transposed [F+1][N] (reduction dimension
+// contiguous) and split into hi / lo parts - so A' = S^T S needs one operand; the reduction over the samples is cut
+// into 512-sample segments added with round-to-nearest adds; only tiles of the lower triangle are computed.  The
+// trailing update A22 -= T21 T21^T of the blocked Cholesky takes the hi / lo split of the panel from the kernel that
+// copies the panel back.  fp16 parts are taken under one power-of-two scale per component: for S from the bound
+// max_n sqrt(w_n) max(|z_n|_inf^2, |z_n|_inf, 1, |y_n|), for the panels from sqrt(max_i A'_ii) >= |T21_ic| (Cholesky rows
+// have norm sqrt(A'_ii); the right-hand-side row is covered because the augmented matrix is a Gram matrix too).
+#include "tc_common.cuh"
 #include "../../include/gmmvi_b200.h"
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 namespace gvi {
 
@@ -32,6 +36,9 @@ int launch_bgemm_ex(int transA, int transB, int batch, int M, int N, int Kd, flo
 int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
                        const float* Bl, float* C, int ldc, long long strideC, float beta, int kseg_kblocks,
                        int lower_only, cudaStream_t st);
+int launch_tc_bgemm_h16_ex(int batch, int M, int N, int Kd, float alpha, const float* alpha_b, const void* Ah,
+                           const void* Al, const void* Bh, const void* Bl, float* C, int ldc, long long strideC,
+                           float beta, int kseg_kblocks, int lower_only, cudaStream_t st);
 bool tc_gemm_enabled();
 
 namespace more {
@@ -96,14 +103,43 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// smax[kc] = max_n sqrt(w_kn) max(|z_n|_inf^2, |z_n|_inf, 1, |y_n|) >= every entry of S (as uint bits; zeroed by the caller)
+__global__ void __launch_bounds__(256)
+feature_bound_kernel(const float* __restrict__ Z, const float* __restrict__ y, const float* __restrict__ W, int N, int D,
+                     int k0, unsigned* __restrict__ smax) {
+  const int kc = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  float b = 0.f;
+  if (n < N) {
+    const float* z = Z + ((long long)kc * N + n) * D;
+    float zm = 0.f;
+    for (int d = lane; d < D; d += 32) zm = fmaxf(zm, fabsf(z[d]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+    b = sqrtf(fmaxf(W[(long long)(k0 + kc) * N + n], 0.f)) * fmaxf(fmaxf(zm * zm, zm), fmaxf(1.f, fabsf(y[n])));
+  }
+  __shared__ float red[8];
+  if (lane == 0) red[warp] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (isfinite(m)) atomicMax(smax + kc, __float_as_uint(m));
+  }
+}
+
+template <bool H16>
 __global__ void __launch_bounds__(256)
 features_split_kernel(const float* __restrict__ Z, const float* __restrict__ y, const float* __restrict__ W, int N,
-                      int Np, int D, int F, int k0, float* __restrict__ Sh, float* __restrict__ Sl) {
+                      int Np, int D, int F, int k0, void* __restrict__ Sh_, void* __restrict__ Sl_,
+                      const unsigned* __restrict__ smax, float* __restrict__ alphaS) {
   extern __shared__ float zs[];      // [32][D + 1]
   __shared__ float sw[32], sy[32];
   const int kc = blockIdx.y;
   const int n0 = blockIdx.x * 32;
   const int Dp = D + 1;
+  const float scale = H16 ? tcx::h16_scale_of(__uint_as_float(smax[kc])) : 1.f;
+  if (H16 && blockIdx.x == 0 && threadIdx.x == 0) alphaS[kc] = 1.f / (scale * scale);
   const float* Zk = Z + (long long)kc * N * D;
   for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {
     const int r = e / D, d = e % D;
@@ -111,7 +147,7 @@ features_split_kernel(const float* __restrict__ Z, const float* __restrict__ y, 
   }
   if (threadIdx.x < 32) {
     const int n = n0 + threadIdx.x;
-    sw[threadIdx.x] = n < N ? sqrtf(fmaxf(W[(long long)(k0 + kc) * N + n], 0.f)) : 0.f;
+    sw[threadIdx.x] = n < N ? scale * sqrtf(fmaxf(W[(long long)(k0 + kc) * N + n], 0.f)) : 0.f;
     sy[threadIdx.x] = n < N ? y[n] : 0.f;
   }
   __syncthreads();
@@ -120,8 +156,7 @@ features_split_kernel(const float* __restrict__ Z, const float* __restrict__ y, 
   const float* zr = zs + lane * Dp;
   const float w = sw[lane];
   const bool live = n0 + lane < Np;
-  float* oh = Sh + (long long)kc * Fa * Np + n0 + lane;
-  float* ol = Sl + (long long)kc * Fa * Np + n0 + lane;
+  const long long o0 = (long long)kc * Fa * Np + n0 + lane;
   // (i, j) of quadratic feature f = warp, advanced by nwarps per step
   int i = 0, j = warp;
   while (i < D && j >= D) { j = j - D + i + 1; ++i; }
@@ -135,24 +170,50 @@ features_split_kernel(const float* __restrict__ Z, const float* __restrict__ y, 
     else if (f == F - 1) v = 1.f;
     else v = sy[lane];
     v *= w;
-    const float h = tf32_rna(v);
     if (live) {
-      oh[(long long)f * Np] = h;
-      ol[(long long)f * Np] = tf32_rna(v - h);
+      if (H16) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(Sh_)[o0 + (long long)f * Np] = h;
+        reinterpret_cast<__half*>(Sl_)[o0 + (long long)f * Np] = __float2half_rn(v - __half2float(h));
+      } else {
+        const float h = tf32_rna(v);
+        reinterpret_cast<float*>(Sh_)[o0 + (long long)f * Np] = h;
+        reinterpret_cast<float*>(Sl_)[o0 + (long long)f * Np] = tf32_rna(v - h);
+      }
     }
   }
 }
 
 // (Fa = row pitch of A, sA = distance between the matrices of two components, here and below)
-__global__ void ridge_kernel(float* __restrict__ A, int Fa, long long sA, int F, const float* __restrict__ l2, int k0) {
+__global__ void ridge_kernel(float* __restrict__ A, int Fa, long long sA, int F, const float* __restrict__ l2, int k0,
+                             unsigned* __restrict__ dmax) {
   const int kc = blockIdx.y;
   float* Ak = A + kc * sA;
   const float lam = l2[k0 + kc];
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F - 1; f += gridDim.x * blockDim.x)
-    Ak[(long long)f * Fa + f] += lam;
+  float m = 0.f;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f <= F; f += gridDim.x * blockDim.x) {
+    float d = Ak[(long long)f * Fa + f];
+    if (f < F - 1) Ak[(long long)f * Fa + f] = d = d + lam;
+    m = fmaxf(m, d);
+  }
+  if (dmax) {       // largest diagonal entry of the augmented matrix (uint bits of a non-negative float)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && isfinite(m)) atomicMax(dmax + kc, __float_as_uint(m));
+  }
+}
+// scale of the fp16 split of the Cholesky panels: every entry of T21 is at most sqrt(max_i A'_ii)
+__global__ void trail_scale_kernel(const unsigned* __restrict__ dmax, int Kc, float* __restrict__ sT,
+                                   float* __restrict__ alphaT) {
+  const int kc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kc < Kc) {
+    const float s = tcx::h16_scale_of(sqrtf(__uint_as_float(dmax[kc])));
+    sT[kc] = s;
+    alphaT[kc] = 1.f / (s * s);
+  }
 }
 
-// Diagonal block [nb x nb] at (p, p): in-place Cholesky (fp64 accumulation) and its inverse into Sinv[kc][NB][NB].
+// Diagonal block [nb x nb] at (p, p): in-place Cholesky and its inverse into Sinv[kc][NB][NB].
 __global__ void __launch_bounds__(256)
 potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, float* __restrict__ Sinv,
                  int32_t* __restrict__ ok, int k0) {
@@ -169,8 +230,9 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
   __syncthreads();
   __shared__ int bad;
   if (tid == 0) bad = 0;
-  // Two threads per row (even / odd columns of the dot product, two accumulators each: the fp64 chain and the
-  // fp32 -> fp64 conversions bound this kernel), combined with a shuffle inside the pair.
+  // Two threads per row (even / odd columns of the dot product), four fp32 accumulators each, combined with a shuffle
+  // inside the pair: dot products of at most 128 terms, as accurate as the fp32-grade trailing updates around them (an
+  // fp64 chain with its fp32 -> fp64 conversions made this kernel 17 % of the C3 iteration).
   const int half = tid & 1, pr = tid >> 1;
   for (int j = 0; j < nb; ++j) {
     __syncthreads();
@@ -178,17 +240,18 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
       const int i = j + pr;                       // blockDim = 256 covers the nb <= 128 rows below the diagonal
       const float* Li = L + min(i, nb - 1) * (NB + 1);
       const float* Lj = L + j * (NB + 1);
-      double s0 = 0.0, s1 = 0.0;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       int m = half;
-      for (; m + 2 < j; m += 4) {
-        s0 += (double)Li[m] * (double)Lj[m];
-        s1 += (double)Li[m + 2] * (double)Lj[m + 2];
+      for (; m + 6 < j; m += 8) {
+        s0 = fmaf(Li[m], Lj[m], s0);
+        s1 = fmaf(Li[m + 2], Lj[m + 2], s1);
+        s2 = fmaf(Li[m + 4], Lj[m + 4], s2);
+        s3 = fmaf(Li[m + 6], Lj[m + 6], s3);
       }
-      if (m < j) s0 += (double)Li[m] * (double)Lj[m];
-      double s = s0 + s1;
+      for (; m < j; m += 2) s0 = fmaf(Li[m], Lj[m], s0);
+      float s = (s0 + s1) + (s2 + s3);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
-      __syncwarp();
-      if (half == 0 && i < nb) L[i * (NB + 1) + j] = (float)((double)Li[j] - s);     // unscaled
+      if (half == 0 && i < nb) L[i * (NB + 1) + j] = Li[j] - s;     // unscaled
     }
     __syncthreads();
     float piv = L[j * (NB + 1) + j];
@@ -196,9 +259,9 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
       if (tid == 0) bad = 1;
       piv = 1.f;
     }
-    const float c = sqrtf(piv);
+    const float c = sqrtf(piv), rc = 1.f / c;
     __syncthreads();
-    for (int i = j + tid; i < nb; i += nt) L[i * (NB + 1) + j] = (i == j) ? c : L[i * (NB + 1) + j] / c;
+    for (int i = j + tid; i < nb; i += nt) L[i * (NB + 1) + j] = (i == j) ? c : L[i * (NB + 1) + j] * rc;
   }
   __syncthreads();
   // inverse: a thread pair per column
@@ -211,16 +274,18 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
     __syncwarp(pm);
     for (int i = c + 1; i < nb; ++i) {
       const float* Li = L + i * (NB + 1);
-      double s0 = 0.0, s1 = 0.0;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       int m = c + half;
-      for (; m + 2 < i; m += 4) {
-        s0 += (double)Li[m] * (double)Y[m * (NB + 1) + c];
-        s1 += (double)Li[m + 2] * (double)Y[(m + 2) * (NB + 1) + c];
+      for (; m + 6 < i; m += 8) {
+        s0 = fmaf(Li[m], Y[m * (NB + 1) + c], s0);
+        s1 = fmaf(Li[m + 2], Y[(m + 2) * (NB + 1) + c], s1);
+        s2 = fmaf(Li[m + 4], Y[(m + 4) * (NB + 1) + c], s2);
+        s3 = fmaf(Li[m + 6], Y[(m + 6) * (NB + 1) + c], s3);
       }
-      if (m < i) s0 += (double)Li[m] * (double)Y[m * (NB + 1) + c];
-      double s = s0 + s1;
+      for (; m < i; m += 2) s0 = fmaf(Li[m], Y[m * (NB + 1) + c], s0);
+      float s = (s0 + s1) + (s2 + s3);
       s += __shfl_xor_sync(pm, s, 1);
-      if (half == 0) Y[i * (NB + 1) + c] = (float)(-s / (double)Li[i]);
+      if (half == 0) Y[i * (NB + 1) + c] = -s / Li[i];
       __syncwarp(pm);
     }
   }
@@ -234,23 +299,57 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
   if (tid == 0 && bad && ok) ok[k0 + kc] = 0;
 }
 
-// A[kc][r0 + r][p + c] = T[kc][r][c]; with Th / Tl also the dense TF32 hi / lo split [kc][rows][nb] of the panel
+// A[kc][r0 + r][p + c] = T[kc][r][c]; with Th / Tl also the dense hi / lo split [kc][rows][nb] of the panel
+// (TF32 floats, or with sT fp16 halves of sT[kc] T)
 __global__ void copy_panel_kernel(const float* __restrict__ T, int ldt, long long strideT, float* __restrict__ A, int Fa,
-                                  long long strideA, int r0, int p, int rows, int nb, float* __restrict__ Th,
-                                  float* __restrict__ Tl) {
+                                  long long strideA, int r0, int p, int rows, int nb, void* __restrict__ Th,
+                                  void* __restrict__ Tl, const float* __restrict__ sT) {
   const int kc = blockIdx.y;
   const float* Tk = T + kc * strideT;
   float* Ak = A + kc * strideA;
   const long long ob = (long long)kc * rows * nb;
+  const float s = sT ? sT[kc] : 1.f;
+  if (nb % 4 == 0 && ldt % 4 == 0 && Fa % 4 == 0 && p % 4 == 0 && strideT % 4 == 0 && strideA % 4 == 0) {
+    // 16 bytes per thread and step, 32-bit index arithmetic (all panels but a ragged last one)
+    const int q4 = nb / 4, total = rows * q4;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const int r = e / q4, c = (e - r * q4) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(Tk + (long long)r * ldt + c);
+      *reinterpret_cast<float4*>(Ak + (long long)(r0 + r) * Fa + p + c) = v;
+      const long long o = ob + (long long)r * nb + c;
+      if (Th && sT) {
+        const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+        __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y), l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Th) + o) = hv;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Tl) + o) = lv;
+      } else if (Th) {
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(Th) + o) = h;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(Tl) + o) = l;
+      }
+    }
+    return;
+  }
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)rows * nb;
        e += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(e / nb), c = (int)(e % nb);
     const float v = Tk[(long long)r * ldt + c];
     Ak[(long long)(r0 + r) * Fa + p + c] = v;
-    if (Th) {
+    if (Th && sT) {
+      const __half h = __float2half_rn(v * s);
+      reinterpret_cast<__half*>(Th)[ob + e] = h;
+      reinterpret_cast<__half*>(Tl)[ob + e] = __float2half_rn(v * s - __half2float(h));
+    } else if (Th) {
       const float h = tf32_rna(v);
-      Th[ob + e] = h;
-      Tl[ob + e] = tf32_rna(v - h);
+      reinterpret_cast<float*>(Th)[ob + e] = h;
+      reinterpret_cast<float*>(Tl)[ob + e] = tf32_rna(v - h);
     }
   }
 }
@@ -290,18 +389,29 @@ backsolve_unpack_kernel(const float* __restrict__ A, int Fa, long long sA, int F
     }
     __syncthreads();
     for (int i = tid; i < nb; i += nt) theta[p + i] = th[i];
-    for (int m = tid; m < p; m += nt) {
+    // rows come from HBM and one CTA per component has to cover the latency with its own requests: 16 bytes per
+    // thread and load, four loads in flight (p is a multiple of BS, the pitch Fa a multiple of 4)
+    for (int m = 4 * tid; m < p; m += 4 * nt) {
       const float* col = Ak + (long long)p * Fa + m;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       int i = 0;
       for (; i + 3 < nb; i += 4) {
-        a0 = fmaf(col[(long long)i * Fa], th[i], a0);
-        a1 = fmaf(col[(long long)(i + 1) * Fa], th[i + 1], a1);
-        a2 = fmaf(col[(long long)(i + 2) * Fa], th[i + 2], a2);
-        a3 = fmaf(col[(long long)(i + 3) * Fa], th[i + 3], a3);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(col + (long long)i * Fa));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(col + (long long)(i + 1) * Fa));
+        const float4 x2 = __ldg(reinterpret_cast<const float4*>(col + (long long)(i + 2) * Fa));
+        const float4 x3 = __ldg(reinterpret_cast<const float4*>(col + (long long)(i + 3) * Fa));
+        const float t0 = th[i], t1 = th[i + 1], t2 = th[i + 2], t3 = th[i + 3];
+        acc.x = fmaf(x0.x, t0, acc.x); acc.y = fmaf(x0.y, t0, acc.y); acc.z = fmaf(x0.z, t0, acc.z); acc.w = fmaf(x0.w, t0, acc.w);
+        acc.x = fmaf(x1.x, t1, acc.x); acc.y = fmaf(x1.y, t1, acc.y); acc.z = fmaf(x1.z, t1, acc.z); acc.w = fmaf(x1.w, t1, acc.w);
+        acc.x = fmaf(x2.x, t2, acc.x); acc.y = fmaf(x2.y, t2, acc.y); acc.z = fmaf(x2.z, t2, acc.z); acc.w = fmaf(x2.w, t2, acc.w);
+        acc.x = fmaf(x3.x, t3, acc.x); acc.y = fmaf(x3.y, t3, acc.y); acc.z = fmaf(x3.z, t3, acc.z); acc.w = fmaf(x3.w, t3, acc.w);
       }
-      for (; i < nb; ++i) a0 = fmaf(col[(long long)i * Fa], th[i], a0);
-      v[m] -= (a0 + a1) + (a2 + a3);
+      for (; i < nb; ++i) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(col + (long long)i * Fa));
+        const float t0 = th[i];
+        acc.x = fmaf(x0.x, t0, acc.x); acc.y = fmaf(x0.y, t0, acc.y); acc.z = fmaf(x0.z, t0, acc.z); acc.w = fmaf(x0.w, t0, acc.w);
+      }
+      v[m] -= acc.x; v[m + 1] -= acc.y; v[m + 2] -= acc.z; v[m + 3] -= acc.w;
     }
   }
   __syncthreads();
@@ -333,49 +443,54 @@ unwhiten_lin_kernel(const float* __restrict__ linv, const float* __restrict__ me
 }
 
 struct Layout {
-  size_t xc, z, phi, sh, sl, a, sinv, t21, t21h, t21l, theta, qz, rz, t1, total;
+  size_t xc, z, phi, sh, sl, a, sinv, t21, t21h, t21l, theta, qz, rz, t1, small, total;
 };
 static inline int pitch_of(int Fa) { return (Fa + 3) & ~3; }      // 16-byte aligned rows of the normal matrix
-static Layout layout(int Kc, int N, int D, bool tc) {
-  const size_t F = (size_t)D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = pitch_of((int)Fa), Np = ((size_t)N + 3) & ~(size_t)3;
+// route: 0 = SIMT fp32, 1 = tensor cores 3xTF32, 2 = tensor cores 2 x fp16
+static Layout layout(int Kc, int N, int D, int route) {
+  const size_t F = (size_t)D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = pitch_of((int)Fa), Np = ((size_t)N + 7) & ~(size_t)7;
+  const size_t opnd = route == 2 ? 2 : 1;        // operand elements per float of workspace
   Layout l;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
   l.xc = take((size_t)Kc * N * D);
   l.z = take((size_t)Kc * N * D);
-  l.phi = take(tc ? 0 : (size_t)Kc * N * Fa);
-  l.sh = take(tc ? (size_t)Kc * Fa * Np : 0);
-  l.sl = take(tc ? (size_t)Kc * Fa * Np : 0);
+  l.phi = take(route ? 0 : (size_t)Kc * N * Fa);
+  l.sh = take(route ? (size_t)Kc * Fa * Np / opnd : 0);
+  l.sl = take(route ? (size_t)Kc * Fa * Np / opnd : 0);
   l.a = take((size_t)Kc * Fa * ld);
   l.sinv = take((size_t)Kc * NB * NB);
   l.t21 = take((size_t)Kc * Fa * NB);
-  l.t21h = take(tc ? (size_t)Kc * Fa * NB : 0);
-  l.t21l = take(tc ? (size_t)Kc * Fa * NB : 0);
+  l.t21h = take(route ? (size_t)Kc * Fa * NB / opnd : 0);
+  l.t21l = take(route ? (size_t)Kc * Fa * NB / opnd : 0);
   l.theta = take((size_t)Kc * F);
   l.qz = take((size_t)Kc * D * D);
   l.rz = take((size_t)Kc * D);
   l.t1 = take((size_t)Kc * D * D);
+  l.small = take((size_t)5 * Kc);               // smax, dmax (uint), alphaS, sT, alphaT
   l.total = o;
   return l;
 }
 
-static bool more_tc() {      // read per call: the tests switch routes inside one process
+static int more_route() {      // read per call: the tests switch routes inside one process
   const char* e = getenv("GMMVI_B200_MORE_TC");
-  return !(e != nullptr && e[0] == '0') && tc_gemm_enabled();
+  if ((e != nullptr && e[0] == '0') || !tc_gemm_enabled()) return 0;
+  if (e != nullptr && e[0] == 't') return 1;
+  return 2;
 }
 
-constexpr int KSEG = 16;      // 16 k-blocks of 32 = 512 samples per accumulator segment of the normal-equation build
+constexpr int SEG_SAMPLES = 512;      // samples per accumulator segment of the normal-equation build
 
 }  // namespace more
 }  // namespace gvi
 
 using namespace gvi;
 
-extern "C" int gvi_more_tensor_cores(void) { return more::more_tc() ? 1 : 0; }
+extern "C" int gvi_more_tensor_cores(void) { return more::more_route(); }
 
 extern "C" size_t gvi_more_workspace(int chunk, int N, int D) {
   if (chunk <= 0 || N <= 0 || D <= 0) return 0;
-  return more::layout(chunk, N, D, more::more_tc()).total * sizeof(float);
+  return more::layout(chunk, N, D, more::more_route()).total * sizeof(float);
 }
 
 extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const float* linv, const float* W,
@@ -389,25 +504,30 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     return GVI_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc = more::more_tc() && (reinterpret_cast<uintptr_t>(ws) % 16 == 0);
-  if (more::more_tc() && !tc) {
+  const int route = more::more_route();
+  if (route && reinterpret_cast<uintptr_t>(ws) % 16 != 0) {
     set_last_error("gvi_more_fit_f32: workspace must be 16-byte aligned for the tensor-core route");
     return GVI_ERR_INVALID;
   }
-  const int F = D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = more::pitch_of(Fa), Np = (N + 3) & ~3;
+  const bool tc = route != 0, h16 = route == 2;
+  const int F = D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = more::pitch_of(Fa), Np = (N + 7) & ~7;
   const long long sA = (long long)Fa * ld;
-  const more::Layout l = more::layout(chunk, N, D, tc);
+  const more::Layout l = more::layout(chunk, N, D, route);
   float* base = (float*)ws;
   float *Xc = base + l.xc, *Z = base + l.z, *Phi = base + l.phi, *Sh = base + l.sh, *Sl = base + l.sl, *A = base + l.a,
         *Sinv = base + l.sinv, *T21 = base + l.t21, *T21h = base + l.t21h, *T21l = base + l.t21l,
         *theta = base + l.theta, *Qz = base + l.qz, *rz = base + l.rz, *T1 = base + l.t1;
+  unsigned* smax = (unsigned*)(base + l.small);
+  unsigned* dmax = smax + chunk;
+  float *alphaS = (float*)(dmax + chunk), *sT = alphaS + chunk, *alphaT = sT + chunk;
   const long long DD = (long long)D * D, ND = (long long)N * D;
   static bool attr_done = false;
   const size_t potrf_smem = (size_t)2 * more::NB * (more::NB + 1) * sizeof(float);
   if (!attr_done) {
     cudaFuncSetAttribute(more::potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
     cudaFuncSetAttribute(more::backsolve_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(more::features_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(more::features_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(more::features_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   if ((size_t)F * sizeof(float) > 200 * 1024) {
@@ -426,10 +546,22 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     if (rc) return rc;
     if (tc) {
       // S = sqrt(w) Phi, transposed and split; A' = S^T S (lower triangle)
+      const size_t fsm = (size_t)32 * (D + 1) * sizeof(float);
       dim3 g2(ceil_div(Np, 32), Kc);
-      more::features_split_kernel<<<g2, 256, (size_t)32 * (D + 1) * sizeof(float), st>>>(Z, y, W, N, Np, D, F, k0, Sh, Sl);
-      if ((rc = check_launch("more::features_split_kernel"))) return rc;
-      rc = launch_tc_bgemm_ex(Kc, Fa, Fa, Np, 1.f, Sh, Sl, Sh, Sl, A, ld, sA, 0.f, more::KSEG, 1, st);
+      if (h16) {
+        cudaMemsetAsync(smax, 0, (size_t)2 * chunk * sizeof(unsigned), st);        // smax and dmax
+        dim3 gb(ceil_div(N, 8), Kc);
+        more::feature_bound_kernel<<<gb, 256, 0, st>>>(Z, y, W, N, D, k0, smax);
+        if ((rc = check_launch("more::feature_bound_kernel"))) return rc;
+        more::features_split_kernel<true><<<g2, 256, fsm, st>>>(Z, y, W, N, Np, D, F, k0, Sh, Sl, smax, alphaS);
+        if ((rc = check_launch("more::features_split_kernel"))) return rc;
+        rc = launch_tc_bgemm_h16_ex(Kc, Fa, Fa, Np, 1.f, alphaS, Sh, Sl, Sh, Sl, A, ld, sA, 0.f, more::SEG_SAMPLES / 64,
+                                    1, st);
+      } else {
+        more::features_split_kernel<false><<<g2, 256, fsm, st>>>(Z, y, W, N, Np, D, F, k0, Sh, Sl, nullptr, nullptr);
+        if ((rc = check_launch("more::features_split_kernel"))) return rc;
+        rc = launch_tc_bgemm_ex(Kc, Fa, Fa, Np, 1.f, Sh, Sl, Sh, Sl, A, ld, sA, 0.f, more::SEG_SAMPLES / 32, 1, st);
+      }
       if (rc) return rc;
     } else {
       dim3 g2(ceil_div(N, 8), Kc);
@@ -440,9 +572,13 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
                            W + (long long)k0 * N, N, 0.f, 1, st);
       if (rc) return rc;
     }
-    dim3 g3(ceil_div(F, 256), Kc);
-    more::ridge_kernel<<<g3, 256, 0, st>>>(A, ld, sA, F, l2reg, k0);
+    dim3 g3(ceil_div(Fa, 256), Kc);
+    more::ridge_kernel<<<g3, 256, 0, st>>>(A, ld, sA, F, l2reg, k0, h16 ? dmax : nullptr);
     if ((rc = check_launch("more::ridge_kernel"))) return rc;
+    if (h16) {
+      more::trail_scale_kernel<<<ceil_div(Kc, 128), 128, 0, st>>>(dmax, Kc, sT, alphaT);
+      if ((rc = check_launch("more::trail_scale_kernel"))) return rc;
+    }
     // blocked Cholesky of A[:F,:F], carried through row F
     for (int p = 0; p < F; p += more::NB) {
       const int nb = min(more::NB, F - p);
@@ -455,14 +591,19 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
                            (long long)more::NB * more::NB, T21, more::NB, (long long)Fa * more::NB, nullptr, 0, 0.f, 0,
                            st);
       if (rc) return rc;
-      // the tensor-core trailing update wants a reduction length that is a multiple of 4 and enough rows to fill a tile
-      const bool tc_trail = tc && nb % 4 == 0 && rows >= 64;
+      // the tensor-core trailing update wants a reduction length that is a multiple of 4 (8 for fp16) and enough
+      // rows to fill a tile
+      const bool tc_trail = tc && nb % 8 == 0 && rows >= 64;
       dim3 g4((unsigned)min((long long)1024, ((long long)rows * nb + 255) / 256), Kc);
       more::copy_panel_kernel<<<g4, 256, 0, st>>>(T21, more::NB, (long long)Fa * more::NB, A, ld, sA, r0, p, rows, nb,
-                                                  tc_trail ? T21h : nullptr, tc_trail ? T21l : nullptr);
+                                                  tc_trail ? T21h : nullptr, tc_trail ? T21l : nullptr,
+                                                  tc_trail && h16 ? sT : nullptr);
       if ((rc = check_launch("more::copy_panel_kernel"))) return rc;
       // A22 -= T21 T21^T (lower triangle)
-      if (tc_trail)
+      if (tc_trail && h16)
+        rc = launch_tc_bgemm_h16_ex(Kc, rows, rows, nb, -1.f, alphaT, T21h, T21l, T21h, T21l,
+                                    A + (long long)r0 * ld + r0, ld, sA, 1.f, 0, 1, st);
+      else if (tc_trail)
         rc = launch_tc_bgemm_ex(Kc, rows, rows, nb, -1.f, T21h, T21l, T21h, T21l, A + (long long)r0 * ld + r0, ld, sA,
                                 1.f, 0, 1, st);
       else

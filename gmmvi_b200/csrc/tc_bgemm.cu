@@ -17,6 +17,7 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <algorithm>
+#include <cuda_fp16.h>
 
 namespace gvi {
 namespace tcg {
@@ -29,7 +30,9 @@ constexpr int THREADS = 256;
 constexpr int A_BYTES = TILE_M * 128;
 constexpr int B_BYTES = 256 * 128;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_PITCH = 33;                                     // floats per staged accumulator row
+constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                 // one 32 x 32 staging tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 
@@ -41,18 +44,37 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+// kind::f16 with fp16 operands, fp32 accumulate, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_h16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// H16 = false: TF32 hi / lo operands (32 floats per 128-byte k-block row, kind::tf32);
+// H16 = true:  fp16 hi / lo operands of matrices pre-scaled by a power of two per batch entry (64 halves per k-block
+//              row, kind::f16 at twice the TF32 rate and half the operand bytes); alpha_b[b] undoes the scales.
+template <bool H16>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, int batch, int M,
-                int N, int Kd, float alpha, float* __restrict__ C, int ldc, long long strideC, float beta, int kseg,
-                int lower_only, int tiles_per_batch) {
+                int N, int Kd, float alpha_all, const float* __restrict__ alpha_b, float* __restrict__ C, int ldc,
+                long long strideC, float beta, int kseg, int lower_only, int tiles_per_batch) {
+  constexpr int KELEMS = H16 ? 64 : 32;          // reduction elements per 128-byte row of a stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt_n = ceil_div(M, TILE_M), nt_n = ceil_div(N, ACC_COLS);
   const long long total = (long long)batch * tiles_per_batch;
-  const int nkb = ceil_div(Kd, KBLK);
+  const int nkb = ceil_div(Kd, KELEMS);
   const int nseg = ceil_div(nkb, kseg);
 
   if (threadIdx.x == 0) {
@@ -104,11 +126,11 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
           mbar_wait(&bars->empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&bars->full[s], 2u * A_BYTES + 2u * nrows_b * 128u);
-          tma_load_3d(st, &mapAh, &bars->full[s], kb * KBLK, m0, b);
-          tma_load_3d(st + A_BYTES, &mapAl, &bars->full[s], kb * KBLK, m0, b);
+          tma_load_3d(st, &mapAh, &bars->full[s], kb * KELEMS, m0, b);
+          tma_load_3d(st + A_BYTES, &mapAl, &bars->full[s], kb * KELEMS, m0, b);
           for (int r = 0; r < nrows_b; r += 32) {
-            tma_load_3d(st + 2 * A_BYTES + r * 128, &mapBh, &bars->full[s], kb * KBLK, n0 + r, b);
-            tma_load_3d(st + 2 * A_BYTES + B_BYTES + r * 128, &mapBl, &bars->full[s], kb * KBLK, n0 + r, b);
+            tma_load_3d(st + 2 * A_BYTES + r * 128, &mapBh, &bars->full[s], kb * KELEMS, n0 + r, b);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES + r * 128, &mapBl, &bars->full[s], kb * KELEMS, n0 + r, b);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -122,7 +144,7 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
       for (long long w = blockIdx.x; w < total; w += gridDim.x) {
         int b, m0, n0, nt;
         decode(w, b, m0, n0, nt);
-        const uint32_t idesc = make_idesc(nt);
+        const uint32_t idesc = H16 ? make_idesc_h16(nt) : make_idesc(nt);
         for (int seg = 0; seg < nseg; ++seg, ++it) {
           const int buf = (int)(it & 1);
           const uint32_t use = (uint32_t)(it >> 1);
@@ -141,9 +163,15 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
               const uint64_t a_lo = make_desc(st + A_BYTES + ks * 32);
               const uint64_t b_hi = make_desc(st + 2 * A_BYTES + ks * 32);
               const uint64_t b_lo = make_desc(st + 2 * A_BYTES + B_BYTES + ks * 32);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
-              umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
-              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              if (H16) {
+                umma_h16(d_tmem, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
+                umma_h16(d_tmem, a_lo, b_hi, idesc, 1u);
+                umma_h16(d_tmem, a_hi, b_lo, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, a_hi, b_hi, idesc, (first && ks == 0) ? 0u : 1u);
+                umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+                umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              }
             }
             umma_commit(&bars->empty[s]);
             if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -161,11 +189,62 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
       decode(w, b, m0, n0, nt);
       const int m = m0 + 32 * q + lane;
       float* crow = C + b * strideC + (long long)m * ldc + n0;
+      const float alpha = alpha_b ? alpha_all * __ldg(alpha_b + b) : alpha_all;
       for (int seg = 0; seg < nseg; ++seg, ++it) {
         const int buf = (int)(it & 1);
         const uint32_t use = (uint32_t)(it >> 1);
         const bool add = seg > 0 || beta != 0.f;       // C (+)= alpha * acc
-        if (!add) {
+        if (vec && n0 + nt <= N && (nt & 31) == 0) {
+          // Coalesced path (all columns of the tile in bounds, 16-byte aligned rows): a tcgen05.ld gives a lane one
+          // ROW of 32 accumulator columns, so stores straight from those registers touch 32 cache lines per
+          // instruction (this, not the MMAs, bounded the short trailing updates of the MORE Cholesky).  The chunk goes
+          // through a 32 x 33 staging tile in shared memory instead and leaves as 4 rows x 128 contiguous bytes per
+          // instruction; the old values of C for the read-modify-write arrive the same way, one chunk ahead.
+          float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + q * 32 * EPI_PITCH;
+          const int rr = lane >> 3, c4 = (lane & 7) * 4;
+          float* cbase = C + b * strideC + (long long)(m0 + 32 * q + rr) * ldc + n0 + c4;
+          const float bscale = seg > 0 ? 1.f : beta;
+          float4 old[2][8];
+          auto fetch = [&](int c, float4 (&o)[8]) {
+            if (add && c * 32 < nt) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (m0 + 32 * q + 4 * t + rr < M)
+                  o[t] = *reinterpret_cast<const float4*>(cbase + (long long)(4 * t) * ldc + c * 32);
+            }
+          };
+          fetch(0, old[0]);
+          mbar_wait(&bars->acc_full[buf], use & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < ACC_COLS / 32; ++c) {
+            if (c * 32 < nt) {
+              fetch(c + 1, old[(c + 1) & 1]);
+              uint32_t v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * ACC_COLS + c * 32), v);
+              tmem_ld_wait();
+              __syncwarp();                           // the previous chunk has been read out of the staging tile
+#pragma unroll
+              for (int i = 0; i < 32; ++i) stg[lane * EPI_PITCH + i] = __uint_as_float(v[i]);
+              __syncwarp();
+              const float4(&o)[8] = old[c & 1];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float* sp = stg + (4 * t + rr) * EPI_PITCH + c4;
+                float4 r = make_float4(alpha * sp[0], alpha * sp[1], alpha * sp[2], alpha * sp[3]);
+                if (m0 + 32 * q + 4 * t + rr < M) {
+                  if (add) {
+                    r.x = fmaf(bscale, o[t].x, r.x);
+                    r.y = fmaf(bscale, o[t].y, r.y);
+                    r.z = fmaf(bscale, o[t].z, r.z);
+                    r.w = fmaf(bscale, o[t].w, r.w);
+                  }
+                  *reinterpret_cast<float4*>(cbase + (long long)(4 * t) * ldc + c * 32) = r;
+                }
+              }
+            }
+          }
+        } else if (!add) {
           mbar_wait(&bars->acc_full[buf], use & 1);
           tc_fence_after();
           for (int c = 0; c * 32 < nt; ++c) {
@@ -344,6 +423,37 @@ __global__ void split_tf32_symlower_kernel(const float* __restrict__ in, int D, 
   }
 }
 
+// ---- fp16 hi / lo split of dense batches under one power-of-two scale per batch entry (stand-alone entry point) ----
+__global__ void absmax_batch_kernel(const float* __restrict__ in, long long per_batch, unsigned* __restrict__ out) {
+  const float* src = in + (long long)blockIdx.y * per_batch;
+  float m = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_batch;
+       e += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(src[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out + blockIdx.y, __float_as_uint(m));      // non-negative floats order as ints
+}
+__global__ void split_h16_batch_kernel(const float* __restrict__ in, long long per_batch,
+                                       const unsigned* __restrict__ mx, __half* __restrict__ hi,
+                                       __half* __restrict__ lo) {
+  const long long ob = (long long)blockIdx.y * per_batch;
+  const float s = h16_scale_of(__uint_as_float(mx[blockIdx.y]));
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_batch;
+       e += (long long)gridDim.x * blockDim.x) {
+    const float v = in[ob + e] * s;
+    const __half h = __float2half_rn(v);
+    hi[ob + e] = h;
+    lo[ob + e] = __float2half_rn(v - __half2float(h));
+  }
+}
+__global__ void alpha_from_max_kernel(const unsigned* __restrict__ ma, const unsigned* __restrict__ mb, int batch,
+                                      float* __restrict__ alpha_b) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch)
+    alpha_b[b] = 1.f / (h16_scale_of(__uint_as_float(ma[b])) * h16_scale_of(__uint_as_float(mb[b])));
+}
+
 static int num_sms_cached() {
   static int n = 0;
   if (n == 0) {
@@ -389,24 +499,33 @@ static int tiles_lower(int mt_n, int nt_n) {
   for (int mt = 0; mt < mt_n; ++mt) t += std::min(nt_n, (mt * tcg::TILE_M + tcg::TILE_M - 1) / tcg::ACC_COLS + 1);
   return t;
 }
-int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
-                       const float* Bl, float* C, int ldc, long long strideC, float beta, int kseg_kblocks,
-                       int lower_only, cudaStream_t st) {
+static int launch_tc_bgemm_any(bool h16, int batch, int M, int N, int Kd, float alpha, const float* alpha_b,
+                               const void* Ah, const void* Al, const void* Bh, const void* Bl, float* C, int ldc,
+                               long long strideC, float beta, int kseg_kblocks, int lower_only, cudaStream_t st) {
   if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
-  if (!tc_gemm_supported(M, N, Kd)) {
+  if (!tc_gemm_supported(M, N, Kd) || (h16 && Kd % 8 != 0)) {
     set_last_error("tc_bgemm: unsupported shape M=%d N=%d K=%d", M, N, Kd);
     return GVI_ERR_UNSUPPORTED;
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if ((rc = tcx::make_map_3d(&mAh, Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-  if ((rc = tcx::make_map_3d(&mAl, Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-  if ((rc = tcx::make_map_3d(&mBh, Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
-  if ((rc = tcx::make_map_3d(&mBl, Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+  if (h16) {
+    if ((rc = tcx::make_map_3d_h16(&mAh, Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mAl, Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mBh, Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mBl, Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+  } else {
+    if ((rc = tcx::make_map_3d(&mAh, (const float*)Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+    if ((rc = tcx::make_map_3d(&mAl, (const float*)Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
+    if ((rc = tcx::make_map_3d(&mBh, (const float*)Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+    if ((rc = tcx::make_map_3d(&mBl, (const float*)Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+  }
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tcg::tc_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tcg::tc_bgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tcg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tcg::tc_bgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("tc_bgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GVI_ERR_CUDA;
@@ -415,13 +534,31 @@ int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float
   }
   const int mt_n = ceil_div(M, tcg::TILE_M), nt_n = ceil_div(N, tcg::ACC_COLS);
   const int tpb = lower_only ? tiles_lower(mt_n, nt_n) : mt_n * nt_n;
-  const int nkb = ceil_div(Kd, tcg::KBLK);
+  const int nkb = ceil_div(Kd, h16 ? 64 : 32);
   const int kseg = (kseg_kblocks > 0 && kseg_kblocks < nkb) ? kseg_kblocks : nkb;
   const long long total = (long long)batch * tpb;
   const int grid = (int)min((long long)tcg::num_sms_cached(), total);
-  tcg::tc_bgemm_kernel<<<grid, tcg::THREADS, tcg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, batch, M, N, Kd, alpha, C, ldc,
-                                                                   strideC, beta, kseg, lower_only ? 1 : 0, tpb);
+  if (h16)
+    tcg::tc_bgemm_kernel<true><<<grid, tcg::THREADS, tcg::SMEM_BYTES, st>>>(
+        mAh, mAl, mBh, mBl, batch, M, N, Kd, alpha, alpha_b, C, ldc, strideC, beta, kseg, lower_only ? 1 : 0, tpb);
+  else
+    tcg::tc_bgemm_kernel<false><<<grid, tcg::THREADS, tcg::SMEM_BYTES, st>>>(
+        mAh, mAl, mBh, mBl, batch, M, N, Kd, alpha, alpha_b, C, ldc, strideC, beta, kseg, lower_only ? 1 : 0, tpb);
   return check_launch("tc_bgemm_kernel");
+}
+int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
+                       const float* Bl, float* C, int ldc, long long strideC, float beta, int kseg_kblocks,
+                       int lower_only, cudaStream_t st) {
+  return launch_tc_bgemm_any(false, batch, M, N, Kd, alpha, nullptr, Ah, Al, Bh, Bl, C, ldc, strideC, beta,
+                             kseg_kblocks, lower_only, st);
+}
+// fp16 hi / lo operands ([b][M][Kd] / [b][N][Kd] halves, Kd % 8 == 0) of matrices scaled by powers of two;
+// C[b] = alpha * alpha_b[b] * A[b] B[b]^T + beta * C[b]; kseg_kblocks counts blocks of 64.
+int launch_tc_bgemm_h16_ex(int batch, int M, int N, int Kd, float alpha, const float* alpha_b, const void* Ah,
+                           const void* Al, const void* Bh, const void* Bl, float* C, int ldc, long long strideC,
+                           float beta, int kseg_kblocks, int lower_only, cudaStream_t st) {
+  return launch_tc_bgemm_any(true, batch, M, N, Kd, alpha, alpha_b, Ah, Al, Bh, Bl, C, ldc, strideC, beta,
+                             kseg_kblocks, lower_only, st);
 }
 int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
                     const float* Bl, float* C, int ldc, long long strideC, cudaStream_t st) {
@@ -558,4 +695,49 @@ extern "C" int gvi_tc_bgemm_f32(int transA, int transB, int batch, int M, int N,
   }
   return launch_tc_gemm(transA, transB, batch, M, N, Kd, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
                         (float*)ws, (cudaStream_t)stream);
+}
+
+// Stand-alone 2 x fp16 split product (used by the tests; the MORE estimator writes its operands pre-split):
+// C[b] = alpha * A[b] B[b]^T + beta * C[b] for dense A [b][M][Kd], B [b][N][Kd], C [b][M][N], Kd % 8 == 0.
+extern "C" size_t gvi_tc_bgemm_h16_workspace(int batch, int M, int N, int Kd) {
+  if (batch <= 0 || M <= 0 || N <= 0 || Kd <= 0) return 0;
+  const size_t halves = (size_t)2 * batch * ((size_t)M + N) * Kd;
+  return ((halves * 2 + 255) / 256) * 256 + (size_t)3 * batch * sizeof(float) + 256;
+}
+extern "C" int gvi_tc_bgemm_h16_f32(int batch, int M, int N, int Kd, float alpha, const float* A, const float* B,
+                                    float* C, float beta, int kseg_kblocks, int lower_only, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  GVI_REQUIRE(batch >= 0 && M >= 0 && N >= 0 && Kd >= 0 && kseg_kblocks >= 0, "gvi_tc_bgemm_h16_f32: bad sizes");
+  GVI_REQUIRE(beta == 0.f || beta == 1.f, "gvi_tc_bgemm_h16_f32: beta must be 0 or 1");
+  if (batch == 0 || M == 0 || N == 0) return GVI_OK;
+  GVI_REQUIRE(A && B && C && ws, "gvi_tc_bgemm_h16_f32: null pointer");
+  if (Kd % 8 != 0) {
+    set_last_error("gvi_tc_bgemm_h16_f32: K must be a multiple of 8");
+    return GVI_ERR_UNSUPPORTED;
+  }
+  if (ws_bytes < gvi_tc_bgemm_h16_workspace(batch, M, N, Kd) || reinterpret_cast<uintptr_t>(ws) % 16 != 0) {
+    set_last_error("gvi_tc_bgemm_h16_f32: workspace too small or not 16-byte aligned");
+    return GVI_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t na = (size_t)batch * M * Kd, nb = (size_t)batch * N * Kd;
+  __half* Ah = (__half*)ws;
+  __half* Al = Ah + na;
+  __half* Bh = Al + na;
+  __half* Bl = Bh + nb;
+  unsigned* mx = (unsigned*)((char*)ws + ((2 * (na + nb) * 2 + 255) / 256) * 256);
+  float* alpha_b = (float*)(mx + 2 * batch);
+  const bool same = A == B && M == N;
+  cudaMemsetAsync(mx, 0, (size_t)2 * batch * sizeof(unsigned), st);
+  const long long pa = (long long)M * Kd, pb = (long long)N * Kd;
+  dim3 ga((unsigned)std::min<long long>(256, (pa + 255) / 256), batch), gb((unsigned)std::min<long long>(256, (pb + 255) / 256), batch);
+  tcg::absmax_batch_kernel<<<ga, 256, 0, st>>>(A, pa, mx);
+  tcg::absmax_batch_kernel<<<gb, 256, 0, st>>>(B, pb, mx + batch);
+  tcg::split_h16_batch_kernel<<<ga, 256, 0, st>>>(A, pa, mx, Ah, Al);
+  if (!same) tcg::split_h16_batch_kernel<<<gb, 256, 0, st>>>(B, pb, mx + batch, Bh, Bl);
+  tcg::alpha_from_max_kernel<<<ceil_div(batch, 128), 128, 0, st>>>(mx, mx + batch, batch, alpha_b);
+  int rc = check_launch("gvi_tc_bgemm_h16_f32: split kernels");
+  if (rc) return rc;
+  return launch_tc_bgemm_h16_ex(batch, M, N, Kd, alpha, alpha_b, Ah, Al, same ? Ah : Bh, same ? Al : Bl, C, N,
+                                (long long)M * N, beta, kseg_kblocks, lower_only, st);
 }

@@ -88,6 +88,17 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// Power of two s with mx * s in [2^13, 2^14): the scale under which a matrix with largest magnitude mx is split into
+// fp16 hi / lo parts (fp16 overflows at 65504; an element down to 2^-17 of mx keeps 22 significant bits, smaller
+// ones an absolute error of 2^-39 mx).  The exponent is clamped so that s^2 stays a normal fp32 number.
+__device__ __forceinline__ float h16_scale_of(float mx) {
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  int e;
+  frexpf(mx, &e);                       // mx = f 2^e, f in [0.5, 1)
+  e = max(-46, min(74, e));
+  return __int_as_float((127 + 14 - e) << 23);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row x 128-byte atoms,
 // stride between atoms (SBO) 1024 B, LBO unused.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -137,6 +148,28 @@ inline int make_map_3d(CUtensorMap* map, const float* base, int cols, int rows, 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return GVI_ERR_CUDA;
+  }
+  return GVI_OK;
+}
+
+// The same for fp16 operands: box = [1][box_rows][64 halves = 128 bytes]
+inline int make_map_3d_h16(CUtensorMap* map, const void* base, int cols, int rows, int batch, long long row_pitch_elems,
+                           long long batch_pitch_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+    return GVI_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)row_pitch_elems * 2, (cuuint64_t)batch_pitch_elems * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
     return GVI_ERR_CUDA;
   }
   return GVI_OK;

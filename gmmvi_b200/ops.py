@@ -381,8 +381,23 @@ def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget
     panels = (F + 127) // 128
     _call("gvi_more_fit_f32", X.data_ptr(), N, D, means.data_ptr(), linv.data_ptr(), W.data_ptr(), y.data_ptr(),
           l2.data_ptr(), K, chunk, quad.data_ptr(), lin.data_ptr(), ok.data_ptr(), ws.data_ptr(), nbytes, _stream(),
-          kernels=((K + chunk - 1) // chunk) * (9 + 4 * panels))
+          kernels=((K + chunk - 1) // chunk) * (9 + 4 * panels + (2 if _lib.lib().gvi_more_tensor_cores() == 2 else 0)))
     return quad, lin, ok
+
+
+def bgemm_h16(A, B, C, alpha=1.0, beta=0.0, kseg_kblocks=0, lower_only=False):
+    """In place C[b] = alpha * A[b] B[b]^T + beta * C[b] in the 2 x fp16 split precision (gvi_tc_bgemm_h16_f32): A [b, M, K],
+    B [b, N, K] with K % 8 == 0, one power-of-two scale per batch entry and operand; kseg_kblocks counts blocks of 64."""
+    A, B, C = _chk(A, "A"), _chk(B, "B"), _chk(C, "C")
+    batch, M, Kd = A.shape
+    N = B.shape[1]
+    if tuple(C.shape) != (batch, M, N) or B.shape[2] != Kd:
+        raise ValueError(f"bgemm_h16: shapes {tuple(A.shape)} {tuple(B.shape)} {tuple(C.shape)} do not match")
+    nbytes = _lib.lib().gvi_tc_bgemm_h16_workspace(batch, M, N, Kd)
+    ws = torch.empty(nbytes // 4 + 4, device=A.device, dtype=torch.float32)
+    _call("gvi_tc_bgemm_h16_f32", batch, M, N, Kd, float(alpha), A.data_ptr(), B.data_ptr(), C.data_ptr(), float(beta),
+          int(kseg_kblocks), int(bool(lower_only)), ws.data_ptr(), nbytes, _stream(), kernels=6)
+    return C
 
 
 def bgemm_ex(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, kseg_kblocks=0, lower_only=False):

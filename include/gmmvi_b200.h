@@ -124,8 +124,9 @@ int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const f
  * Components are processed `chunk` at a time (workspace grows with chunk); ok[k] (caller-initialised to 1) is
  * cleared when the normal matrix of component k is not positive definite.
  * gvi_more_tensor_cores() != 0: the normal matrix and the trailing updates of its blocked Cholesky run on the tcgen05
- * tensor cores (3xTF32, features written pre-split and transposed); GMMVI_B200_MORE_TC=0 selects the SIMT fp32 engine.
- * The workspace size depends on that switch. */
+ * tensor cores, features written pre-split and transposed: 2 = 2 x fp16 split (default), 1 = 3xTF32
+ * (GMMVI_B200_MORE_TC=tf32); GMMVI_B200_MORE_TC=0 selects the SIMT fp32 engine.  The workspace size depends on that
+ * switch. */
 int gvi_more_tensor_cores(void);
 size_t gvi_more_workspace(int chunk, int N, int D);
 int gvi_more_fit_f32(const float* X, int N, int D, const float* means, const float* linv, const float* W,
@@ -193,6 +194,14 @@ int gvi_tc_bgemm_ex_f32(int transA, int transB, int batch, int M, int N, int Kd,
                         long long strideA, const float* B, int ldb, long long strideB, float* C, int ldc,
                         long long strideC, float beta, int kseg_kblocks, int lower_only, void* ws, size_t ws_bytes,
                         void* stream);
+
+/* The same product in the "2 x fp16" split precision of the log-density kernel (kind::f16 at twice the TF32 rate, half
+ * the operand bytes): each operand batch entry is scaled by a power of two derived from its largest magnitude and split
+ * into fp16 hi / lo parts.  Dense A [b][M][Kd], B [b][N][Kd] (C = A B^T), C [b][M][N]; Kd % 8 == 0; kseg_kblocks counts
+ * blocks of 64.  The MORE estimator uses this kernel with operands it writes pre-split. */
+size_t gvi_tc_bgemm_h16_workspace(int batch, int M, int N, int Kd);
+int gvi_tc_bgemm_h16_f32(int batch, int M, int N, int Kd, float alpha, const float* A, const float* B, float* C,
+                         float beta, int kseg_kblocks, int lower_only, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- tensor-core mixture gradient (same contraction as gvi_mixture_grad_full_f32) ------------------------------
  * grad[n, :] = -sum_k r_kn P_k (x_n - mu_k) with tcgen05 MMAs in the 2 x fp16 split precision of the log-density kernel.

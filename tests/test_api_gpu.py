@@ -224,9 +224,9 @@ def test_more_iteration_matches_oracle():
         assert rel_err(gmmvi.model.chol_cov.cpu().numpy(), og.chol_cov) < 2e-3
 
 
-@pytest.mark.parametrize("route", ["tensor", "simt"])
+@pytest.mark.parametrize("route", ["h16", "tf32", "simt"])
 def test_more_c3_shape(route, monkeypatch):
-    monkeypatch.setenv("GMMVI_B200_MORE_TC", "1" if route == "tensor" else "0")
+    monkeypatch.setenv("GMMVI_B200_MORE_TC", {"h16": "1", "tf32": "tf32", "simt": "0"}[route])
     _more_c3_shape()
 
 

@@ -473,11 +473,43 @@ def test_tc_bgemm_segments_beta_lower(b, M, N, Kd, kseg, beta, lower):
         assert np.array_equal(C2.cpu().numpy()[:, written], out[:, written])
 
 
-@pytest.fixture(params=["tensor", "simt"])
+@pytest.mark.parametrize("b,M,N,Kd,kseg,beta,lower", [
+    (2, 300, 300, 1000, 4, 0.0, True),
+    (1, 517, 517, 128, 0, 1.0, True),
+    (3, 130, 70, 264, 3, 1.0, False),
+    (1, 1030, 1030, 2056, 8, 0.0, True),
+])
+def test_tc_bgemm_h16_split(b, M, N, Kd, kseg, beta, lower):
+    """gvi_tc_bgemm_h16_f32: the batched product in the 2 x fp16 split precision; rows of very different magnitude
+    (a factor 2^-12 .. 1 per row) check that the per-matrix power-of-two scale keeps fp32-grade accuracy."""
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(M + Kd + 1)
+    same = M == N
+    rowscale = 2.0 ** rng.integers(-12, 1, size=(b, M, 1))
+    A = (rng.standard_normal((b, M, Kd)) * rowscale).astype(np.float32)
+    B = A if same else rng.standard_normal((b, N, Kd)).astype(np.float32)
+    C0 = rng.standard_normal((b, M, N)).astype(np.float32)
+    alpha = -1.0 if beta else 0.5
+    prod = A.astype(np.float64) @ B.astype(np.float64).transpose(0, 2, 1)
+    ref = alpha * prod + beta * C0
+    # error scale of an fp32-grade product: |a|.|b| per entry
+    mag = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).transpose(0, 2, 1) + beta * np.abs(C0)
+    C = dev(C0.copy())
+    Ad = dev(A)
+    ops.bgemm_h16(Ad, Ad if same else dev(B), C, alpha, beta, kseg, lower)
+    out = C.cpu().numpy()
+    rows, cols = np.arange(M)[:, None], np.arange(N)[None, :]
+    written = np.ones((M, N), bool) if not lower else (cols // 256) * 256 <= (rows // 128) * 128 + 127
+    err = np.abs(out - ref) / (mag + 1e-30)
+    assert err[:, written].max() < 8e-6, err[:, written].max()       # incl. the truncating accumulator (<= 96 adds per segment)
+    assert np.array_equal(out[:, ~written], C0[:, ~written])
+
+
+@pytest.fixture(params=["h16", "tf32", "simt"])
 def more_route(request, monkeypatch):
-    monkeypatch.setenv("GMMVI_B200_MORE_TC", "1" if request.param == "tensor" else "0")
+    monkeypatch.setenv("GMMVI_B200_MORE_TC", {"h16": "1", "tf32": "tf32", "simt": "0"}[request.param])
     from gmmvi_b200 import _lib
-    assert bool(_lib.lib().gvi_more_tensor_cores()) == (request.param == "tensor")
+    assert _lib.lib().gvi_more_tensor_cores() == {"h16": 2, "tf32": 1, "simt": 0}[request.param]
     return request.param
 
 
