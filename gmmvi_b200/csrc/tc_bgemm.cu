@@ -184,9 +184,26 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     const int q = warp - 4;
     long long it = 0;
     const bool vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && (strideC % 4 == 0);
+    // beta = 1: the old C tile of the NEXT work item is pulled into L2 while this one is processed (one bulk prefetch
+    // per row and lane); the trailing updates of the MORE Cholesky stream C from HBM with few MMAs per tile, and the
+    // one-chunk-ahead register prefetch of the read-modify-write alone covers only ~1/3 of the HBM latency.
+    auto prefetch_c = [&](long long wq) {
+      if (beta != 0.f && vec && wq < total) {
+        int b2, m2, n2, nt2;
+        decode(wq, b2, m2, n2, nt2);
+        const int row = m2 + 32 * q + lane;
+        const int ncols = min(nt2, N - n2) & ~3;
+        if (row < M && ncols > 0) {
+          const float* src = C + b2 * strideC + (long long)row * ldc + n2;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(ncols * 4) : "memory");
+        }
+      }
+    };
+    prefetch_c(blockIdx.x);
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
       int b, m0, n0, nt;
       decode(w, b, m0, n0, nt);
+      prefetch_c(w + gridDim.x);
       const int m = m0 + 32 * q + lane;
       float* crow = C + b * strideC + (long long)m * ldc + n0;
       const float alpha = alpha_b ? alpha_all * __ldg(alpha_b + b) : alpha_all;
