@@ -39,6 +39,10 @@ int launch_tc_bgemm_ex(int batch, int M, int N, int Kd, float alpha, const float
 int launch_tc_bgemm_h16_ex(int batch, int M, int N, int Kd, float alpha, const float* alpha_b, const void* Ah,
                            const void* Al, const void* Bh, const void* Bl, float* C, int ldc, long long strideC,
                            float beta, int kseg_kblocks, int lower_only, cudaStream_t st);
+int launch_tc_bgemm_h16_strided(int batch, int M, int N, int Kd, float alpha, const float* alpha_b, const void* Ah,
+                                const void* Al, long long opStrideA, const void* Bh, const void* Bl,
+                                long long opStrideB, float* C, int ldc, long long strideC, float beta,
+                                int kseg_kblocks, int lower_only, cudaStream_t st);
 bool tc_gemm_enabled();
 
 namespace more {
@@ -300,10 +304,12 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
 }
 
 // A[kc][r0 + r][p + c] = T[kc][r][c]; with Th / Tl also the dense hi / lo split [kc][rows][nb] of the panel
-// (TF32 floats, or with sT fp16 halves of sT[kc] T)
+// (TF32 floats, or with sT fp16 halves of sT[kc] T); with Ch / Cl (fp16 route, full-width panels) the rows from cat_row0
+// on also go to columns cat_col0 .. cat_col0 + nb of the two-panel operand [kc][cat_rows][2 NB] of the paired update
 __global__ void copy_panel_kernel(const float* __restrict__ T, int ldt, long long strideT, float* __restrict__ A, int Fa,
                                   long long strideA, int r0, int p, int rows, int nb, void* __restrict__ Th,
-                                  void* __restrict__ Tl, const float* __restrict__ sT) {
+                                  void* __restrict__ Tl, const float* __restrict__ sT, __half* __restrict__ Ch,
+                                  __half* __restrict__ Cl, int cat_row0, int cat_col0, int cat_rows) {
   const int kc = blockIdx.y;
   const float* Tk = T + kc * strideT;
   float* Ak = A + kc * strideA;
@@ -317,7 +323,7 @@ __global__ void copy_panel_kernel(const float* __restrict__ T, int ldt, long lon
       const float4 v = *reinterpret_cast<const float4*>(Tk + (long long)r * ldt + c);
       *reinterpret_cast<float4*>(Ak + (long long)(r0 + r) * Fa + p + c) = v;
       const long long o = ob + (long long)r * nb + c;
-      if (Th && sT) {
+      if (sT && (Th || Ch)) {
         const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
         __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -325,8 +331,15 @@ __global__ void copy_panel_kernel(const float* __restrict__ T, int ldt, long lon
         uint2 hv, lv;
         hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
         lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Th) + o) = hv;
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Tl) + o) = lv;
+        if (Th) {
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Th) + o) = hv;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(Tl) + o) = lv;
+        }
+        if (Ch && r >= cat_row0) {
+          const long long oc = ((long long)kc * cat_rows + (r - cat_row0)) * (2 * NB) + cat_col0 + c;
+          *reinterpret_cast<uint2*>(Ch + oc) = hv;
+          *reinterpret_cast<uint2*>(Cl + oc) = lv;
+        }
       } else if (Th) {
         float4 h, l;
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -443,7 +456,7 @@ unwhiten_lin_kernel(const float* __restrict__ linv, const float* __restrict__ me
 }
 
 struct Layout {
-  size_t xc, z, phi, sh, sl, a, sinv, t21, t21h, t21l, theta, qz, rz, t1, small, total;
+  size_t xc, z, phi, sh, sl, a, sinv, t21, t21h, t21l, tcath, tcatl, theta, qz, rz, t1, small, total;
 };
 static inline int pitch_of(int Fa) { return (Fa + 3) & ~3; }      // 16-byte aligned rows of the normal matrix
 // route: 0 = SIMT fp32, 1 = tensor cores 3xTF32, 2 = tensor cores 2 x fp16
@@ -463,6 +476,8 @@ static Layout layout(int Kc, int N, int D, int route) {
   l.t21 = take((size_t)Kc * Fa * NB);
   l.t21h = take(route ? (size_t)Kc * Fa * NB / opnd : 0);
   l.t21l = take(route ? (size_t)Kc * Fa * NB / opnd : 0);
+  l.tcath = take(route == 2 ? (size_t)Kc * Fa * NB : 0);      // [Kc][rows][2 NB] halves: two panels side by side
+  l.tcatl = take(route == 2 ? (size_t)Kc * Fa * NB : 0);
   l.theta = take((size_t)Kc * F);
   l.qz = take((size_t)Kc * D * D);
   l.rz = take((size_t)Kc * D);
@@ -472,6 +487,10 @@ static Layout layout(int Kc, int N, int D, int route) {
   return l;
 }
 
+static bool more_pairs() {      // trailing updates applied two panels at a time (fp16 route)
+  const char* e = getenv("GMMVI_B200_MORE_PAIRS");
+  return !(e != nullptr && e[0] == '0');
+}
 static int more_route() {      // read per call: the tests switch routes inside one process
   const char* e = getenv("GMMVI_B200_MORE_TC");
   if ((e != nullptr && e[0] == '0') || !tc_gemm_enabled()) return 0;
@@ -510,6 +529,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     return GVI_ERR_INVALID;
   }
   const bool tc = route != 0, h16 = route == 2;
+  constexpr int NBc = more::NB;
   const int F = D * (D + 1) / 2 + D + 1, Fa = F + 1, ld = more::pitch_of(Fa), Np = (N + 7) & ~7;
   const long long sA = (long long)Fa * ld;
   const more::Layout l = more::layout(chunk, N, D, route);
@@ -517,6 +537,8 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
   float *Xc = base + l.xc, *Z = base + l.z, *Phi = base + l.phi, *Sh = base + l.sh, *Sl = base + l.sl, *A = base + l.a,
         *Sinv = base + l.sinv, *T21 = base + l.t21, *T21h = base + l.t21h, *T21l = base + l.t21l,
         *theta = base + l.theta, *Qz = base + l.qz, *rz = base + l.rz, *T1 = base + l.t1;
+  __half *Tch = (__half*)(base + l.tcath), *Tcl = (__half*)(base + l.tcatl);
+  const bool pairs = h16 && more::more_pairs();
   unsigned* smax = (unsigned*)(base + l.small);
   unsigned* dmax = smax + chunk;
   float *alphaS = (float*)(dmax + chunk), *sT = alphaS + chunk, *alphaT = sT + chunk;
@@ -582,6 +604,39 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     // blocked Cholesky of A[:F,:F], carried through row F
     for (int p = 0; p < F; p += more::NB) {
       const int nb = min(more::NB, F - p);
+      if (pairs && F - p >= 2 * NBc && Fa - (p + 2 * NBc) >= 64) {
+        // Two full panels at a time: the trailing matrix is read and written once per PAIR (its read-modify-write from
+        // HBM bounds the update, not the MMAs).  Panel p is factored and applied only to the columns of panel p + NB;
+        // panel p + NB is factored; both are applied to the rest as one product with a reduction length of 2 NB.
+        const int p1 = p + NBc, rW = p + 2 * NBc, rows0 = Fa - p1, rowsW = Fa - rW;
+        dim3 gp((unsigned)min((long long)1024, ((long long)rows0 * (NBc / 4) + 255) / 256), Kc);
+        more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, NBc, Sinv, ok, k0);
+        if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
+        rc = launch_bgemm_ex(0, 1, Kc, rows0, NBc, NBc, 1.f, A + (long long)p1 * ld + p, ld, sA, Sinv, NBc,
+                             (long long)NBc * NBc, T21, NBc, (long long)Fa * NBc, nullptr, 0, 0.f, 0, st);
+        if (rc) return rc;
+        more::copy_panel_kernel<<<gp, 256, 0, st>>>(T21, NBc, (long long)Fa * NBc, A, ld, sA, p1, p, rows0, NBc, T21h, T21l,
+                                                    sT, Tch, Tcl, NBc, 0, rowsW);
+        if ((rc = check_launch("more::copy_panel_kernel"))) return rc;
+        // A[p1:, p1 : p1 + NB] -= T0 T0[0:NB]^T
+        rc = launch_tc_bgemm_h16_strided(Kc, rows0, NBc, NBc, -1.f, alphaT, T21h, T21l, (long long)rows0 * NBc, T21h, T21l,
+                                         (long long)rows0 * NBc, A + (long long)p1 * ld + p1, ld, sA, 1.f, 0, 0, st);
+        if (rc) return rc;
+        more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p1, NBc, Sinv, ok, k0);
+        if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
+        rc = launch_bgemm_ex(0, 1, Kc, rowsW, NBc, NBc, 1.f, A + (long long)rW * ld + p1, ld, sA, Sinv, NBc,
+                             (long long)NBc * NBc, T21, NBc, (long long)Fa * NBc, nullptr, 0, 0.f, 0, st);
+        if (rc) return rc;
+        more::copy_panel_kernel<<<gp, 256, 0, st>>>(T21, NBc, (long long)Fa * NBc, A, ld, sA, rW, p1, rowsW, NBc, nullptr,
+                                                    nullptr, sT, Tch, Tcl, 0, NBc, rowsW);
+        if ((rc = check_launch("more::copy_panel_kernel"))) return rc;
+        // A[rW:, rW:] -= [T0 T1] [T0 T1]^T (lower triangle)
+        rc = launch_tc_bgemm_h16_ex(Kc, rowsW, rowsW, 2 * NBc, -1.f, alphaT, Tch, Tcl, Tch, Tcl,
+                                    A + (long long)rW * ld + rW, ld, sA, 1.f, 0, 1, st);
+        if (rc) return rc;
+        p += NBc;         // two panels done
+        continue;
+      }
       more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, nb, Sinv, ok, k0);
       if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
       const int r0 = p + nb, rows = Fa - r0;
@@ -597,7 +652,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
       dim3 g4((unsigned)min((long long)1024, ((long long)rows * nb + 255) / 256), Kc);
       more::copy_panel_kernel<<<g4, 256, 0, st>>>(T21, more::NB, (long long)Fa * more::NB, A, ld, sA, r0, p, rows, nb,
                                                   tc_trail ? T21h : nullptr, tc_trail ? T21l : nullptr,
-                                                  tc_trail && h16 ? sT : nullptr);
+                                                  tc_trail && h16 ? sT : nullptr, nullptr, nullptr, 0, 0, 0);
       if ((rc = check_launch("more::copy_panel_kernel"))) return rc;
       // A22 -= T21 T21^T (lower triangle)
       if (tc_trail && h16)

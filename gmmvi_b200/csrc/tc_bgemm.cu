@@ -518,7 +518,9 @@ static int tiles_lower(int mt_n, int nt_n) {
 }
 static int launch_tc_bgemm_any(bool h16, int batch, int M, int N, int Kd, float alpha, const float* alpha_b,
                                const void* Ah, const void* Al, const void* Bh, const void* Bl, float* C, int ldc,
-                               long long strideC, float beta, int kseg_kblocks, int lower_only, cudaStream_t st) {
+                               long long strideC, float beta, int kseg_kblocks, int lower_only, cudaStream_t st,
+                               long long opStrideA = 0, long long opStrideB = 0) {
+  const long long sOa = opStrideA ? opStrideA : (long long)M * Kd, sOb = opStrideB ? opStrideB : (long long)N * Kd;
   if (batch <= 0 || M <= 0 || N <= 0) return GVI_OK;
   if (!tc_gemm_supported(M, N, Kd) || (h16 && Kd % 8 != 0)) {
     set_last_error("tc_bgemm: unsupported shape M=%d N=%d K=%d", M, N, Kd);
@@ -527,15 +529,15 @@ static int launch_tc_bgemm_any(bool h16, int batch, int M, int N, int Kd, float 
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if (h16) {
-    if ((rc = tcx::make_map_3d_h16(&mAh, Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-    if ((rc = tcx::make_map_3d_h16(&mAl, Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-    if ((rc = tcx::make_map_3d_h16(&mBh, Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
-    if ((rc = tcx::make_map_3d_h16(&mBl, Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mAh, Ah, Kd, M, batch, Kd, sOa, 128))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mAl, Al, Kd, M, batch, Kd, sOa, 128))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mBh, Bh, Kd, N, batch, Kd, sOb, 32))) return rc;
+    if ((rc = tcx::make_map_3d_h16(&mBl, Bl, Kd, N, batch, Kd, sOb, 32))) return rc;
   } else {
-    if ((rc = tcx::make_map_3d(&mAh, (const float*)Ah, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-    if ((rc = tcx::make_map_3d(&mAl, (const float*)Al, Kd, M, batch, Kd, (long long)M * Kd, 128))) return rc;
-    if ((rc = tcx::make_map_3d(&mBh, (const float*)Bh, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
-    if ((rc = tcx::make_map_3d(&mBl, (const float*)Bl, Kd, N, batch, Kd, (long long)N * Kd, 32))) return rc;
+    if ((rc = tcx::make_map_3d(&mAh, (const float*)Ah, Kd, M, batch, Kd, sOa, 128))) return rc;
+    if ((rc = tcx::make_map_3d(&mAl, (const float*)Al, Kd, M, batch, Kd, sOa, 128))) return rc;
+    if ((rc = tcx::make_map_3d(&mBh, (const float*)Bh, Kd, N, batch, Kd, sOb, 32))) return rc;
+    if ((rc = tcx::make_map_3d(&mBl, (const float*)Bl, Kd, N, batch, Kd, sOb, 32))) return rc;
   }
   static bool attr = false;
   if (!attr) {
@@ -576,6 +578,15 @@ int launch_tc_bgemm_h16_ex(int batch, int M, int N, int Kd, float alpha, const f
                            float beta, int kseg_kblocks, int lower_only, cudaStream_t st) {
   return launch_tc_bgemm_any(true, batch, M, N, Kd, alpha, alpha_b, Ah, Al, Bh, Bl, C, ldc, strideC, beta,
                              kseg_kblocks, lower_only, st);
+}
+// the same with explicit distances (in halves) between the operand matrices of two batch entries: the B operand may
+// be the leading rows of a taller matrix
+int launch_tc_bgemm_h16_strided(int batch, int M, int N, int Kd, float alpha, const float* alpha_b, const void* Ah,
+                                const void* Al, long long opStrideA, const void* Bh, const void* Bl,
+                                long long opStrideB, float* C, int ldc, long long strideC, float beta,
+                                int kseg_kblocks, int lower_only, cudaStream_t st) {
+  return launch_tc_bgemm_any(true, batch, M, N, Kd, alpha, alpha_b, Ah, Al, Bh, Bl, C, ldc, strideC, beta,
+                             kseg_kblocks, lower_only, st, opStrideA, opStrideB);
 }
 int launch_tc_bgemm(int batch, int M, int N, int Kd, float alpha, const float* Ah, const float* Al, const float* Bh,
                     const float* Bl, float* C, int ldc, long long strideC, cudaStream_t st) {

@@ -505,11 +505,12 @@ def test_tc_bgemm_h16_split(b, M, N, Kd, kseg, beta, lower):
     assert np.array_equal(out[:, ~written], C0[:, ~written])
 
 
-@pytest.fixture(params=["h16", "tf32", "simt"])
+@pytest.fixture(params=["h16", "h16-single-panels", "tf32", "simt"])
 def more_route(request, monkeypatch):
-    monkeypatch.setenv("GMMVI_B200_MORE_TC", {"h16": "1", "tf32": "tf32", "simt": "0"}[request.param])
+    monkeypatch.setenv("GMMVI_B200_MORE_TC", {"h16": "1", "h16-single-panels": "1", "tf32": "tf32", "simt": "0"}[request.param])
+    monkeypatch.setenv("GMMVI_B200_MORE_PAIRS", "0" if request.param == "h16-single-panels" else "1")
     from gmmvi_b200 import _lib
-    assert _lib.lib().gvi_more_tensor_cores() == {"h16": 2, "tf32": 1, "simt": 0}[request.param]
+    assert _lib.lib().gvi_more_tensor_cores() == {"h16": 2, "h16-single-panels": 2, "tf32": 1, "simt": 0}[request.param]
     return request.param
 
 
