@@ -34,13 +34,26 @@ for r in rows[2:]:
         if name.startswith("smsp__pcsamp_warps_issue_stalled") and not name.endswith("not_issued") and r[i] not in ("", "0"):
             print(f"{name:85s} {r[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-h, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
-iS, iI, isrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
-stall_cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
-print("# total samples", sum(int(r[iS]) for r in data), "warp instructions", sum(int(r[iI]) for r in data))
-for i in sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:top_n]:
-    r = data[i]
-    st = sorted(((h[c][6:], int(r[c])) for c in stall_cols if int(r[c]) > 0), key=lambda kv: -kv[1])[:3]
-    print(f"{i:5d} {int(r[iS]):7d} {int(r[iI]):10d}  {r[isrc].strip()[:64]:64s} {st}")
+# the source page repeats its header per captured launch (twice per launch: SASS and the high-level view)
+blocks, cur = [], None
+for r in csv.reader(io.StringIO(src)):
+    if r and r[0] == "Address":
+        cur = {"h": r, "d": []}
+        blocks.append(cur)
+    elif cur is not None and len(r) == len(cur["h"]):
+        cur["d"].append(r)
+seen = set()
+for bi, blk in enumerate(blocks):
+    h, data = blk["h"], blk["d"]
+    iS, iI, isrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
+    tot = sum(int(r[iS]) for r in data)
+    key = (len(data), tot)
+    if key in seen or tot < 1000:          # duplicate view of the same launch, or a launch too short to sample
+        continue
+    seen.add(key)
+    stall_cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
+    print(f"# source block {bi}: total samples", tot, "warp instructions", sum(int(r[iI]) for r in data))
+    for i in sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:top_n]:
+        r = data[i]
+        st = sorted(((h[c][6:], int(r[c])) for c in stall_cols if int(r[c] or 0) > 0), key=lambda kv: -kv[1])[:3]
+        print(f"{i:5d} {int(r[iS]):7d} {int(r[iI]):10d}  {r[isrc].strip()[:64]:64s} {st}")
