@@ -303,6 +303,135 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
   if (tid == 0 && bad && ok) ok[k0 + kc] = 0;
 }
 
+// The same factorisation and inverse, blocked by 32 (opt-in with GMMVI_B200_MORE_POTRF=blocked until it has been timed
+// against the column-by-column kernel above, which spends 3 block barriers per column and runs at ~10 cycles per
+// instruction).  Per 32-column block: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, the column
+// being eliminated is passed round by shuffles) and inverts it (lane = column of the inverse); all warps solve the
+// panel below against that inverse (lane = column, its row of the inverse in registers) and apply the rank-32 update to
+// the trailing lower triangle (warp = row, lane = column).  The off-diagonal blocks of the inverse follow from
+// Y_ij = -Y_ii sum_k L_ik Y_kj, block diagonal by block diagonal, the intermediate product parked in the unused upper
+// triangle of L.  Blocks beyond nb are padded with the identity.
+__global__ void __launch_bounds__(256)
+potrf_inv_blocked_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, float* __restrict__ Sinv,
+                         int32_t* __restrict__ ok, int k0) {
+  extern __shared__ float sm[];          // L[NB][NB+1], Y[NB][NB+1]
+  constexpr int P = NB + 1;
+  float* L = sm;
+  float* Y = sm + NB * P;
+  const int kc = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* Ak = A + kc * sA + (long long)p * Fa + p;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    float v = 0.f;
+    if (i < nb && j <= i) v = Ak[(long long)i * Fa + j];
+    else if (i >= nb && i == j) v = 1.f;
+    L[i * P + j] = v;
+    Y[i * P + j] = 0.f;
+  }
+  __syncthreads();
+  for (int jb = 0; jb < NB / 32; ++jb) {
+    const int j0 = 32 * jb;
+    if (warp == 0) {
+      // a[c] = entry (lane, k + c) of the block while column k is eliminated: the array is shifted down by one after
+      // every column, so all register indices are static and the loop over k stays rolled
+      float a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = L[(j0 + lane) * P + j0 + c];
+      int mybad = 0;
+      for (int k = 0; k < 32; ++k) {
+        float akk = __shfl_sync(0xffffffffu, a[0], k);
+        if (!(akk > 0.f) || !isfinite(akk)) {
+          mybad = 1;
+          akk = 1.f;
+        }
+        const float d = sqrtf(akk);
+        const float lk = lane == k ? d : a[0] * (1.f / d);          // L[lane][k] (zero above the diagonal)
+        L[(j0 + lane) * P + j0 + k] = lane >= k ? lk : 0.f;
+#pragma unroll
+        for (int c = 1; c < 32; ++c) {
+          const float lck = __shfl_sync(0xffffffffu, lk, (k + c) & 31);        // L[k + c][k]
+          if (k + c < 32 && lane >= k + c) a[c] = fmaf(-lk, lck, a[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 31; ++c) a[c] = a[c + 1];
+        a[31] = 0.f;
+      }
+      if (mybad) bad = 1;
+      __syncwarp();
+      // inverse of the diagonal block, lane = column: forward substitution on the unit vector, right-hand side shifted
+      // the same way (b[r] = entry i + r while row i is solved)
+      float b[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) b[r] = r == lane ? 1.f : 0.f;
+      for (int i = 0; i < 32; ++i) {
+        const float yi = b[0] / L[(j0 + i) * P + j0 + i];
+        Y[(j0 + i) * P + j0 + lane] = yi;
+#pragma unroll
+        for (int r = 1; r < 32; ++r)
+          if (i + r < 32) b[r] = fmaf(-L[(j0 + i + r) * P + j0 + i], yi, b[r]);
+#pragma unroll
+        for (int r = 0; r < 31; ++r) b[r] = b[r + 1];
+        b[31] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (j0 + 32 < NB) {
+      // panel: X[i][c] = sum_m A[i][j0 + m] Yjj[c][m], in place
+      float yr[32];
+#pragma unroll
+      for (int m = 0; m < 32; ++m) yr[m] = Y[(j0 + lane) * P + j0 + m];
+      for (int i = j0 + 32 + warp; i < NB; i += 8) {
+        float x = 0.f;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) x = fmaf(L[i * P + j0 + m], yr[m], x);
+        __syncwarp();
+        L[i * P + j0 + lane] = x;
+      }
+      __syncthreads();
+      // trailing lower triangle: A[i][c] -= sum_m X[i][m] X[c][m]
+      for (int i = j0 + 32 + warp; i < NB; i += 8) {
+        float xi[32];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) xi[m] = L[i * P + j0 + m];
+        for (int c = j0 + 32 + lane; c <= i; c += 32) {
+          float s = 0.f;
+#pragma unroll
+          for (int m = 0; m < 32; ++m) s = fmaf(xi[m], L[c * P + j0 + m], s);
+          L[i * P + c] -= s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int d = 1; d < NB / 32; ++d) {
+    const int ntask = 32 * (NB / 32 - d);
+    for (int t = warp; t < ntask; t += 8) {          // T = sum_k L_ik Y_kj, parked at block (jb, ib) of L
+      const int jb = t >> 5, r = t & 31, ib = jb + d;
+      float s = 0.f;
+      for (int k = 32 * jb; k < 32 * ib; ++k) s = fmaf(L[(32 * ib + r) * P + k], Y[k * P + 32 * jb + lane], s);
+      L[(32 * jb + r) * P + 32 * ib + lane] = s;
+    }
+    __syncthreads();
+    for (int t = warp; t < ntask; t += 8) {          // Y_ij = -Y_ii T
+      const int jb = t >> 5, r = t & 31, ib = jb + d;
+      float s = 0.f;
+      for (int m = 0; m <= r; ++m)
+        s = fmaf(Y[(32 * ib + r) * P + 32 * ib + m], L[(32 * jb + m) * P + 32 * ib + lane], s);
+      Y[(32 * ib + r) * P + 32 * jb + lane] = -s;
+    }
+    __syncthreads();
+  }
+  float* So = Sinv + (long long)kc * NB * NB;
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    Ak[(long long)i * Fa + j] = j <= i ? L[i * P + j] : 0.f;
+    So[i * NB + j] = Y[i * P + j];
+  }
+  if (tid == 0 && bad && ok) ok[k0 + kc] = 0;
+}
+
 // A[kc][r0 + r][p + c] = T[kc][r][c]; with Th / Tl also the dense hi / lo split [kc][rows][nb] of the panel
 // (TF32 floats, or with sT fp16 halves of sT[kc] T); with Ch / Cl (fp16 route, full-width panels) the rows from cat_row0
 // on also go to columns cat_col0 .. cat_col0 + nb of the two-panel operand [kc][cat_rows][2 NB] of the paired update
@@ -491,6 +620,10 @@ static bool more_pairs() {      // trailing updates applied two panels at a time
   const char* e = getenv("GMMVI_B200_MORE_PAIRS");
   return !(e != nullptr && e[0] == '0');
 }
+static bool more_potrf_blocked() {
+  const char* e = getenv("GMMVI_B200_MORE_POTRF");
+  return e != nullptr && e[0] == 'b';
+}
 static int more_route() {      // read per call: the tests switch routes inside one process
   const char* e = getenv("GMMVI_B200_MORE_TC");
   if ((e != nullptr && e[0] == '0') || !tc_gemm_enabled()) return 0;
@@ -547,6 +680,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
   const size_t potrf_smem = (size_t)2 * more::NB * (more::NB + 1) * sizeof(float);
   if (!attr_done) {
     cudaFuncSetAttribute(more::potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
+    cudaFuncSetAttribute(more::potrf_inv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
     cudaFuncSetAttribute(more::backsolve_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(more::features_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(more::features_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -557,6 +691,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
     return GVI_ERR_UNSUPPORTED;
   }
   int rc;
+  auto potrf = more::more_potrf_blocked() ? more::potrf_inv_blocked_kernel : more::potrf_inv_kernel;
   for (int k0 = 0; k0 < K; k0 += chunk) {
     const int Kc = min(chunk, K - k0);
     dim3 g1((unsigned)min((long long)2048, (ND + 255) / 256), Kc);
@@ -610,7 +745,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
         // panel p + NB is factored; both are applied to the rest as one product with a reduction length of 2 NB.
         const int p1 = p + NBc, rW = p + 2 * NBc, rows0 = Fa - p1, rowsW = Fa - rW;
         dim3 gp((unsigned)min((long long)1024, ((long long)rows0 * (NBc / 4) + 255) / 256), Kc);
-        more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, NBc, Sinv, ok, k0);
+        potrf<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, NBc, Sinv, ok, k0);
         if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
         rc = launch_bgemm_ex(0, 1, Kc, rows0, NBc, NBc, 1.f, A + (long long)p1 * ld + p, ld, sA, Sinv, NBc,
                              (long long)NBc * NBc, T21, NBc, (long long)Fa * NBc, nullptr, 0, 0.f, 0, st);
@@ -622,7 +757,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
         rc = launch_tc_bgemm_h16_strided(Kc, rows0, NBc, NBc, -1.f, alphaT, T21h, T21l, (long long)rows0 * NBc, T21h, T21l,
                                          (long long)rows0 * NBc, A + (long long)p1 * ld + p1, ld, sA, 1.f, 0, 0, st);
         if (rc) return rc;
-        more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p1, NBc, Sinv, ok, k0);
+        potrf<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p1, NBc, Sinv, ok, k0);
         if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
         rc = launch_bgemm_ex(0, 1, Kc, rowsW, NBc, NBc, 1.f, A + (long long)rW * ld + p1, ld, sA, Sinv, NBc,
                              (long long)NBc * NBc, T21, NBc, (long long)Fa * NBc, nullptr, 0, 0.f, 0, st);
@@ -637,7 +772,7 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
         p += NBc;         // two panels done
         continue;
       }
-      more::potrf_inv_kernel<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, nb, Sinv, ok, k0);
+      potrf<<<Kc, 256, potrf_smem, st>>>(A, ld, sA, p, nb, Sinv, ok, k0);
       if ((rc = check_launch("more::potrf_inv_kernel"))) return rc;
       const int r0 = p + nb, rows = Fa - r0;
       if (rows <= 0) continue;
