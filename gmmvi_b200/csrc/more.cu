@@ -303,9 +303,9 @@ potrf_inv_kernel(float* __restrict__ A, int Fa, long long sA, int p, int nb, flo
   if (tid == 0 && bad && ok) ok[k0 + kc] = 0;
 }
 
-// The same factorisation and inverse, blocked by 32 (opt-in with GMMVI_B200_MORE_POTRF=blocked until it has been timed
-// against the column-by-column kernel above, which spends 3 block barriers per column and runs at ~10 cycles per
-// instruction).  Per 32-column block: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, the column
+// The same factorisation and inverse, blocked by 32: the default (0.26 -> 0.13 ms per launch at C3; the column-by-column
+// kernel above spends 3 block barriers per column and runs at ~10 cycles per instruction; it stays selectable with
+// GMMVI_B200_MORE_POTRF=columns and as cross-check in the tests).  Per 32-column block: warp 0 factors the 32 x 32 diagonal block in registers (lane = row, the column
 // being eliminated is passed round by shuffles) and inverts it (lane = column of the inverse); all warps solve the
 // panel below against that inverse (lane = column, its row of the inverse in registers) and apply the rank-32 update to
 // the trailing lower triangle (warp = row, lane = column).  The off-diagonal blocks of the inverse follow from
@@ -620,9 +620,9 @@ static bool more_pairs() {      // trailing updates applied two panels at a time
   const char* e = getenv("GMMVI_B200_MORE_PAIRS");
   return !(e != nullptr && e[0] == '0');
 }
-static bool more_potrf_blocked() {
+static bool more_potrf_blocked() {      // default; GMMVI_B200_MORE_POTRF=columns selects the column-by-column kernel
   const char* e = getenv("GMMVI_B200_MORE_POTRF");
-  return e != nullptr && e[0] == 'b';
+  return !(e != nullptr && e[0] == 'c');
 }
 static int more_route() {      // read per call: the tests switch routes inside one process
   const char* e = getenv("GMMVI_B200_MORE_TC");

@@ -509,6 +509,8 @@ def test_tc_bgemm_h16_split(b, M, N, Kd, kseg, beta, lower):
 def more_route(request, monkeypatch):
     monkeypatch.setenv("GMMVI_B200_MORE_TC", {"h16": "1", "h16-single-panels": "1", "tf32": "tf32", "simt": "0"}[request.param])
     monkeypatch.setenv("GMMVI_B200_MORE_PAIRS", "0" if request.param == "h16-single-panels" else "1")
+    # the column-by-column diagonal-block kernel rides along with the single-panel route, the blocked one with the rest
+    monkeypatch.setenv("GMMVI_B200_MORE_POTRF", "columns" if request.param == "h16-single-panels" else "blocked")
     from gmmvi_b200 import _lib
     assert _lib.lib().gvi_more_tensor_cores() == {"h16": 2, "h16-single-panels": 2, "tf32": 1, "simt": 0}[request.param]
     return request.param
