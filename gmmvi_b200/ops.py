@@ -388,7 +388,10 @@ def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget
 def bgemm_h16(A, B, C, alpha=1.0, beta=0.0, kseg_kblocks=0, lower_only=False):
     """In place C[b] = alpha * A[b] B[b]^T + beta * C[b] in the 2 x fp16 split precision (gvi_tc_bgemm_h16_f32): A [b, M, K],
     B [b, N, K] with K % 8 == 0, one power-of-two scale per batch entry and operand; kseg_kblocks counts blocks of 64."""
-    A, B, C = _chk(A, "A"), _chk(B, "B"), _chk(C, "C")
+    A, B = _chk(A, "A"), _chk(B, "B")
+    if not C.is_contiguous():
+        raise ValueError("bgemm_h16: C is updated in place and must be contiguous")
+    C = _chk(C, "C")
     batch, M, Kd = A.shape
     N = B.shape[1]
     if tuple(C.shape) != (batch, M, N) or B.shape[2] != Kd:
@@ -404,7 +407,10 @@ def bgemm_ex(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, kseg_kblo
     """In place C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b] on the tcgen05 tensor cores (3xTF32) with the reduction
     cut into round-to-nearest accumulated segments of `kseg_kblocks` x 32 and, with lower_only, only the tiles that
     touch the lower triangle written (gvi_tc_bgemm_ex_f32; the MORE normal equations and Cholesky trailing updates)."""
-    A, B, C = _chk(A, "A"), _chk(B, "B"), _chk(C, "C")
+    A, B = _chk(A, "A"), _chk(B, "B")
+    if not C.is_contiguous():
+        raise ValueError("bgemm_ex: C is updated in place and must be contiguous")
+    C = _chk(C, "C")
     batch = A.shape[0]
     M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
     N = B.shape[1] if transB else B.shape[2]
