@@ -1,0 +1,134 @@
+"""Golden vectors produced by the REFERENCE'S OWN PYTHON SOURCES (/root/reference/src/gmmvi), executed unmodified in
+this container against tests/golden/tf_shim (a torch-CPU stand-in for the TensorFlow ops the hot path uses: TensorFlow
+itself is not installable here).  Writes tests/golden/reference_<case>.npz; tests/test_oracle_pins.py
+checks the oracle (oracle/gmmvi_oracle.py) against them, the GPU tests check the device path against the oracle.
+
+What this pins: the reference's control flow, formulas and quirks (module order, double normalisation of the importance
+weights, bracketing searches and their stop rules, l2 / eta bookkeeping, first-occurrence unique, ...), evaluated in
+float64 so that rounding does not blur the comparison.  What it cannot pin: TensorFlow's own kernels (replaced by torch
+ops of the same documented semantics) and its random generators (noise is injected from a seeded NumPy generator).
+
+Usage (needs /root/reference; not run on the GPU box):  python tests/golden/make_reference_golden.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "tf_shim"))
+sys.path.insert(0, "/root/reference/src")
+if ROOT not in sys.path:
+    sys.path.append(ROOT)
+np.bool = bool          # least_squares.py:111 uses np.bool, removed from NumPy >= 1.24
+
+import tensorflow as tf  # noqa: E402  (the shim)
+
+tf.set_float_dtype(torch.float64)
+
+from gmmvi.experiments.target_distributions.lnpdf import LNPDF  # noqa: E402
+from gmmvi.models.diagonal_gmm import DiagonalGMM  # noqa: E402
+from gmmvi.models.full_cov_gmm import FullCovGMM  # noqa: E402
+from gmmvi.models.gmm_wrapper import GmmWrapper  # noqa: E402
+from gmmvi.optimization.gmmvi import GMMVI  # noqa: E402
+
+
+
+class GmmTarget(LNPDF):
+    """A Gaussian-mixture target written against the reference's LNPDF interface with the reference's own FullCovGMM
+    (what experiments/target_distributions/gmm.py does with tfp distributions)."""
+
+    def __init__(self, weights, means, covs):
+        super().__init__(use_log_density_and_grad=False, safe_for_tf_graph=True)
+        self.gmm = FullCovGMM(tf.constant(weights), tf.constant(means), tf.constant(covs))
+
+    def get_num_dimensions(self):
+        return int(self.gmm.num_dimensions)
+
+    def log_density(self, x):
+        return self.gmm.log_density(x)
+
+
+from cases import CASES, DESIRED, K, D, base_config  # noqa: E402,F401  (pure data, shared with the tests)
+
+
+def f32(a):
+    """Round to float32 and return as float64: every input is exactly representable on the device."""
+    return np.asarray(a, np.float32).astype(np.float64)
+
+
+def problem(diagonal, K, D, seed=2025):
+    """Initial mixture and target with fp32-representable parameters.  Covariances are L L^T of fp32-representable
+    factors, so the reference's (float64) Cholesky returns L to 1e-16 and the device can be started from exactly the same
+    factor (FullCovGMM.from_cholesky)."""
+    rng = np.random.default_rng(seed)
+    means = f32(rng.standard_normal((K, D)) * 2)
+    A = rng.standard_normal((K, D, D))
+    chols = f32(np.linalg.cholesky(A @ A.transpose(0, 2, 1) / D + np.eye(D)))
+    if diagonal:
+        chols = np.stack([np.diag(np.diag(c)) for c in chols])
+    tm = f32(rng.standard_normal((3, D)) * 2)
+    tA = rng.standard_normal((3, D, D))
+    tchols = f32(np.linalg.cholesky(tA @ tA.transpose(0, 2, 1) / D + np.eye(D)))
+    return means, chols, tm, tchols
+
+
+def run_reference(name):
+    over, iters, diagonal = CASES[name][:3]
+    K_, D_ = CASES[name][3] if len(CASES[name]) > 3 else (K, D)
+    cfg = base_config(**over)
+    means, chols, tm, tchols = problem(diagonal, K_, D_)
+    covs, tc = chols @ chols.transpose(0, 2, 1), tchols @ tchols.transpose(0, 2, 1)
+    w = np.ones(K_) / K_
+    if diagonal:
+        model = DiagonalGMM(tf.constant(w), tf.constant(means), tf.constant(np.stack([np.diag(c) for c in covs])))
+    else:
+        model = FullCovGMM(tf.constant(w), tf.constant(means), tf.constant(covs))
+    target = GmmTarget(np.ones(3) / 3, tm, tc)
+    wrapped = GmmWrapper.build_from_config(model, cfg)
+    gmmvi = GMMVI.build_from_config(cfg, target, wrapped)
+    rng = np.random.default_rng(7)
+    draws = []                                   # every (D, n) block of standard-normal noise, in call order
+
+    def normal_hook(shape):
+        e = f32(rng.standard_normal(shape))
+        draws.append(e)
+        return e
+    tf.random.normal_hook = normal_hook
+    out = {"init_means": means, "init_chols": chols, "init_covs": covs, "target_means": tm, "target_chols": tchols,
+           "target_covs": tc}
+    big = D_ > 32          # keep the fixture small: samples / gradients are derivable and are checked in the small cases
+    for it in range(iters):
+        n0 = len(draws)
+        samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples()
+        H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
+        gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
+        gmmvi.num_component_adapter.adapt_number_of_components(gmmvi.num_updates)
+        m = gmmvi.model
+        out.update({
+            f"noise_shapes{it}": np.array([d.shape for d in draws[n0:]], dtype=np.int64).reshape(-1, 2),
+            f"noise{it}": np.concatenate([d.T for d in draws[n0:]], axis=0) if len(draws) > n0 else np.zeros((0, D_)),
+            f"samples{it}": samples.numpy(), f"mapping{it}": mapping.numpy().astype(np.int64), f"bg{it}": bg.numpy(),
+            f"lnpdfs{it}": lnpdfs.numpy(), f"grads{it}": grads.numpy(), f"H{it}": H.numpy(), f"g{it}": g.numpy(),
+            f"means{it}": m.means.numpy().copy(), f"chol{it}": m.chol_cov.numpy().copy(),
+            f"log_weights{it}": m.log_weights.numpy().copy(), f"stepsizes{it}": m.stepsizes.numpy().copy(),
+            f"l2{it}": m.l2_regularizers.numpy().copy(), f"last_log_etas{it}": m.last_log_etas.numpy().copy(),
+            f"num_received_updates{it}": m.num_received_updates.numpy().copy(),
+        })
+        if big:
+            for key in ("samples", "grads"):
+                del out[f"{key}{it}"]
+            out.pop("init_covs", None)              # = chols chols^T
+            out.pop("target_covs", None)
+            out[f"noise{it}"] = out[f"noise{it}"].astype(np.float32)        # exactly representable (f32() above)
+    out["iterations"] = np.array(iters)
+    return out
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:] or list(CASES)
+    for name in only:
+        res = run_reference(name)
+        np.savez_compressed(os.path.join(HERE, f"reference_{name}.npz"), **res)
+        print(f"wrote reference_{name}.npz  ({len(res)} arrays)")

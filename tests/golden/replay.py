@@ -1,0 +1,70 @@
+"""Replays the cases of tests/golden/reference_<case>.npz (outputs of the reference's own sources, see
+make_reference_golden.py) with the oracle; shared by the CPU pin test and the GPU parity test."""
+import os
+
+import numpy as np
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_IMPROVE = dict(min_stepsize=1e-4, max_stepsize=0.1, inc=1.1, dec=0.85)
+
+# the oracle-side spelling of the configurations in make_reference_golden.CASES
+CASES = {
+    "samtron_fixed": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05), stepsize=0.1),
+    "samtron_d96": dict(cfg=O.IterationConfig(desired_samples_per_component=64, weight_stepsize=0.05), stepsize=0.1),
+    "stein_standard_iw_direct": dict(cfg=O.IterationConfig(
+        desired_samples_per_component=60, weight_stepsize=0.05, ng_self_normalized=False, updater="direct",
+        weight_updater="direct", weight_self_normalized=False), stepsize=0.01),
+    "stein_iblr_improvement": dict(cfg=O.IterationConfig(
+        desired_samples_per_component=60, updater="iBLR", component_stepsize="improvement-based",
+        component_stepsize_cfg=_IMPROVE), stepsize=0.01,
+        weight_adapter=dict(initial=0.05, min_stepsize=1e-3, max_stepsize=1.0, inc=1.1, dec=0.85)),
+    "more_trust_region": dict(cfg=O.IterationConfig(desired_samples_per_component=80, weight_stepsize=0.05,
+                                                    ng_estimator="MORE"), stepsize=0.1, regularizer=1e-8),
+    "diagonal_stein_trust_region": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05),
+                                        stepsize=0.1, diagonal=True),
+    "samtron_reuse": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05,
+                                                ratio_reused_samples_to_desired=2.0), stepsize=0.1, keep_samples=True),
+}
+
+
+def load(name):
+    return np.load(os.path.join(HERE, f"reference_{name}.npz"))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if a.size else 0.0
+
+
+def replay_oracle(name, dt=np.float64):
+    """Runs the oracle on the case's inputs and noise; yields (iteration, golden, oracle outputs, oracle model)."""
+    g, oc = load(name), CASES[name]
+    K, D = g["init_means"].shape
+    kw = dict(initial_stepsize=oc["stepsize"])
+    if "regularizer" in oc:
+        kw["initial_regularizer"] = oc["regularizer"]
+    chols, tchols = g["init_chols"], g["target_chols"]
+    if oc.get("diagonal"):
+        gm = O.make_diag_gmm(np.ones(K) / K, g["init_means"], np.stack([np.diag(c) ** 2 for c in chols]), dt, **kw)
+    else:
+        gm = O.make_full_gmm(np.ones(K) / K, g["init_means"], chols @ chols.transpose(0, 2, 1), dt, **kw)
+    target = O.gmm_target(np.ones(3) / 3, g["target_means"], tchols @ tchols.transpose(0, 2, 1), dt)
+    db = O.OracleSampleDB(D, bool(oc.get("diagonal")), bool(oc.get("keep_samples")),
+                          100000 if oc.get("keep_samples") else None, dt)
+    wad = O.ImprovementBasedWeightStepsize(dt=dt, **oc["weight_adapter"]) if "weight_adapter" in oc else None
+    for it in range(int(g["iterations"])):
+        noise, shapes = g[f"noise{it}"].astype(np.float64), g[f"noise_shapes{it}"]
+        offs = np.concatenate(([0], np.cumsum(shapes[:, 1])))
+        calls = [0]
+
+        def noise_fn(k, D_, n):
+            i = calls[0]
+            calls[0] += 1
+            assert tuple(shapes[i]) == (D_, n), f"draw {i}: the reference drew {tuple(shapes[i])}, the oracle asks {(D_, n)}"
+            return noise[offs[i]:offs[i + 1]].T
+        res = O.train_iter(gm, db, target, oc["cfg"], noise_fn, wad)
+        assert calls[0] == len(shapes), "number of sampling calls differs from the reference"
+        yield it, g, res, gm
