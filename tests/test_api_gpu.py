@@ -263,3 +263,52 @@ def _more_c3_shape():
     err = rel_err(quad.cpu().numpy(), Href)
     print(f"MORE C3 shape: device error {err:.3e}, fp32-oracle error {floor:.3e}")
     assert err < max(1e-3, 5 * floor), (err, floor)     # 5151-feature regression in fp32
+
+
+@pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "diagonal_stein_trust_region", "stein_iblr_improvement"])
+def test_first_iteration_matches_reference_sources(case):
+    """The device path against outputs of the reference's OWN sources (tests/golden/reference_<case>.npz, produced by
+    tests/golden/make_reference_golden.py from /root/reference/src/gmmvi in float64): one full iteration from the
+    case's initial mixture on the case's noise.  All inputs of the fixtures are fp32-representable, so the device
+    starts from exactly the reference's parameters.  samtron_d96 takes the tensor-core kernels (D = 96)."""
+    from golden.cases import CASES, base_config as golden_config
+    from golden.replay import load
+    from gmmvi_b200.experiments.target_distributions.gmm import GMM_LNPDF
+    from gmmvi_b200.models.diagonal_gmm import DiagonalGMM
+    from gmmvi_b200.models.full_cov_gmm import FullCovGMM
+    from gmmvi_b200.models.gmm_wrapper import GmmWrapper
+    from gmmvi_b200.optimization.gmmvi import GMMVI
+    g = load(case)
+    over, _, diagonal = CASES[case][:3]
+    cfg = golden_config(**over)
+    K, D = g["init_means"].shape
+    w = np.ones(K, np.float32) / K
+    chols = g["init_chols"]
+    if diagonal:
+        model = DiagonalGMM(w, g["init_means"], np.stack([np.diag(c) ** 2 for c in chols]))
+    else:
+        model = FullCovGMM.from_cholesky(w, g["init_means"], chols)
+    target = GMM_LNPDF.from_cholesky(np.ones(3) / 3, g["target_means"], g["target_chols"])
+    gmmvi = GMMVI.build_from_config(cfg, target, GmmWrapper.build_from_config(model, cfg))
+    noise = torch.as_tensor(np.asarray(g["noise0"], np.float32)).cuda()
+    samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=noise)
+    assert np.array_equal(mapping.cpu().numpy(), g["mapping0"])                     # bit exact
+    if "samples0" in g.files:
+        assert rel_err(samples.cpu().numpy(), g["samples0"]) < 1e-5
+        assert rel_err(grads.cpu().numpy(), g["grads0"]) < 2e-4
+    assert rel_err(bg.cpu().numpy(), g["bg0"]) < 1e-5
+    assert rel_err(lnpdfs.cpu().numpy(), g["lnpdfs0"]) < 1e-5
+    H, gn = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
+    assert rel_err(H.cpu().numpy(), g["H0"]) < 4e-4
+    assert rel_err(gn.cpu().numpy(), g["g0"]) < 4e-4
+    gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
+    m = gmmvi.model
+    chol_ref = np.stack([np.diag(c) for c in g["chol0"]]) if (diagonal and g["chol0"].ndim == 3) else g["chol0"]
+    assert rel_err(m.means.cpu().numpy(), g["means0"]) < 1e-3
+    assert rel_err(m.chol_cov.cpu().numpy(), chol_ref) < 1e-3
+    assert np.allclose(m.log_weights.cpu().numpy(), g["log_weights0"], rtol=4e-3, atol=1e-5)
+    assert np.allclose(m.stepsizes.cpu().numpy(), g["stepsizes0"], rtol=1e-5)
+    assert np.allclose(m.l2_regularizers.cpu().numpy(), g["l20"])
+    assert np.array_equal(m.num_received_updates.cpu().numpy(), g["num_received_updates0"])
+    if cfg["ng_based_updater_type"] == "trust-region":
+        assert np.allclose(m.last_log_etas.cpu().numpy(), g["last_log_etas0"], rtol=1e-3)
