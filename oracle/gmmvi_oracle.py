@@ -1,8 +1,9 @@
 """NumPy restatement of the reference's SAMTRON hot path (TEST INFRASTRUCTURE ONLY).
 
-PARITY UNPINNED (see oracle/__init__.py): the reference has no golden vectors and TF cannot
-be imported here; every function below follows the cited reference lines op for op and is
-pinned against independent closed forms in tests/test_oracle_pins.py.
+PARITY PIN (see oracle/__init__.py): the reference has no golden vectors and TF cannot be imported here; every function
+below follows the cited reference lines op for op and is pinned (a) against the outputs of the reference's own sources
+executed over a torch stand-in for the TensorFlow API (tests/golden/reference_*.npz, <= 1e-13 in float64) and (b) against
+independent closed forms, both in tests/test_oracle_pins.py.
 
 All paths are relative to /root/reference/src/gmmvi/ .  `dt` selects the arithmetic type:
 np.float32 mimics the reference (tf.float32 everywhere), np.float64 is the "truth" used to
