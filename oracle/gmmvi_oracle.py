@@ -332,6 +332,12 @@ class OracleSampleDB:
             log_pdfs = logsumexp(np.stack((log_pdfs, nxt), axis=0), axis=0)
         return log_pdfs.astype(self.dt)
 
+    def get_random_sample(self, N, shuffle_fn):
+        """sample_db.py:137-152: the first N entries of a random permutation of the database (shuffle_fn(n) -> the
+        permutation tf.random.shuffle(tf.range(n)) produced)."""
+        chosen = np.asarray(shuffle_fn(self.samples.shape[0]), np.int64)[:int(N)]
+        return self.samples[chosen], self.target_lnpdfs[chosen]
+
     def get_newest_samples(self, N):
         """sample_db.py:195-228 -> (bg, samples, mapping, lnpdfs, grads)."""
         dt, D = self.dt, self._dim
@@ -890,6 +896,114 @@ def train_iter(gmm: OracleGMM, db: OracleSampleDB, target: Callable, cfg: Iterat
         direct_weight_update(gmm, elr, ws, cfg.temperature)
     return dict(samples=X, mapping=mapping, bg=bg, lnpdfs=lnpdfs, grads=grads, H_neg=H, g_neg=g,
                 elr=elr, update=info)
+
+
+# --------------------------------------------------------------------------------------
+# N2: adding / deleting components (gmm_wrapper.py:90-148, component_adaptation.py:145-300)
+# --------------------------------------------------------------------------------------
+def add_component(gmm: OracleGMM, initial_weight, initial_mean, initial_cov):
+    """GmmWrapper.add_component (gmm_wrapper.py:90-127) on top of FullCovGMM / DiagonalGMM.add_component
+    (full_cov_gmm.py:64-68, diagonal_gmm.py:55-59).  The model's weights are renormalised by GMM.replace_weights, i.e.
+    WITHOUT a new column in weight_history; the new component's history rows are -FLT_MAX rewards and its initial weight."""
+    dt = gmm.dt
+    gmm.means = np.concatenate((gmm.means, np.asarray(initial_mean, dt)[None]), axis=0)
+    new_chol = np.sqrt(np.asarray(initial_cov, dt)) if gmm.diagonal_covs else cholesky_or_nan(np.asarray(initial_cov, dt))
+    gmm.chol_cov = np.concatenate((gmm.chol_cov, new_chol[None]), axis=0)
+    gmm.replace_weights(np.concatenate((gmm.log_weights, np.log(np.asarray([initial_weight], dt)))))
+    H = gmm.reward_history.shape[1]
+    gmm.l2_regularizers = np.concatenate((gmm.l2_regularizers, np.asarray([gmm.initial_regularizer], dt)))
+    gmm.last_log_etas = np.concatenate((gmm.last_log_etas, np.asarray([-1.0], dt)))
+    gmm.num_received_updates = np.concatenate((gmm.num_received_updates, np.zeros(1, dt)))
+    gmm.stepsizes = np.concatenate((gmm.stepsizes, np.asarray([gmm.initial_stepsize], dt)))
+    gmm.reward_history = np.concatenate((gmm.reward_history, np.full((1, H), FLT_MIN, dt)), axis=0)
+    gmm.weight_history = np.concatenate((gmm.weight_history, np.full((1, H), initial_weight, dt)), axis=0)
+
+
+def remove_component(gmm: OracleGMM, idx: int):
+    """GmmWrapper.remove_component (gmm_wrapper.py:129-148) + GMM.remove_component (gmm.py:388-399)."""
+    keep = np.arange(gmm.num_components) != idx
+    log_weights = gmm.log_weights[keep]
+    gmm.means, gmm.chol_cov = gmm.means[keep], gmm.chol_cov[keep]
+    gmm.replace_weights(log_weights)
+    for name in ("l2_regularizers", "last_log_etas", "num_received_updates", "stepsizes", "reward_history",
+                 "weight_history"):
+        setattr(gmm, name, getattr(gmm, name)[keep])
+
+
+class VipsComponentAdaptation:
+    """component_adaptation.py:145-300 (without prior samples: num_prior_samples = 0, the default of every shipped
+    configuration).  Randomness is injected: uniform_fn() -> the draw of tf.random.uniform([1]) (:208), shuffle_fn(n) ->
+    the permutation of sample_db.get_random_sample (sample_db.py:151)."""
+
+    def __init__(self, gmm: OracleGMM, db: OracleSampleDB, prior_mean, initial_cov, del_iters, add_iters, max_components,
+                 thresholds_for_add_heuristic, min_weight_for_del_heuristic, num_database_samples):
+        self.gmm, self.db = gmm, db
+        dt, D = gmm.dt, gmm.num_dimensions
+        # prior = DiagonalGMM(1, prior_mean, initial_cov): its average entropy (gmm.py:262-272, diagonal_gmm.py:36-37)
+        self.prior_entropy = None
+        if prior_mean is not None and initial_cov is not None:
+            cov = np.broadcast_to(np.asarray(initial_cov, dt), (D,))
+            self.prior_entropy = dt.type(0.5 * D * (LOG_2PI + 1)) + np.sum(np.log(np.sqrt(cov)))
+        self.del_iters, self.add_iters, self.max_components = int(del_iters), int(add_iters), int(max_components)
+        self.num_db_samples = num_database_samples
+        self.num_calls_to_add_heuristic = 0
+        self.thresholds = np.atleast_1d(np.asarray(thresholds_for_add_heuristic, dt))
+        self.min_weight = min_weight_for_del_heuristic
+        fd = int(math.floor(self.del_iters / 3))                                      # :171
+        sigma = dt.type(self.del_iters / 8.0)
+        xs = np.arange(-fd, fd).astype(dt)
+        kernel = np.exp(-0.5 * (xs / sigma) ** 2) / (sigma * dt.type(math.sqrt(2 * math.pi)))      # Normal(0, sigma).prob
+        self.kernel = kernel / np.sum(kernel)
+        self.reward_improvements = np.zeros(0, dt)
+
+    def adapt_number_of_components(self, iteration, uniform_fn, shuffle_fn, target):
+        """:177-190.  Returns (deleted indices, index of the added component or None)."""
+        deleted, added = [], None
+        if iteration > self.del_iters:
+            deleted = self.delete_bad_components()
+        if iteration > 1 and iteration % self.add_iters == 0 and self.gmm.num_components < self.max_components:
+            self.num_calls_to_add_heuristic += 1                                      # :242
+            samples, lnpdfs = self.db.get_random_sample(self.num_db_samples, shuffle_fn)
+            added = self.add_at_best_location(samples, lnpdfs, uniform_fn)
+        return deleted, added
+
+    def add_at_best_location(self, samples, target_lnpdfs, uniform_fn):
+        """:193-226."""
+        g = self.gmm
+        dt, D = g.dt, g.num_dimensions
+        it = self.num_calls_to_add_heuristic % len(self.thresholds)
+        model_lq = log_density(g, samples)
+        a = dt.type(uniform_fn())
+        des_entropy = get_average_entropy(g) * a + self.prior_entropy * (1 - a) if self.prior_entropy is not None \
+            else get_average_entropy(g)
+        rewards = target_lnpdfs - np.maximum(np.max(model_lq) - self.thresholds[it], model_lq)
+        new_mean = samples[int(np.argmax(rewards))]
+        H_unscaled = dt.type(0.5 * D * (LOG_2PI + 1))
+        c = np.exp((2 * (des_entropy - H_unscaled)) / D)
+        new_cov = c * np.ones(D, dt) if g.diagonal_covs else c * np.eye(D, dtype=dt)
+        add_component(g, 1e-29, new_mean, new_cov)
+        return g.num_components - 1
+
+    def delete_bad_components(self):
+        """:261-300."""
+        g = self.gmm
+        ks, d = self.kernel.size, self.del_iters
+        rh, wh = g.reward_history, g.weight_history
+        current = np.mean(rh[:, -ks:] * self.kernel[None, :], axis=1)
+        old = np.mean(rh[:, -ks - d:-d] * self.kernel[None, :], axis=1)
+        old = old - np.max(current)
+        current = current - np.max(current)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            self.reward_improvements = (current - old) / np.abs(old)
+            max_actual = np.max(wh[:, -ks - d:-1], axis=1)
+            window = rh[:, -ks - d:]
+            max_greedy = np.max(np.exp(window - logsumexp(window, axis=0, keepdims=True)), axis=1)
+        max_weights = np.maximum(max_actual, max_greedy)
+        is_bad = (self.reward_improvements <= 0.4) & (max_weights < self.min_weight) & (rh[:, -d] != -FLT_MAX)
+        bad = sorted(np.nonzero(is_bad)[0].tolist(), reverse=True)
+        for idx in bad:
+            remove_component(g, idx)
+        return bad
 
 
 # =====================================================================================================

@@ -50,6 +50,14 @@ CASES = {
                            "ng_estimator_config": {"initial_l2_regularizer": 1e-8},
                            "sample_selector_config": {"desired_samples_per_component": 80}}, 3, False),
     "diagonal_stein_trust_region": ({"model_initialization": {"use_diagonal_covs": True}}, 3, True),
+    # SAMTRON proper: components are added (every 2nd iteration, at the best of 500 database samples) and deleted
+    # (Gaussian-smoothed reward window of del_iters = 6) by VipsComponentAdaptation
+    "samtron_adaptive": ({"use_sample_database": True, "num_component_adapter_type": "adaptive",
+                          "num_component_adapter_config": {"del_iters": 6, "add_iters": 2, "max_components": 9,
+                                                           "thresholds_for_add_heuristic": [50.0, 10.0],
+                                                           "min_weight_for_del_heuristic": 0.05,
+                                                           "num_database_samples": 500, "num_prior_samples": 0},
+                          "sample_selector_config": {"desired_samples_per_component": 40}}, 16, False),
     "samtron_reuse": ({"use_sample_database": True,
                        "sample_selector_config": {"ratio_reused_samples_to_desired": 2.0}}, 4, False),
 }

@@ -96,11 +96,23 @@ def run_reference(name):
         draws.append(e)
         return e
     tf.random.normal_hook = normal_hook
+    uniforms, perms = [], []                     # draws of the component adaptation, in call order
+
+    def uniform_hook(shape):
+        u = f32(rng.uniform(size=shape))
+        uniforms.append(u.reshape(-1))
+        return u
+
+    def shuffle_hook(n):
+        p = rng.permutation(n)
+        perms.append(p)
+        return p
+    tf.random.uniform_hook, tf.random.shuffle_hook = uniform_hook, shuffle_hook
     out = {"init_means": means, "init_chols": chols, "init_covs": covs, "target_means": tm, "target_chols": tchols,
            "target_covs": tc}
     big = D_ > 32          # keep the fixture small: samples / gradients are derivable and are checked in the small cases
     for it in range(iters):
-        n0 = len(draws)
+        n0, u0, p0 = len(draws), len(uniforms), len(perms)
         samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples()
         H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
         gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
@@ -116,6 +128,16 @@ def run_reference(name):
             f"l2{it}": m.l2_regularizers.numpy().copy(), f"last_log_etas{it}": m.last_log_etas.numpy().copy(),
             f"num_received_updates{it}": m.num_received_updates.numpy().copy(),
         })
+        if cfg["num_component_adapter_type"] == "adaptive":
+            out.update({f"uniform{it}": np.concatenate(uniforms[u0:]) if len(uniforms) > u0 else np.zeros(0),
+                        f"perm{it}": np.concatenate(perms[p0:]).astype(np.int32) if len(perms) > p0 else np.zeros(0, np.int32),
+                        f"reward_history{it}": m.reward_history.numpy().copy(),
+                        f"weight_history{it}": m.weight_history.numpy().copy()})
+        if cfg["num_component_adapter_type"] == "adaptive":
+            for key in ("samples", "grads"):            # derivable; checked in the fixed-K cases
+                del out[f"{key}{it}"]
+            out[f"noise{it}"] = out[f"noise{it}"].astype(np.float32)
+            out[f"mapping{it}"] = out[f"mapping{it}"].astype(np.int32)
         if big:
             for key in ("samples", "grads"):
                 del out[f"{key}{it}"]

@@ -24,6 +24,11 @@ CASES = {
                                                     ng_estimator="MORE"), stepsize=0.1, regularizer=1e-8),
     "diagonal_stein_trust_region": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05),
                                         stepsize=0.1, diagonal=True),
+    "samtron_adaptive": dict(cfg=O.IterationConfig(desired_samples_per_component=40, weight_stepsize=0.05), stepsize=0.1,
+                             keep_samples=True,
+                             adaptive=dict(del_iters=6, add_iters=2, max_components=9,
+                                           thresholds_for_add_heuristic=[50.0, 10.0], min_weight_for_del_heuristic=0.05,
+                                           num_database_samples=500)),
     "samtron_reuse": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05,
                                                 ratio_reused_samples_to_desired=2.0), stepsize=0.1, keep_samples=True),
 }
@@ -44,6 +49,8 @@ def replay_oracle(name, dt=np.float64):
     g, oc = load(name), CASES[name]
     K, D = g["init_means"].shape
     kw = dict(initial_stepsize=oc["stepsize"])
+    if "adaptive" in oc:                  # GmmWrapper.build_from_config, gmm_wrapper.py:53-54
+        kw["max_reward_history_length"] = 2 * max(2, oc["adaptive"]["del_iters"])
     if "regularizer" in oc:
         kw["initial_regularizer"] = oc["regularizer"]
     chols, tchols = g["init_chols"], g["target_chols"]
@@ -55,6 +62,7 @@ def replay_oracle(name, dt=np.float64):
     db = O.OracleSampleDB(D, bool(oc.get("diagonal")), bool(oc.get("keep_samples")),
                           100000 if oc.get("keep_samples") else None, dt)
     wad = O.ImprovementBasedWeightStepsize(dt=dt, **oc["weight_adapter"]) if "weight_adapter" in oc else None
+    adapter = O.VipsComponentAdaptation(gm, db, 0.0, 1.0, **oc["adaptive"]) if "adaptive" in oc else None
     for it in range(int(g["iterations"])):
         noise, shapes = g[f"noise{it}"].astype(np.float64), g[f"noise_shapes{it}"]
         offs = np.concatenate(([0], np.cumsum(shapes[:, 1])))
@@ -67,4 +75,13 @@ def replay_oracle(name, dt=np.float64):
             return noise[offs[i]:offs[i + 1]].T
         res = O.train_iter(gm, db, target, oc["cfg"], noise_fn, wad)
         assert calls[0] == len(shapes), "number of sampling calls differs from the reference"
+        if adapter is not None:           # GMMVI.train_iter: adapt_number_of_components(num_updates), gmmvi.py:161
+            res["pre_adaptation"] = dict(means=gm.means.copy(), chol=gm.chol_cov.copy(), log_weights=gm.log_weights.copy())
+            us, perm = list(g[f"uniform{it}"]), g[f"perm{it}"]
+
+            def shuffle_fn(n):
+                assert n == len(perm), (n, len(perm))
+                return perm
+            res["deleted"], res["added"] = adapter.adapt_number_of_components(it + 1, lambda: us.pop(0), shuffle_fn, target)
+            assert not us, "the reference drew a uniform number the oracle did not ask for"
         yield it, g, res, gm

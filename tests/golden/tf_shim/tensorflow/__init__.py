@@ -233,7 +233,9 @@ def rank(x):
     return _torch.tensor(_t(x).dim(), dtype=_INT)
 
 
-def range(*args, dtype=None, **_):  # noqa: A001
+def range(*args, start=None, limit=None, delta=None, dtype=None, **_):  # noqa: A001
+    if start is not None or limit is not None:
+        args = tuple(a for a in (start if start is not None else 0, limit, delta) if a is not None)
     vals = [int(a) if not (isinstance(a, float)) else a for a in args]
     return _torch.arange(*vals, dtype=_dt(dtype) or _INT)
 

@@ -306,13 +306,16 @@ def test_mmd_restatement():
 # /root/reference/src/gmmvi unmodified over a torch stand-in for the TensorFlow API and commits the results)
 # =====================================================================================================
 @pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "stein_standard_iw_direct", "stein_iblr_improvement",
-                                  "more_trust_region", "diagonal_stein_trust_region", "samtron_reuse"])
+                                  "more_trust_region", "diagonal_stein_trust_region", "samtron_reuse",
+                                  "samtron_adaptive"])
 def test_oracle_matches_reference_sources(case):
     """Every quantity of every iteration of GMMVI.train_iter as the reference's code computes it (float64): sample
     selection and mapping bit exact (incl. the per-component numbers of new samples under sample reuse), background and
     target densities, target gradients, natural-gradient estimates (Stein self-normalised / standard importance
     weights, MORE), component updates (KL-constrained bracketing search incl. the stored etas, direct, iBLR), weight
-    updates (trust region, direct), stepsize adaptation and the l2 / update-count bookkeeping."""
+    updates (trust region, direct), stepsize adaptation and the l2 / update-count bookkeeping; samtron_adaptive adds
+    VipsComponentAdaptation (16 iterations with five added and four deleted components: the comparison of the mixture
+    after every iteration fails on the first wrong addition or deletion) and the reward / weight histories."""
     from golden.replay import rel, replay_oracle
     n = 0
     for it, g, res, gm in replay_oracle(case):
@@ -331,5 +334,10 @@ def test_oracle_matches_reference_sources(case):
         assert rel(gm.l2_regularizers, g[f"l2{it}"]) < 1e-12
         assert rel(gm.last_log_etas, g[f"last_log_etas{it}"]) < 1e-9
         assert np.array_equal(gm.num_received_updates, g[f"num_received_updates{it}"])
+        if f"reward_history{it}" in g.files:
+            for mine, ref in ((gm.reward_history, g[f"reward_history{it}"]), (gm.weight_history, g[f"weight_history{it}"])):
+                unset = ref == -np.finfo(np.float32).max              # never written: tf.float32.min, exactly
+                assert mine.shape == ref.shape and np.array_equal(mine == -np.finfo(np.float32).max, unset)
+                assert np.allclose(mine[~unset], ref[~unset], rtol=1e-9, atol=1e-300)
         n += 1
     assert n == int(g["iterations"])
