@@ -63,13 +63,17 @@ class GMMVI:
         gmm = self.model.model if hasattr(self.model, "model") else self.model
         gmm.shard = shard
 
-    def train_iter(self, noise=None):
+    def train_iter(self, noise=None, adaptation_draws=None):
         """optimization/gmmvi.py:146-161.  `noise` ([N,D] standard-normal draws, optional) replaces the device
-        generator for this iteration's samples (used by the parity tests and the end-to-end benchmark)."""
+        generator for this iteration's samples (used by the parity tests and the end-to-end benchmark);
+        `adaptation_draws` = (uniform, permutation) does the same for the two random draws of a component addition."""
         samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
             self.sample_selector.select_samples(**({} if noise is None else {"noise": noise}))
         self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
-        self.num_component_adapter.adapt_number_of_components(self.num_updates)
+        if adaptation_draws is None:
+            self.num_component_adapter.adapt_number_of_components(self.num_updates)
+        else:
+            self.num_component_adapter.adapt_number_of_components(self.num_updates, *adaptation_draws)
 
     def _run_updates(self, samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads):
         """optimization/gmmvi.py:163-174."""

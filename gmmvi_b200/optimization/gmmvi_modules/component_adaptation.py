@@ -65,16 +65,17 @@ class VipsComponentAdaptation(ComponentAdaptation):
         kernel = torch.exp(-0.5 * (xs / sigma) ** 2) / (sigma * sqrt(2 * pi))
         self.kernel = (kernel / torch.sum(kernel)).to(dev)
 
-    def adapt_number_of_components(self, iteration):
-        """component_adaptation.py:177-190."""
+    def adapt_number_of_components(self, iteration, uniform=None, permutation=None):
+        """component_adaptation.py:177-190.  `uniform` / `permutation` (optional) replace the two random draws of an
+        addition (the entropy mix of :208 and the database shuffle of sample_db.py:151) in the parity tests."""
         iteration = int(iteration)
         if iteration > self.del_iters:
             self.delete_bad_components()
         if iteration > 1 and iteration % self.add_iters == 0:
             if self.model.num_components < self.max_components:
-                self.add_new_component()
+                self.add_new_component(uniform, permutation)
 
-    def add_at_best_location(self, samples, target_lnpdfs):
+    def add_at_best_location(self, samples, target_lnpdfs, uniform=None):
         """component_adaptation.py:193-226."""
         m = self.model
         D = m.num_dimensions
@@ -82,7 +83,7 @@ class VipsComponentAdaptation(ComponentAdaptation):
         thr = self.thresholds_for_addHeuristic[it]
         model_log_densities = m.log_density(samples.contiguous())
         init_weight = 1e-29
-        a = torch.rand(1, device=m.device)
+        a = torch.rand(1, device=m.device) if uniform is None else torch.full((1,), float(uniform), device=m.device)
         if self.prior is not None:
             des_entropy = m.get_average_entropy() * a + self.prior.get_average_entropy() * (1 - a)
         else:
@@ -98,23 +99,23 @@ class VipsComponentAdaptation(ComponentAdaptation):
             new_cov = c * torch.eye(D, device=m.device)
         m.add_component(init_weight, new_mean, new_cov, torch.tensor([thr], device=m.device), des_entropy.reshape(1))
 
-    def select_samples_for_adding_heuristic(self):
+    def select_samples_for_adding_heuristic(self, permutation=None):
         """component_adaptation.py:229-249."""
         self.num_calls_to_add_heuristic += 1
-        samples, target_lnpdfs = self.sample_db.get_random_sample(self.num_db_samples)
+        samples, target_lnpdfs = self.sample_db.get_random_sample(self.num_db_samples, permutation)
         prior_samples = torch.zeros((0, self.model.num_dimensions), device=self.model.device)
         if self.num_prior_samples > 0:
             prior_samples = self.prior.sample(self.num_prior_samples)[0]
             self.sample_db.num_samples_written += self.num_prior_samples
         return samples, target_lnpdfs, prior_samples
 
-    def add_new_component(self):
+    def add_new_component(self, uniform=None, permutation=None):
         """component_adaptation.py:251-259."""
-        samples, target_lnpdfs, prior_samples = self.select_samples_for_adding_heuristic()
+        samples, target_lnpdfs, prior_samples = self.select_samples_for_adding_heuristic(permutation)
         if self.num_prior_samples > 0:
             samples = torch.cat((samples, prior_samples), 0)
             target_lnpdfs = torch.cat((target_lnpdfs, self.target_lnpdf.log_density(prior_samples)), 0)
-        self.add_at_best_location(samples, target_lnpdfs)
+        self.add_at_best_location(samples, target_lnpdfs, uniform)
 
     def delete_bad_components(self):
         """component_adaptation.py:261-300."""

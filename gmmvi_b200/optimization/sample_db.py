@@ -119,9 +119,13 @@ class SampleDB:
             self.consts = cst if cst is not None else self.consts
             self.samples, self.target_lnpdfs, self.target_grads = samples, target_lnpdfs, target_grads
 
-    def get_random_sample(self, N: int):
-        """optimization/sample_db.py:137-152."""
-        idx = torch.randperm(self.samples.shape[0], device=self.device)[:N]
+    def get_random_sample(self, N: int, permutation=None):
+        """optimization/sample_db.py:137-152.  `permutation` (optional, a permutation of range(#samples)) replaces the
+        device generator's shuffle: the parity tests inject the one the reference drew."""
+        if permutation is None:
+            idx = torch.randperm(self.samples.shape[0], device=self.device)[:N]
+        else:
+            idx = torch.as_tensor(permutation, dtype=torch.long, device=self.device)[:N]
         return self.samples[idx], self.target_lnpdfs[idx]
 
     def gaussian_log_pdf(self, mean, chol, inv_chol, x):
