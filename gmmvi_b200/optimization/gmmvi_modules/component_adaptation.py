@@ -21,12 +21,12 @@ class ComponentAdaptation:
             return FixedComponentAdaptation(**config["num_component_adapter_config"])
         raise ValueError(f"config['num_component_adapter_type'] is '{t}' which is an unknown type")
 
-    def adapt_number_of_components(self, iteration):
+    def adapt_number_of_components(self, iteration, uniform=None, permutation=None):
         raise NotImplementedError
 
 
 class FixedComponentAdaptation(ComponentAdaptation):
-    def adapt_number_of_components(self, iteration):
+    def adapt_number_of_components(self, iteration, uniform=None, permutation=None):
         pass
 
 
