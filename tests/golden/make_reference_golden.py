@@ -148,9 +148,76 @@ def run_reference(name):
     return out
 
 
+def run_model_api(diagonal):
+    """Direct calls of the model surface of the reference's FullCovGMM / DiagonalGMM."""
+    K_, D_, N_ = 5, 7, 40
+    means, chols, _, _ = problem(diagonal, K_, D_, seed=77)
+    rng = np.random.default_rng(78)
+    w = f32(rng.dirichlet(np.ones(K_)))
+    X = f32(rng.standard_normal((N_, D_)) * 2.5)
+    covs = chols @ chols.transpose(0, 2, 1)
+    if diagonal:
+        model = DiagonalGMM(tf.constant(w), tf.constant(means), tf.constant(np.stack([np.diag(c) for c in covs])))
+    else:
+        model = FullCovGMM(tf.constant(w), tf.constant(means), tf.constant(covs))
+    Xt = tf.constant(X)
+    out = {"init_means": means, "init_chols": chols, "weights_in": w, "X": X}
+    out["log_weights"] = model.log_weights.numpy().copy()
+    out["component_log_densities"] = model.component_log_densities(Xt).numpy()
+    lq, lqk = model.log_densities_also_individual(Xt)
+    out["log_density"], out["individual"] = lq.numpy(), lqk.numpy()
+    out["log_density_only"] = model.log_density(Xt).numpy()
+    out["density"] = model.density(Xt).numpy()
+    lq2, grad, lqk2 = model.log_density_and_grad(tf.constant(X))
+    out["lq_grad"], out["grad"], out["lqk_grad"] = lq2.numpy(), grad.numpy(), lqk2.numpy()
+    out["component_entropies"] = model.component_entropies().numpy()
+    out["average_entropy"] = np.asarray(model.get_average_entropy().numpy())
+    out["covs"] = model.covs.numpy()
+    if not diagonal:
+        out["component_log_density_2"] = model.component_log_density(2, Xt).numpy()
+        cl, cg = model.component_log_density_and_grad(1, tf.constant(X))
+        out["component_lq_1"], out["component_grad_1"] = cl.numpy(), cg.numpy()
+        out["component_marginal_3"] = model.component_marginal_log_densities(Xt, 3).numpy()
+        out["marginal_3"] = model.marginal_log_density(Xt, 3).numpy()
+    # sampling: categorical, GMM.sample (quirk 4: samples grouped by component, component indices in draw order),
+    # per-component counts.  (Quirk 5 - an all-False comparison row selects component 0 - needs u >= cumsum(w)[-1],
+    # which depends on the last ulp of the cumulative sum: it is tested on the oracle and the device directly.)
+    u = f32(rng.uniform(size=(30, 1)))
+    u[0, 0] = np.nextafter(np.float32(1.0), np.float32(0.0))
+    tf.random.uniform_hook = lambda shape: u
+    out["u"] = u[:, 0]
+    out["sample_categorical"] = model.sample_categorical(30).numpy().astype(np.int32)
+    draws = []
+
+    def normal_hook(shape):
+        e = f32(rng.standard_normal(shape))
+        draws.append(e)
+        return e
+    tf.random.normal_hook = normal_hook
+    xs, comps = model.sample(30)
+    out["sample_x"], out["sample_components"] = xs.numpy(), comps.numpy().astype(np.int32)
+    out["sample_noise"] = np.concatenate([d.T for d in draws], axis=0)
+    out["sample_noise_shapes"] = np.array([d.shape for d in draws], dtype=np.int64)
+    draws.clear()
+    n_per = np.array([3, 0, 5, 1, 2], dtype=np.int64)
+    xs2, mapping = model.sample_from_components_no_shuffle(tf.constant(n_per))
+    out["n_per"], out["no_shuffle_x"], out["no_shuffle_mapping"] = n_per, xs2.numpy(), mapping.numpy().astype(np.int32)
+    out["no_shuffle_noise"] = np.concatenate([d.T for d in draws], axis=0)
+    # structural edits: replace_weights (normalises), add_component, remove_component
+    model.replace_weights(tf.constant(f32(np.log(w) + rng.standard_normal(K_))))
+    out["log_weights_replaced"] = model.log_weights.numpy().copy()
+    new_cov = f32(np.diag(covs[0]) * 0.5) if diagonal else f32(covs[0] * 0.5 + np.eye(D_))
+    model.add_component(tf.constant(f32(0.2)), tf.constant(f32(means[0] + 1.0)), tf.constant(new_cov))
+    out["new_cov"] = new_cov
+    out["added_log_weights"], out["added_chol"] = model.log_weights.numpy().copy(), model.chol_cov.numpy().copy()
+    model.remove_component(1)
+    out["removed_log_weights"], out["removed_means"] = model.log_weights.numpy().copy(), model.means.numpy().copy()
+    return out
+
+
 if __name__ == "__main__":
-    only = sys.argv[1:] or list(CASES)
+    only = sys.argv[1:] or list(CASES) + ["model_api_full", "model_api_diagonal"]
     for name in only:
-        res = run_reference(name)
+        res = run_model_api(name.endswith("diagonal")) if name.startswith("model_api") else run_reference(name)
         np.savez_compressed(os.path.join(HERE, f"reference_{name}.npz"), **res)
         print(f"wrote reference_{name}.npz  ({len(res)} arrays)")

@@ -341,3 +341,67 @@ def test_oracle_matches_reference_sources(case):
                 assert np.allclose(mine[~unset], ref[~unset], rtol=1e-9, atol=1e-300)
         n += 1
     assert n == int(g["iterations"])
+
+
+@pytest.mark.parametrize("diagonal", [False, True])
+def test_oracle_model_surface_matches_reference_sources(diagonal):
+    """The model API as the reference's FullCovGMM / DiagonalGMM compute it: densities, the
+    GradientTape gradient, marginals, entropies, categorical sampling, GMM.sample's grouping (quirk 4), sampling with
+    injected noise, weight replacement, adding and removing components."""
+    from golden.replay import load, rel
+    g = load("model_api_diagonal" if diagonal else "model_api_full")
+    K, D = g["init_means"].shape
+    chols, X = g["init_chols"], g["X"]
+    dt = np.float64
+    if diagonal:
+        gm = O.make_diag_gmm(g["weights_in"], g["init_means"], np.stack([np.diag(c) ** 2 for c in chols]), dt)
+    else:
+        gm = O.make_full_gmm(g["weights_in"], g["init_means"], chols @ chols.transpose(0, 2, 1), dt)
+    assert rel(gm.log_weights, g["log_weights"]) < 1e-13
+    assert rel(O.component_log_densities(gm, X), g["component_log_densities"]) < 1e-13
+    lq, lqk = O.log_densities_also_individual(gm, X)
+    assert rel(lq, g["log_density"]) < 1e-13 and rel(lqk, g["individual"]) < 1e-13
+    assert rel(O.log_density(gm, X), g["log_density_only"]) < 1e-13
+    assert rel(np.exp(O.log_density(gm, X)), g["density"]) < 1e-12
+    lq2, grad, lqk2 = O.log_density_and_grad(gm, X)
+    assert rel(lq2, g["lq_grad"]) < 1e-13 and rel(grad, g["grad"]) < 1e-11 and rel(lqk2, g["lqk_grad"]) < 1e-13
+    assert rel(O.component_entropies(gm), g["component_entropies"]) < 1e-13
+    assert rel(O.get_average_entropy(gm), g["average_entropy"]) < 1e-13
+    covs = np.stack([np.diag(c) ** 2 for c in chols]) if diagonal else chols @ chols.transpose(0, 2, 1)
+    assert rel(covs, g["covs"]) < 1e-13
+    if not diagonal:
+        assert rel(O.component_log_densities(gm, X)[2], g["component_log_density_2"]) < 1e-13
+        one = O.make_full_gmm(np.ones(1), g["init_means"][1:2], covs[1:2], dt)
+        l1, g1, _ = O.log_density_and_grad(one, X)
+        assert rel(l1, g["component_lq_1"]) < 1e-13 and rel(g1, g["component_grad_1"]) < 1e-11
+        cm = O.component_marginal_log_densities(gm, X, 3)
+        assert rel(cm, g["component_marginal_3"]) < 1e-13
+        assert rel(O.logsumexp(cm + gm.log_weights[:, None], axis=0), g["marginal_3"]) < 1e-13
+    # sampling
+    comps = O.sample_categorical(gm, g["u"])
+    assert np.array_equal(comps, g["sample_categorical"]) and comps[0] == K - 1      # u just below 1
+    assert np.array_equal(g["sample_components"], comps)                               # draw order (quirk 4)
+    counts = np.bincount(comps, minlength=K)
+    assert np.array_equal(g["sample_noise_shapes"][:, 1], counts)
+    offs = np.concatenate(([0], np.cumsum(counts)))
+    xs, _ = O.sample_from_components_no_shuffle(gm, counts, lambda k, D_, n: g["sample_noise"][offs[k]:offs[k + 1]].T)
+    assert rel(xs, g["sample_x"]) < 1e-13                                              # grouped by component
+    n_per = g["n_per"]
+    offs = np.concatenate(([0], np.cumsum(n_per)))
+    xs2, mapping = O.sample_from_components_no_shuffle(gm, n_per,
+                                                       lambda k, D_, n: g["no_shuffle_noise"][offs[k]:offs[k + 1]].T)
+    assert np.array_equal(mapping, g["no_shuffle_mapping"]) and rel(xs2, g["no_shuffle_x"]) < 1e-13
+    # structural edits
+    rng = np.random.default_rng(78)                  # replay the generator's stream up to the replace_weights draw
+    rng.dirichlet(np.ones(K)); rng.standard_normal(X.shape); rng.uniform(size=(30, 1))
+    for s in g["sample_noise_shapes"]:
+        rng.standard_normal(tuple(s))
+    for k in range(K):
+        rng.standard_normal((D, int(n_per[k])))
+    new_lw = (np.log(g["weights_in"]) + rng.standard_normal(K)).astype(np.float32).astype(np.float64)
+    gm.replace_weights(new_lw)
+    assert rel(gm.log_weights, g["log_weights_replaced"]) < 1e-13
+    O.add_component(gm, np.float32(0.2), (g["init_means"][0] + 1.0).astype(np.float32), g["new_cov"])
+    assert rel(gm.log_weights, g["added_log_weights"]) < 1e-13 and rel(gm.chol_cov, g["added_chol"]) < 1e-13
+    O.remove_component(gm, 1)
+    assert rel(gm.log_weights, g["removed_log_weights"]) < 1e-13 and rel(gm.means, g["removed_means"]) < 1e-13
