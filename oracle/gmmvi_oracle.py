@@ -385,6 +385,35 @@ def vips_select_samples(gmm: OracleGMM, db: OracleSampleDB, target, desired, rat
     return X, mapping, bg, lnpdfs, grads
 
 
+def gmm_sample(gmm: OracleGMM, u, noise_fn):
+    """GMM.sample (gmm.py:139-163) with the uniform draws u[n] and the normal draws injected: the samples come back
+    GROUPED BY COMPONENT, the component indices in DRAW ORDER (quirk 4)."""
+    comps = sample_categorical(gmm, np.asarray(u, gmm.dt))
+    counts = np.bincount(comps, minlength=gmm.num_components)
+    parts = [sample_from_component(gmm, k, np.asarray(noise_fn(k, gmm.num_dimensions, int(counts[k])), gmm.dt))
+             for k in range(gmm.num_components)]
+    return np.concatenate(parts, axis=0).astype(gmm.dt), comps
+
+
+def lin_select_samples(gmm: OracleGMM, db: OracleSampleDB, target, desired, ratio_reused, uniform_fn, noise_fn):
+    """LinSampleSelector.select_samples (sample_selector.py:258-339): `desired` is the TOTAL number of samples, the
+    effective sample size is the mixture's (:273-276), new samples are drawn from the mixture with GMM.sample, whose
+    mapping is not aligned with its samples (quirk 4) - stored in the database as is.  uniform_fn(n) -> u[n]."""
+    reused = int(math.floor(ratio_reused * desired))
+    old_bg, old_X, _, _, _ = db.get_newest_samples(reused * gmm.num_components)
+    n_reused = old_X.shape[0]
+    if n_reused == 0:
+        n_eff = 0
+    else:
+        n_eff = int(np.floor(get_effective_samples(log_density(gmm, old_X)[None, :], old_bg))[0])
+    n_add = max(1, desired - n_eff)
+    new_X, mapping = gmm_sample(gmm, uniform_fn(n_add), noise_fn)
+    new_lnpdf, new_grad = target(new_X)
+    db.add_samples(new_X, gmm.means, gmm.chol_cov, new_lnpdf, new_grad, mapping)
+    bg, X, mapping, lnpdfs, grads = db.get_newest_samples(n_reused + new_X.shape[0])
+    return X, mapping, bg, lnpdfs, grads
+
+
 # --------------------------------------------------------------------------------------
 # A9: Stein natural-gradient estimator
 # --------------------------------------------------------------------------------------
@@ -855,6 +884,7 @@ def gmm_target(weights, means, covs, dt=np.float32):
 # --------------------------------------------------------------------------------------
 @dataclass
 class IterationConfig:
+    sample_selector: str = "component-based"        # or "mixture-based" (LinSampleSelector)
     desired_samples_per_component: int = 100
     ratio_reused_samples_to_desired: float = 0.0
     ng_estimator: str = "Stein"                     # or "MORE"
@@ -870,10 +900,14 @@ class IterationConfig:
 
 
 def train_iter(gmm: OracleGMM, db: OracleSampleDB, target: Callable, cfg: IterationConfig, noise_fn,
-               weight_stepsize_adapter: Optional[ImprovementBasedWeightStepsize] = None):
+               weight_stepsize_adapter: Optional[ImprovementBasedWeightStepsize] = None, uniform_fn=None):
     """GMMVI.train_iter with FixedComponentAdaptation: select -> _run_updates."""
-    X, mapping, bg, lnpdfs, grads = vips_select_samples(
-        gmm, db, target, cfg.desired_samples_per_component, cfg.ratio_reused_samples_to_desired, noise_fn)
+    if cfg.sample_selector == "mixture-based":
+        X, mapping, bg, lnpdfs, grads = lin_select_samples(
+            gmm, db, target, cfg.desired_samples_per_component, cfg.ratio_reused_samples_to_desired, uniform_fn, noise_fn)
+    else:
+        X, mapping, bg, lnpdfs, grads = vips_select_samples(
+            gmm, db, target, cfg.desired_samples_per_component, cfg.ratio_reused_samples_to_desired, noise_fn)
     if cfg.component_stepsize == "improvement-based":
         gmm.stepsizes = improvement_based_component_stepsize(gmm, **cfg.component_stepsize_cfg)
     elif cfg.component_stepsize == "decaying":

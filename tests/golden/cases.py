@@ -58,6 +58,12 @@ CASES = {
                                                            "min_weight_for_del_heuristic": 0.05,
                                                            "num_database_samples": 500, "num_prior_samples": 0},
                           "sample_selector_config": {"desired_samples_per_component": 40}}, 16, False),
+    # the algorithm of BASELINE config C3: samples drawn from the mixture (LinSampleSelector, the number is the total),
+    # MORE estimator, trust-region updates; with reuse of the newest database samples
+    "more_mixture_based": ({"ng_estimator_type": "MORE", "ng_estimator_config": {"initial_l2_regularizer": 1e-8},
+                            "use_sample_database": True, "sample_selector_type": "mixture-based",
+                            "sample_selector_config": {"desired_samples_per_component": 360,
+                                                       "ratio_reused_samples_to_desired": 0.25}}, 4, False),
     "samtron_reuse": ({"use_sample_database": True,
                        "sample_selector_config": {"ratio_reused_samples_to_desired": 2.0}}, 4, False),
 }

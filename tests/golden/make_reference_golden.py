@@ -128,6 +128,8 @@ def run_reference(name):
             f"l2{it}": m.l2_regularizers.numpy().copy(), f"last_log_etas{it}": m.last_log_etas.numpy().copy(),
             f"num_received_updates{it}": m.num_received_updates.numpy().copy(),
         })
+        if cfg["sample_selector_type"] == "mixture-based":
+            out[f"uniform{it}"] = np.concatenate(uniforms[u0:]) if len(uniforms) > u0 else np.zeros(0)
         if cfg["num_component_adapter_type"] == "adaptive":
             out.update({f"uniform{it}": np.concatenate(uniforms[u0:]) if len(uniforms) > u0 else np.zeros(0),
                         f"perm{it}": np.concatenate(perms[p0:]).astype(np.int32) if len(perms) > p0 else np.zeros(0, np.int32),

@@ -29,6 +29,10 @@ CASES = {
                              adaptive=dict(del_iters=6, add_iters=2, max_components=9,
                                            thresholds_for_add_heuristic=[50.0, 10.0], min_weight_for_del_heuristic=0.05,
                                            num_database_samples=500)),
+    "more_mixture_based": dict(cfg=O.IterationConfig(sample_selector="mixture-based", desired_samples_per_component=360,
+                                                     ratio_reused_samples_to_desired=0.25, weight_stepsize=0.05,
+                                                     ng_estimator="MORE"), stepsize=0.1, regularizer=1e-8,
+                               keep_samples=True),
     "samtron_reuse": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05,
                                                 ratio_reused_samples_to_desired=2.0), stepsize=0.1, keep_samples=True),
 }
@@ -73,7 +77,12 @@ def replay_oracle(name, dt=np.float64):
             calls[0] += 1
             assert tuple(shapes[i]) == (D_, n), f"draw {i}: the reference drew {tuple(shapes[i])}, the oracle asks {(D_, n)}"
             return noise[offs[i]:offs[i + 1]].T
-        res = O.train_iter(gm, db, target, oc["cfg"], noise_fn, wad)
+        us = list(g[f"uniform{it}"]) if oc["cfg"].sample_selector == "mixture-based" else []
+
+        def uniform_fn(n):
+            assert n == len(us), f"the reference drew {len(us)} uniform numbers, the oracle asks {n}"
+            return np.asarray(us)
+        res = O.train_iter(gm, db, target, oc["cfg"], noise_fn, wad, uniform_fn)
         assert calls[0] == len(shapes), "number of sampling calls differs from the reference"
         if adapter is not None:           # GMMVI.train_iter: adapt_number_of_components(num_updates), gmmvi.py:161
             res["pre_adaptation"] = dict(means=gm.means.copy(), chol=gm.chol_cov.copy(), log_weights=gm.log_weights.copy())

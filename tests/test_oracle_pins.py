@@ -307,7 +307,7 @@ def test_mmd_restatement():
 # =====================================================================================================
 @pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "stein_standard_iw_direct", "stein_iblr_improvement",
                                   "more_trust_region", "diagonal_stein_trust_region", "samtron_reuse",
-                                  "samtron_adaptive"])
+                                  "samtron_adaptive", "more_mixture_based"])
 def test_oracle_matches_reference_sources(case):
     """Every quantity of every iteration of GMMVI.train_iter as the reference's code computes it (float64): sample
     selection and mapping bit exact (incl. the per-component numbers of new samples under sample reuse), background and
@@ -315,7 +315,9 @@ def test_oracle_matches_reference_sources(case):
     weights, MORE), component updates (KL-constrained bracketing search incl. the stored etas, direct, iBLR), weight
     updates (trust region, direct), stepsize adaptation and the l2 / update-count bookkeeping; samtron_adaptive adds
     VipsComponentAdaptation (16 iterations with five added and four deleted components: the comparison of the mixture
-    after every iteration fails on the first wrong addition or deletion) and the reward / weight histories."""
+    after every iteration fails on the first wrong addition or deletion) and the reward / weight histories;
+    more_mixture_based runs LinSampleSelector (samples from the mixture, misaligned mapping of GMM.sample, reuse of the
+    newest database samples by the mixture's effective sample size) with the MORE estimator."""
     from golden.replay import rel, replay_oracle
     n = 0
     for it, g, res, gm in replay_oracle(case):
