@@ -146,12 +146,14 @@ class GMM:
         eps = uniforms.reshape(-1, 1) if uniforms is not None else torch.rand((int(num_samples), 1), device=self.device)
         return torch.argmax((eps < thresholds).to(torch.int32), dim=-1).to(torch.int32)
 
-    def sample(self, num_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """models/gmm.py:139-163: samples grouped by component, indices in draw order (quirk 4)."""
-        sampled_components = self.sample_categorical(num_samples)
+    def sample(self, num_samples: int, uniforms: Optional[torch.Tensor] = None,
+               noise: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """models/gmm.py:139-163: samples grouped by component, indices in draw order (quirk 4).  `uniforms` [n] and
+        `noise` [n, D] (rows in component order) inject the random draws (parity tests)."""
+        sampled_components = self.sample_categorical(num_samples, uniforms)
         counts = torch.zeros(self.num_components, device=self.device, dtype=torch.int32)
         counts.scatter_add_(0, sampled_components.long(), torch.ones_like(sampled_components))
-        samples, _ = self.sample_from_components_no_shuffle(counts)
+        samples, _ = self.sample_from_components_no_shuffle(counts, noise=noise)
         return samples, sampled_components
 
     @property

@@ -109,7 +109,7 @@ class LinSampleSelector(SampleSelector):
         """sample_selector.py:258-278 (one row: the mixture density)."""
         return ops.importance_weights(model_densities.reshape(1, -1).contiguous(), oldsamples_pdf, want_ess=True)["ess"]
 
-    def sample_where_needed(self):
+    def sample_where_needed(self, noise=None, uniforms=None):
         """sample_selector.py:280-325 -> (new_samples, mapping, num_reused_samples)."""
         num_samples_to_reuse = self.reused_samples_per_component * self.model.num_components
         oldsamples_pdf, old_samples, _, _, _ = self.sample_db.get_newest_samples(num_samples_to_reuse)
@@ -120,12 +120,12 @@ class LinSampleSelector(SampleSelector):
             model_logpdfs = self.model.log_density(old_samples)
             n_eff = int(torch.floor(self.get_effective_samples(model_logpdfs, oldsamples_pdf))[0].item())
         n_add = max(1, self.desired_samples_per_component - n_eff)
-        new_samples, mapping = self.model.sample(n_add)
+        new_samples, mapping = self.model.sample(n_add, uniforms=uniforms, noise=noise)
         return new_samples, mapping, num_reused_samples
 
-    def select_samples(self):
-        """sample_selector.py:327-339."""
-        new_samples, mapping, num_reused_samples = self.sample_where_needed()
+    def select_samples(self, noise=None, uniforms=None):
+        """sample_selector.py:327-339.  `noise` / `uniforms` inject the draws of GMM.sample (parity tests)."""
+        new_samples, mapping, num_reused_samples = self.sample_where_needed(noise, uniforms)
         new_target_grads, new_target_lnpdfs = self.get_target_grads(new_samples)
         self.sample_db.add_samples(new_samples, self.model.means, self.model.chol_cov, new_target_lnpdfs,
                                    new_target_grads, mapping, prepared=self._prepared())

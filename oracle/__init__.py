@@ -7,8 +7,8 @@ legs may import it, and only as the checker / the timed CPU baseline.
 PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path and
 TensorFlow is not installable in this image, so the pin is built from the reference's own Python sources:
 tests/golden/make_reference_golden.py executes /root/reference/src/gmmvi/{models,optimization}/... UNMODIFIED against
-tests/golden/tf_shim (a torch-CPU stand-in for the ~75 TensorFlow / TFP ops the hot path uses, float64) on seven
-configurations and commits every intermediate of every iteration (tests/golden/reference_*.npz); the restatement
+tests/golden/tf_shim (a torch-CPU stand-in for the ~75 TensorFlow / TFP ops the hot path uses, float64) on nine
+configurations (+ the model surface) and commits every intermediate of every iteration (tests/golden/reference_*.npz); the restatement
 reproduces all of them to <= 1e-13, mappings and sample counts bit exact (tests/test_oracle_pins.py::
 test_oracle_matches_reference_sources).  What this cannot pin is TensorFlow's own kernels and random generators (replaced
 by torch ops of the same documented semantics / by injected noise): in that sense the parity claim remains "the
