@@ -188,3 +188,25 @@ def test_sharded_importance_weights_match_unsharded_gloo(tmp_path):
     for p in parts:
         assert np.allclose(p["dot"], w @ rho, rtol=1e-12)
         assert np.allclose(p["gathered"][:, 0], np.arange(K) + 0.5)
+
+
+def test_default_configs_equal_the_reference_yml_files():
+    """gmmvi_b200.configs against tests/golden/reference_configs.json, which tests/golden/make_reference_configs.py wrote by
+    calling the reference's own configs/__init__.py on its yml files: every module letter, the codewords of the examples /
+    BASELINE configurations, the shipped experiment configs, get_default_config and update_config."""
+    import contextlib
+    import io
+    import json
+    from gmmvi_b200 import configs as C
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_configs.json")) as f:
+        ref = json.load(f)
+    norm = lambda d: json.loads(json.dumps(d))
+    with contextlib.redirect_stdout(io.StringIO()):
+        for codeword, want in ref["algorithm"].items():
+            assert norm(C.get_default_algorithm_config(codeword)) == want, codeword
+        for name, want in ref["experiment"].items():
+            assert norm(C.get_default_experiment_config(name)) == want, name
+        assert norm(C.get_default_config("SAMTRON", "stm20")) == ref["merged"]["SAMTRON/stm20"]
+        upd = C.update_config(C.get_default_algorithm_config("SAMTRON"),
+                              {"sample_selector_config": {"desired_samples_per_component": 7}, "temperature": 0.5})
+        assert norm(upd) == ref["merged"]["update"]
