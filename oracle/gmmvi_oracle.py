@@ -846,6 +846,19 @@ def decaying_component_stepsize(gmm: OracleGMM, initial_stepsize, annealing_expo
     return (dt.type(initial_stepsize) / (1 + np.power(gmm.num_received_updates, dt.type(annealing_exponent)))).astype(dt)
 
 
+class DecayingWeightStepsize:
+    """weight_stepsize_adaptation.py:70-106: initial / (1 + n^exponent), n = number of previous weight updates."""
+
+    def __init__(self, initial, annealing_exponent, dt=np.float32):
+        self.dt = np.dtype(dt)
+        self.initial, self.exponent, self.n = self.dt.type(initial), annealing_exponent, 0.0
+
+    def update(self, gmm: "OracleGMM"):
+        stepsize = self.initial / (1.0 + self.dt.type(self.n) ** self.exponent)
+        self.n += 1.0
+        return self.dt.type(stepsize)
+
+
 class ImprovementBasedWeightStepsize:
     """gmmvi_modules/weight_stepsize_adaptation.py:108-156."""
 

@@ -64,6 +64,23 @@ CASES = {
                             "use_sample_database": True, "sample_selector_type": "mixture-based",
                             "sample_selector_config": {"desired_samples_per_component": 360,
                                                        "ratio_reused_samples_to_desired": 0.25}}, 4, False),
+    # quirk 6 (own samples only: uniform importance weights), decaying component and weight stepsizes, temperature != 1
+    # (weight updater and eta = max(eta, temperature), but not the Stein log-ratios: quirk 7)
+    "own_samples_decaying_temperature": ({"temperature": 0.7,
+                                          "ng_estimator_config": {"only_use_own_samples": True},
+                                          "component_stepsize_adapter_type": "decaying",
+                                          "component_stepsize_adapter_config": {"initial_stepsize": 0.1,
+                                                                                "annealing_exponent": 0.5},
+                                          "weight_updater_type": "direct",
+                                          "weight_stepsize_adapter_type": "decaying",
+                                          "weight_stepsize_adapter_config": {"initial_stepsize": 0.1,
+                                                                             "annealing_exponent": 0.5}}, 4, False),
+    # one component: the weight updaters do nothing (quirk 13)
+    "single_component": ({}, 2, False, (1, 6)),
+    # direct updater with a step far too large: precision matrices lose positive definiteness, the failed Cholesky
+    # rejects the step and the l2 regulariser follows the failure rule (quirk 11)
+    "direct_rejected_steps": ({"ng_based_updater_type": "direct",
+                               "component_stepsize_adapter_config": {"initial_stepsize": 1.5}}, 3, False),
     "samtron_reuse": ({"use_sample_database": True,
                        "sample_selector_config": {"ratio_reused_samples_to_desired": 2.0}}, 4, False),
 }

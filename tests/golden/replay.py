@@ -33,6 +33,13 @@ CASES = {
                                                      ratio_reused_samples_to_desired=0.25, weight_stepsize=0.05,
                                                      ng_estimator="MORE"), stepsize=0.1, regularizer=1e-8,
                                keep_samples=True),
+    "own_samples_decaying_temperature": dict(cfg=O.IterationConfig(
+        desired_samples_per_component=60, only_use_own_samples=True, component_stepsize="decaying",
+        component_stepsize_cfg=dict(initial_stepsize=0.1, annealing_exponent=0.5), weight_updater="direct",
+        temperature=0.7), stepsize=0.1, weight_decay=dict(initial=0.1, annealing_exponent=0.5)),
+    "single_component": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05), stepsize=0.1),
+    "direct_rejected_steps": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05,
+                                                        updater="direct"), stepsize=1.5),
     "samtron_reuse": dict(cfg=O.IterationConfig(desired_samples_per_component=60, weight_stepsize=0.05,
                                                 ratio_reused_samples_to_desired=2.0), stepsize=0.1, keep_samples=True),
 }
@@ -66,6 +73,8 @@ def replay_oracle(name, dt=np.float64):
     db = O.OracleSampleDB(D, bool(oc.get("diagonal")), bool(oc.get("keep_samples")),
                           100000 if oc.get("keep_samples") else None, dt)
     wad = O.ImprovementBasedWeightStepsize(dt=dt, **oc["weight_adapter"]) if "weight_adapter" in oc else None
+    if "weight_decay" in oc:
+        wad = O.DecayingWeightStepsize(dt=dt, **oc["weight_decay"])
     adapter = O.VipsComponentAdaptation(gm, db, 0.0, 1.0, **oc["adaptive"]) if "adaptive" in oc else None
     for it in range(int(g["iterations"])):
         noise, shapes = g[f"noise{it}"].astype(np.float64), g[f"noise_shapes{it}"]

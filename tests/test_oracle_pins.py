@@ -307,7 +307,8 @@ def test_mmd_restatement():
 # =====================================================================================================
 @pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "stein_standard_iw_direct", "stein_iblr_improvement",
                                   "more_trust_region", "diagonal_stein_trust_region", "samtron_reuse",
-                                  "samtron_adaptive", "more_mixture_based"])
+                                  "samtron_adaptive", "more_mixture_based", "own_samples_decaying_temperature",
+                                  "single_component", "direct_rejected_steps"])
 def test_oracle_matches_reference_sources(case):
     """Every quantity of every iteration of GMMVI.train_iter as the reference's code computes it (float64): sample
     selection and mapping bit exact (incl. the per-component numbers of new samples under sample reuse), background and
@@ -317,7 +318,9 @@ def test_oracle_matches_reference_sources(case):
     VipsComponentAdaptation (16 iterations with five added and four deleted components: the comparison of the mixture
     after every iteration fails on the first wrong addition or deletion) and the reward / weight histories;
     more_mixture_based runs LinSampleSelector (samples from the mixture, misaligned mapping of GMM.sample, reuse of the
-    newest database samples by the mixture's effective sample size) with the MORE estimator."""
+    newest database samples by the mixture's effective sample size) with the MORE estimator; the last three cover
+    only_use_own_samples, decaying stepsizes and a temperature != 1, a single component (weight update is a no-op), and
+    rejected component updates with both branches of the l2-regulariser rule."""
     from golden.replay import rel, replay_oracle
     n = 0
     for it, g, res, gm in replay_oracle(case):
