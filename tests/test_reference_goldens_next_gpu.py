@@ -110,3 +110,13 @@ def test_component_adaptation_matches_reference_sources(iteration):
     assert np.allclose(wrapper.stepsizes.cpu().numpy(), after.stepsizes)
     assert np.allclose(wrapper.last_log_etas.cpu().numpy(), after.last_log_etas, rtol=1e-6)
     assert np.array_equal(wrapper.num_received_updates.cpu().numpy(), after.num_received_updates)
+
+
+@pytest.mark.parametrize("case", ["own_samples_decaying_temperature", "single_component", "direct_rejected_steps",
+                                  "stein_standard_iw_direct", "samtron_reuse"])
+def test_first_iteration_of_further_cases(case):
+    """The first-iteration check of tests/test_api_gpu.py on the cases that were added after the GPU budget was spent
+    (own samples / decaying stepsizes / temperature, K = 1, rejected direct steps) or left out there (standard
+    importance weights, reuse)."""
+    from test_api_gpu import test_first_iteration_matches_reference_sources as check
+    check(case)
