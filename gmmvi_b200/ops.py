@@ -364,7 +364,7 @@ def stein_diag(X, means, stds, W, G):
 
 def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=32 << 30):
     """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32).
-    Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.28 GB per component)."""
+    Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.2 GB per component)."""
     X, y, W = _chk(samples, "samples"), _chk(rewards, "rewards"), _chk(weights, "weights")
     means, linv, l2 = _chk(means, "means"), _chk(linv, "linv"), _chk(regularizers, "regularizers")
     N, D = X.shape
