@@ -200,14 +200,14 @@ def run_ours(args):
     lo_hi = ShardContext(rank, world).row_range(N_total)
     N = lo_hi[1] - lo_hi[0]                      # rows this rank draws and evaluates
 
-    def build(mean_scale):
+    def build(mean_scale, shard=True):
         means, chols, tmeans, tchols = workload_arrays(K, D, 0, mean_scale)
         model = FullCovGMM.from_cholesky(np.ones(K, np.float32) / K, means, chols, device=dev)
         tgt = GMM_LNPDF.from_cholesky(np.ones(TARGET_COMPONENTS) / TARGET_COMPONENTS, tmeans, tchols, device=dev)
         cfg = samtron_config(per)
         wrapper = GmmWrapper.build_from_config(model, cfg)
         g = GMMVI.build_from_config(cfg, tgt, wrapper)
-        if world > 1:
+        if world > 1 and shard:
             g.enable_sharding(ShardContext(rank, world))
         return g
 
@@ -299,6 +299,44 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
+    # ---- N > 1: the sharded iteration against the single-GPU iteration on the same samples -------------------
+    # (outside every timed region)  The counter-based generator draws a sample from its GLOBAL row index, so a fresh
+    # mixture iterated `parity_iters` times from a fixed seed sees the same samples sharded over `world` ranks as on one
+    # GPU; rank 0 then repeats the run unsharded and compares the resulting mixtures (max-abs / max-abs per tensor).
+    parity = None
+    if world > 1 and not args.no_parity:
+        rng.set_seed(4321)
+        gs = build(PRIOR_SCALE)
+        for _ in range(args.parity_iters):
+            gs.train_iter()
+        sh = [t.detach().clone() for t in (gs.model.means, gs.model.chol_cov, gs.model.log_weights)]
+        same = torch.tensor([1.0], device=dev)
+        for t_ in sh:                       # every rank must hold the same replicated mixture, bit for bit
+            ref_t = t_.clone()
+            dist.broadcast(ref_t, src=0)
+            if not torch.equal(ref_t, t_):
+                same.zero_()
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        del gs
+        sync_all()
+        if rank == 0:
+            rng.set_seed(4321)
+            g1 = build(PRIOR_SCALE, shard=False)
+            for _ in range(args.parity_iters):
+                g1.train_iter()
+            torch.cuda.synchronize()
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+            parity = {"iterations": args.parity_iters, "means": rel(sh[0], g1.model.means),
+                      "chol": rel(sh[1], g1.model.chol_cov),
+                      "weights": rel(torch.exp(sh[2]), g1.model.weights),
+                      "ranks_bit_identical": bool(same.item() == 1.0),
+                      "tolerance": 1e-4,
+                      "note": "sharded vs single-GPU mixture after the same iterations from the same seed (identical "
+                              "samples: counter-based generator keyed on the global row); sums are re-associated "
+                              "across ranks, nothing else differs"}
+            del g1
+        sync_all()
+
     # ---- dominant kernel: component log-density, timed alone with CUDA events -------------------------
     linv, prec, cst = gmmvi.model.prepared()
     X = gmmvi.sample_db.samples.contiguous()
@@ -382,6 +420,8 @@ def run_ours(args):
                         "overlapping the neighbouring steps' kernels, all inside the timed region"},
         "gpu_launches": launches, "clocks": clk,
     }
+    if parity is not None:
+        line["parity_vs_1gpu"] = parity
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["iters_per_sec"], "unit": "iterations/s", "cores": os.cpu_count(),
                                 "kind": "port", "sample": cpu["sample"], "pairs_per_sec": cpu["pairs_per_sec"],
@@ -429,6 +469,8 @@ def main():
     ap.add_argument("--cpu-sample-per-comp", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-single-GPU check at N > 1")
+    ap.add_argument("--parity-iters", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

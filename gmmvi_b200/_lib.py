@@ -56,9 +56,13 @@ _SIGNATURES = {
                                                 C.c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "gvi_gauss_kernel_sum_partials": (C.c_size_t, [C.c_int, C.c_int]),
     "gvi_gauss_kernel_sum_f32": (C.c_int, [c_f, C.c_int, c_f, C.c_int, C.c_int, c_f, c_vp, c_vp]),
+    "gvi_planar_robot_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_float, c_f, c_f, c_vp]),
     "gvi_tridiag_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_vp]),
     "gvi_update_full_f32": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float,
                                       c_f, c_f, c_i, c_f, c_f, c_i, c_vp, C.c_size_t, c_vp]),
+    "gvi_update_full_general_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_update_full_general_f32": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_i,
+                                              c_vp, C.c_size_t, c_vp]),
     "gvi_update_diag_f32": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float,
                                       c_f, c_f, c_i, c_f, c_f, c_vp]),
     "gvi_weight_update_f32": (C.c_int, [C.c_int, c_f, c_f, C.c_int, c_f, C.c_float, c_f, c_f, c_vp]),

@@ -476,11 +476,11 @@ importance_weights_kernel(const float* __restrict__ lq, const float* __restrict_
   if (ess && threadIdx.x == 0) ess[k] = 1.f / sq;
   if (W == nullptr && dot == nullptr && active == nullptr) return;
   const float inv_s2 = 1.f / s2;
-  const float logN = logf((float)N);
+  const float logN = self_normalized == 2 ? 0.f : logf((float)N);     // mode 2: plain exp(lw) (MORE, ng_estimator.py:356)
   float d = 0.f;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     const float lw = row[n] - bg[n];
-    const float w = self_normalized ? expf(lw - lse) * inv_s2 : expf(lw - logN);
+    const float w = self_normalized == 1 ? expf(lw - lse) * inv_s2 : expf(lw - logN);
     if (W) W[(long long)k * N + n] = w;
     if (rho) d = fmaf(w, rho[n], d);
     if (active && (lw - m) > -60.f) active[(long long)k * nblk + (n >> 7)] = 1;
@@ -512,7 +512,8 @@ importance_weights_cached_kernel(const float* __restrict__ lq, const float* __re
   const int nblk = ceil_div(N, 128);
   const float4* __restrict__ bg4 = reinterpret_cast<const float4*>(bg);
   const float4* __restrict__ rho4 = reinterpret_cast<const float4*>(rho);
-  const float logN = logf((float)N);
+  const float logN = self_normalized == 2 ? 0.f : logf((float)N);      // mode 2: plain exp(lw) (MORE)
+  const bool sn = self_normalized == 1;
   for (int k = blockIdx.x; k < K; k += gridDim.x) {
     const float4* __restrict__ row4 = reinterpret_cast<const float4*>(lq + (long long)k * N);
     float4 r[IWC_REG4];
@@ -565,10 +566,10 @@ importance_weights_cached_kernel(const float* __restrict__ lq, const float* __re
     float4* __restrict__ W4 = W ? reinterpret_cast<float4*>(W + (long long)k * N) : nullptr;
     auto fin = [&](const float4 v, int i) {
       float4 w;
-      w.x = self_normalized ? expf(v.x - lse) * inv_s2 : expf(v.x - logN);
-      w.y = self_normalized ? expf(v.y - lse) * inv_s2 : expf(v.y - logN);
-      w.z = self_normalized ? expf(v.z - lse) * inv_s2 : expf(v.z - logN);
-      w.w = self_normalized ? expf(v.w - lse) * inv_s2 : expf(v.w - logN);
+      w.x = sn ? expf(v.x - lse) * inv_s2 : expf(v.x - logN);
+      w.y = sn ? expf(v.y - lse) * inv_s2 : expf(v.y - logN);
+      w.z = sn ? expf(v.z - lse) * inv_s2 : expf(v.z - logN);
+      w.w = sn ? expf(v.w - lse) * inv_s2 : expf(v.w - logN);
       if (W4) __stcs(W4 + i, w);
       if (rho) {
         const float4 q = __ldg(rho4 + i);
@@ -966,18 +967,19 @@ extern "C" int gvi_importance_weights_f32(const float* lq, const float* bg, cons
   const bool aligned = (reinterpret_cast<uintptr_t>(lq) | reinterpret_cast<uintptr_t>(bg) | reinterpret_cast<uintptr_t>(rho) |
                         reinterpret_cast<uintptr_t>(W)) % 16 == 0;
   if (rel_map == nullptr && N % 4 == 0 && N >= 4096 && N <= IWC_MAX_N && aligned) {
-    static int num_sms = 0;
+    static int sms_of_device[64] = {0};             // per device ordinal: SM count, and the smem attribute is set
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int num_sms = (dev >= 0 && dev < 64) ? sms_of_device[dev] : 0;
     if (num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
       cudaError_t e = cudaFuncSetAttribute(importance_weights_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            IWC_SMEM4 * 16);
       if (e != cudaSuccess) {
         set_last_error("gvi_importance_weights_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        num_sms = 0;
         return GVI_ERR_CUDA;
       }
+      if (dev >= 0 && dev < 64) sms_of_device[dev] = num_sms;
     }
     importance_weights_cached_kernel<<<min(K, num_sms), IWC_THREADS, IWC_SMEM4 * 16, st>>>(lq, bg, K, N, self_normalized,
                                                                                            rho, W, dot, ess, active);

@@ -1,6 +1,9 @@
 """Planar-robot target (mirror of experiments/target_distributions/planar_robot.py:13-138): D = num_links joint
-angles, zero-mean Gaussian prior, max over goal Gaussians on the end-effector position.  Gradient by autograd,
-as in the reference (use_log_density_and_grad=False)."""
+angles, zero-mean Gaussian prior, max over goal Gaussians on the end-effector position.  The reference differentiates
+`log_density` with a GradientTape (use_log_density_and_grad=False, sample_selector.py:73-77); here density and gradient
+come from one fused kernel (`gvi_planar_robot_f32`, analytic gradient through the arg-max goal), so the target reports
+use_log_density_and_grad=True.  `likelihood` / `forward_kinematics` keep the reference's signatures (torch ops; they are
+only used by the metrics)."""
 from __future__ import annotations
 
 from math import log, pi
@@ -8,12 +11,13 @@ from math import log, pi
 import numpy as np
 import torch
 
+from ... import ops
 from .lnpdf import LNPDF
 
 
 class PlanarRobot(LNPDF):
     def __init__(self, num_links, num_goals, prior_std=2e-1, likelihood_std=1e-2, device="cuda"):
-        super().__init__(use_log_density_and_grad=False)
+        super().__init__(use_log_density_and_grad=True)
         self._num_dimensions = num_links
         prior_stds = prior_std * np.ones(num_links)
         prior_stds[0] = 1.0
@@ -45,10 +49,11 @@ class PlanarRobot(LNPDF):
         return torch.stack((x, y), dim=1)
 
     def log_density(self, theta):
-        D = self._num_dimensions
-        prior = -0.5 * torch.sum((theta / self.prior_stds) ** 2, dim=1) - torch.sum(torch.log(self.prior_stds)) \
-            - 0.5 * D * log(2 * pi)
-        return prior + self.likelihood(self.forward_kinematics(theta))
+        """planar_robot.py:65-66."""
+        return ops.planar_robot(theta.to(torch.float32), self.prior_stds, self.goals, self.likelihood_std, False)[0]
+
+    def log_density_and_grad(self, theta):
+        return ops.planar_robot(theta.to(torch.float32), self.prior_stds, self.goals, self.likelihood_std, True)
 
 
 def make_single_goal(device="cuda"):

@@ -27,7 +27,6 @@ class GMM:
         self._version = 0
         self.shard = None              # gmmvi_b200.distributed.ShardContext when samples are sharded over GPUs
         self._prepared = None          # (version, linv, prec, cst) for full covariances
-        self._prec_work = None         # in-flight all-gather of prec (sharded runs)
         self._chol_work = None         # in-flight all-gather of chol_cov (sharded component update)
         self._local_chol = None        # (version, a, b, chol[a:b]) of the most recent sharded update
         self.log_weights = log_weights
@@ -73,35 +72,41 @@ class GMM:
     def device(self):
         return self._means.device
 
+    def local_chol(self, a: int, b: int) -> torch.Tensor:
+        """Cholesky factors of the components [a, b) WITHOUT waiting for an in-flight all-gather when they are the rows
+        this rank computed itself in the most recent sharded update."""
+        lc = self._local_chol
+        if lc is not None and lc[0] == self._version and (lc[1], lc[2]) == (a, b):
+            return lc[3]
+        return self.chol_cov[a:b].contiguous()
+
+    @property
+    def chol_cov_handle(self) -> torch.Tensor:
+        """The factor tensor for STORAGE only (sample database): does not wait for an in-flight all-gather; a reader
+        must go through `chol_cov`."""
+        return self._chol_cov
+
     def prepared(self, need_prec: bool = True):
         """(linv, prec, cst): inverse Cholesky factors, precisions and log-normalisers of the current
         full-covariance components (one `gvi_prepare_full_f32` per parameter change).  In sharded runs every rank
-        prepares its own components and the results are all-gathered; the gather of `prec` is asynchronous and only
-        waited for when a caller asks for it (`need_prec`)."""
+        inverts the factors of its own components and ONE all-gather distributes `linv` (+ the [K] normalisers); the
+        precisions are formed locally from the gathered `linv` (a tensor-core batched GEMM, cheaper than moving another
+        K D^2 floats) the first time a caller asks for them (`need_prec`)."""
         if self._prepared is None or self._prepared[0] != self._version:
             rng_ = self.shard.component_range(self.num_components) if self.shard is not None else None
-            if self._prec_work is not None:
-                self._prec_work.wait()
-                self._prec_work = None
             if rng_ is None:
                 linv, prec, cst, _ = ops.prepare_full(self.chol_cov, want_prec=True)
-            else:       # components sharded over the ranks, derived operands all-gathered
+            else:       # components sharded over the ranks
                 a, b = rng_
                 K = self.num_components
-                lc = self._local_chol
-                if lc is not None and lc[0] == self._version and (lc[1], lc[2]) == (a, b):
-                    mine = lc[3]
-                else:
-                    mine = self.chol_cov[a:b].contiguous()
-                l_loc, p_loc, c_loc = ops.prepare_full(mine, want_prec=True)[:3]
+                l_loc, _, c_loc = ops.prepare_full(self.local_chol(a, b), want_prec=False)[:3]
                 linv = self.shard.all_gather_rows(l_loc, K)
                 cst = self.shard.all_gather_rows(c_loc, K)
-                prec, self._prec_work = self.shard.all_gather_rows_async(p_loc, K)
-                self._prec_keep = p_loc
+                prec = None
             self._prepared = (self._version, linv, prec, cst)
-        if need_prec and self._prec_work is not None:
-            self._prec_work.wait()
-            self._prec_work = None
+        if need_prec and self._prepared[2] is None:
+            v, linv, _, cst = self._prepared
+            self._prepared = (v, linv, ops.bgemm(linv, linv, transA=True), cst)       # P = L^-T L^-1
         return self._prepared[1:]
 
     # ---- abstract per-family pieces ---------------------------------------------------------------
@@ -114,7 +119,7 @@ class GMM:
             noise = ops.fill_normal(n, D, rng.seed(), rng.next_subsequence(), 0, self.device)
         offsets = torch.tensor([0, n], device=self.device, dtype=torch.int32)
         X, _ = ops.sample_components(self.diagonal_covs, noise, offsets, self._means[index:index + 1].contiguous(),
-                                     self._chol_cov[index:index + 1].contiguous(), n)
+                                     self.chol_cov[index:index + 1].contiguous(), n)
         return X
 
     def component_log_density(self, index: int, samples: torch.Tensor) -> torch.Tensor:
@@ -185,7 +190,8 @@ class GMM:
     def component_entropies(self) -> torch.Tensor:
         """models/gmm.py:249-260."""
         D = self.num_dimensions
-        diag = self._chol_cov if self.diagonal_covs else torch.diagonal(self._chol_cov, dim1=1, dim2=2)
+        chol = self.chol_cov          # the property waits for an in-flight all-gather of the sharded update
+        diag = chol if self.diagonal_covs else torch.diagonal(chol, dim1=1, dim2=2)
         return 0.5 * D * (torch.log(torch.tensor(2 * pi)).item() + 1) + torch.sum(torch.log(diag), dim=1)
 
     def get_average_entropy(self) -> torch.Tensor:
@@ -218,10 +224,11 @@ class GMM:
 
     def sample_from_components_no_shuffle(self, samples_per_component, noise: Optional[torch.Tensor] = None,
                                           total: Optional[int] = None, max_per_component: Optional[int] = None,
-                                          row_offset: int = 0):
+                                          row_offset: int = 0, component_range=None):
         """models/gmm.py:361-386 -> (samples[N,D] in component order, mapping[N] int32).
         `total` / `max_per_component` let a caller that already knows them avoid the host sync;
-        `noise` injects the standard-normal draws ([N,D])."""
+        `noise` injects the standard-normal draws ([N,D]); `component_range` = (a, b) promises that only the components
+        [a, b) have a non-zero count (sharded runs)."""
         n, offsets = self._offsets(samples_per_component)
         if total is None or max_per_component is None:
             total, max_per_component = int(offsets[-1].item()), int(n.max().item()) if n.numel() else 0
@@ -230,7 +237,14 @@ class GMM:
             noise = ops.fill_normal(total, D, rng.seed(), rng.next_subsequence(), row_offset, self.device)
         if total == 0:
             return torch.zeros((0, D), device=self.device), torch.zeros(0, device=self.device, dtype=torch.int32)
-        return ops.sample_components(self.diagonal_covs, noise, offsets, self._means, self._chol_cov,
+        if component_range is not None:
+            # sharded iteration whose rows all belong to the components [a, b) this rank updated itself: their factors
+            # are at hand, the all-gather of the other ranks' factors need not have finished
+            a, b = component_range
+            X, mapping = ops.sample_components(self.diagonal_covs, noise, (offsets[a:b + 1] - offsets[a]).contiguous(),
+                                               self._means[a:b].contiguous(), self.local_chol(a, b), max_per_component)
+            return X, mapping + a
+        return ops.sample_components(self.diagonal_covs, noise, offsets, self._means, self.chol_cov,
                                      max_per_component)
 
     def sample_from_components(self, samples_per_component) -> torch.Tensor:
@@ -245,7 +259,7 @@ class GMM:
         sel = torch.tensor(keep, device=self.device, dtype=torch.long)
         self.replace_weights(self.log_weights[sel])
         self.means = self._means[sel].contiguous()
-        self.chol_cov = self._chol_cov[sel].contiguous()
+        self.chol_cov = self.chol_cov[sel].contiguous()
 
     def replace_components(self, new_means, new_chols):
         """models/gmm.py:401-418."""

@@ -265,7 +265,9 @@ def mixture_grad_diag(X, means, stds, lq, logw, logq):
 
 def importance_weights(lq, bg, rel_map=None, self_normalized=True, rho=None, want_W=False, want_dot=False,
                        want_ess=False, want_active=False):
-    """Returns dict with the requested of W[K,N], dot[K], ess[K], active[K, ceil(N/128)] (uint8)."""
+    """Returns dict with the requested of W[K,N], dot[K], ess[K], active[K, ceil(N/128)] (uint8).
+    self_normalized: True / 1 = softmax over the samples, normalised twice like the reference; False / 0 = the Stein
+    convention exp(lw) / N (ng_estimator.py:155); 2 = plain exp(lw), what MORE hands to its regression (:356)."""
     lq = _chk(lq, "lq")
     K, N = lq.shape
     bg = _chk(bg, "bg") if bg is not None else None
@@ -276,7 +278,7 @@ def importance_weights(lq, bg, rel_map=None, self_normalized=True, rho=None, wan
     dot = torch.empty(K, device=dev, dtype=torch.float32) if want_dot else None
     ess = torch.empty(K, device=dev, dtype=torch.float32) if want_ess else None
     active = torch.empty((K, (N + 127) // 128), device=dev, dtype=torch.uint8) if want_active else None
-    _call("gvi_importance_weights_f32", lq.data_ptr(), _ptr(bg), _ptr(rel_map), K, N, int(bool(self_normalized)),
+    _call("gvi_importance_weights_f32", lq.data_ptr(), _ptr(bg), _ptr(rel_map), K, N, int(self_normalized),
           _ptr(rho), _ptr(W), _ptr(dot), _ptr(ess), _ptr(active), _stream())
     return dict(W=W, dot=dot, ess=ess, active=active)
 
@@ -463,6 +465,24 @@ def update_components(mode: str, diagonal: bool, means, chols, Hneg, gneg, steps
     return om, oc, succ, etas, kls
 
 
+def update_components_general(mode: str, means, chols, prec, Hneg, gneg, stepsizes, num_updates=None):
+    """Direct / iBLR update for a non-symmetric -E[H] (gvi_update_full_general_f32) -> (new_means, new_chols, success)."""
+    m = UPDATE_MODES[mode]
+    means, chols, prec, Hneg, gneg = (_chk(means, "means"), _chk(chols, "chols"), _chk(prec, "prec"), _chk(Hneg, "Hneg"),
+                                      _chk(gneg, "gneg"))
+    stepsizes = _chk(stepsizes, "stepsizes")
+    num_updates = _chk(num_updates, "num_updates") if num_updates is not None else None
+    K, D = means.shape
+    om, oc = torch.empty_like(means), torch.empty_like(chols)
+    succ = torch.empty(K, device=means.device, dtype=torch.int32)
+    nbytes = _lib.lib().gvi_update_full_general_workspace(K, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=means.device, dtype=torch.float32)
+    _call("gvi_update_full_general_f32", m, means.data_ptr(), chols.data_ptr(), prec.data_ptr(), Hneg.data_ptr(),
+          gneg.data_ptr(), stepsizes.data_ptr(), _ptr(num_updates), K, D, om.data_ptr(), oc.data_ptr(), succ.data_ptr(),
+          ws.data_ptr(), nbytes, _stream(), kernels=4 if m == 2 else 1)
+    return om, oc, succ
+
+
 def gauss_kernel_sum(X, Y, w):
     """sum_{i,j} exp(-sum_d w[d] (X[i,d] - Y[j,d])^2) -> 0-d float32 tensor (MMD evaluation, mmd.py:38-56)."""
     X, Y, w = _chk(X, "X"), _chk(Y, "Y"), _chk(w, "w")
@@ -472,6 +492,17 @@ def gauss_kernel_sum(X, Y, w):
     partial = torch.zeros(max(npart, 1), device=X.device, dtype=torch.float64)
     _call("gvi_gauss_kernel_sum_f32", X.data_ptr(), n1, Y.data_ptr(), n2, D, w.data_ptr(), partial.data_ptr(), _stream())
     return partial.sum().to(torch.float32)
+
+
+def planar_robot(theta, prior_stds, goals, likelihood_std: float, want_grad: bool = True):
+    """PlanarRobot.log_density (planar_robot.py:49-66) and its gradient -> (lnpdf[N], grad[N,D] | None)."""
+    theta, prior_stds, goals = _chk(theta, "theta"), _chk(prior_stds, "prior_stds"), _chk(goals, "goals")
+    N, D = theta.shape
+    lnpdf = torch.empty(N, device=theta.device, dtype=torch.float32)
+    grad = torch.empty_like(theta) if want_grad else None
+    _call("gvi_planar_robot_f32", theta.data_ptr(), N, D, prior_stds.data_ptr(), None, goals.data_ptr(), goals.shape[0],
+          float(likelihood_std), lnpdf.data_ptr(), _ptr(grad), _stream())
+    return lnpdf, grad
 
 
 def tridiag(B, h):

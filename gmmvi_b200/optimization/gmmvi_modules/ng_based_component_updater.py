@@ -35,7 +35,18 @@ class NgBasedComponentUpdater:
                                       "(ng_based_component_updater.py:106 inverts a rank-1 tensor)")
         shard = m.shard
         rng_ = shard.component_range(m.num_components) if shard is not None else None
-        if rng_ is None:
+        general = (self._mode != "trust-region" and not m.diagonal_covs
+                   and getattr(expected_hessians_neg, "gvi_nonsymmetric", False))
+        if general:
+            # non-symmetric -E[H] (Stein with standard importance weights, ng_estimator.py:168): the reference's general
+            # inverse + Cholesky of its lower triangle, restated literally (every rank updates all components)
+            _, prec, _ = m.prepared()
+            means, chols, succ = ops.update_components_general(
+                self._mode, m.means, m.chol_cov, prec, expected_hessians_neg, expected_gradients_neg, stepsizes,
+                m.num_received_updates)
+            etas = kls = None
+            rng_ = None
+        elif rng_ is None:
             means, chols, succ, etas, kls = ops.update_components(
                 self._mode, m.diagonal_covs, m.means, m.chol_cov, expected_hessians_neg, expected_gradients_neg,
                 stepsizes, m.last_log_etas, m.num_received_updates, self.temperature)
@@ -45,7 +56,7 @@ class NgBasedComponentUpdater:
             K = m.num_components
             sl = lambda t: t[a:b].contiguous()
             parts = ops.update_components(
-                self._mode, m.diagonal_covs, sl(m.means), sl(m.chol_cov), sl(expected_hessians_neg),
+                self._mode, m.diagonal_covs, sl(m.means), m.local_chol(a, b), sl(expected_hessians_neg),
                 sl(expected_gradients_neg), sl(stepsizes), sl(m.last_log_etas), sl(m.num_received_updates),
                 self.temperature)
             means, succ, etas, kls = (shard.all_gather_rows(parts[i], K) for i in (0, 2, 3, 4))

@@ -34,8 +34,10 @@ class NgEstimator:
         """ng_estimator.py:244,343 (quirk 3)."""
         return (mapping - torch.max(mapping) + self._model.num_components - 1).to(torch.int32).contiguous()
 
-    def _importance_weights(self, lq, mapping, background_densities, **want):
-        """ng_estimator.py:107-120 + :173-176 / :155: W[K,N] per component, all on device."""
+    def _importance_weights(self, lq, mapping, background_densities, unnormalized_mean=True, **want):
+        """ng_estimator.py:107-120 + :173-176 / :155: W[K,N] per component, all on device.  Without self-normalisation
+        the Stein estimator averages exp(lw) over the samples (weights exp(lw) / N, :147-155) while MORE hands the plain
+        exp(lw) to its ridge regression (:352-356, `unnormalized_mean=False`): the ridge term is not scale free."""
         shard = self._model.shard
         if shard is not None:
             if self._only_use_own_samples:
@@ -46,7 +48,8 @@ class NgEstimator:
                                                   self._use_self_normalized_importance_weights, n_total=n_total, **want)
         if self._only_use_own_samples:
             return ops.importance_weights(lq, None, self._relative_mapping(mapping), True, **want)
-        return ops.importance_weights(lq, background_densities, None, self._use_self_normalized_importance_weights, **want)
+        mode = 1 if self._use_self_normalized_importance_weights else (0 if unnormalized_mean else 2)
+        return ops.importance_weights(lq, background_densities, None, mode, **want)
 
 
 class SteinNgEstimator(NgEstimator):
@@ -68,6 +71,9 @@ class SteinNgEstimator(NgEstimator):
             _, prec, _ = model.prepared()
             symmetrize = self._use_self_normalized_importance_weights       # quirk 7
             H, g = ops.stein_full(samples, model.means, prec, iw["W"], iw["active"], G, symmetrize)
+            # the standard-IW estimate is not symmetric: the direct / iBLR updaters must treat it like the reference's
+            # LU-based tf.linalg.inv / solve does (ng_based_component_updater.py:116-117, 199)
+            H.gvi_nonsymmetric = not symmetrize
         if model.shard is not None:     # partial sums over this rank's samples -> sums over the whole iteration
             rng_ = model.shard.component_range(model.num_components)
             if rng_ is not None and model.shard.world > 1:
@@ -99,7 +105,7 @@ class MoreNgEstimator(NgEstimator):
         samples = samples.contiguous()
         model_densities, lq = model.log_densities_also_individual(samples)
         log_ratios = (target_lnpdfs - model_densities).contiguous()
-        iw = self._importance_weights(lq, mapping, background_densities, want_W=True)
+        iw = self._importance_weights(lq, mapping, background_densities, unnormalized_mean=False, want_W=True)
         if model.diagonal_covs:
             raise NotImplementedError("MORE does not support diagonal covariances (least_squares.py:172 inverts the "
                                       "Cholesky factor as a matrix)")

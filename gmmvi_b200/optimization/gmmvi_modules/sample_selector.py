@@ -62,6 +62,7 @@ class VipsSampleSelector(SampleSelector):
         K = self.model.num_components
         shard = self.model.shard
         row_offset = 0
+        own = None
         if shard is not None:
             # sample-sharded iteration (no reuse): this rank draws only its contiguous range of the global rows
             if samples.shape[0] != 0:
@@ -70,6 +71,9 @@ class VipsSampleSelector(SampleSelector):
             local, row_offset = shard.local_counts([per] * K)
             n_add = torch.tensor(local, device=self.model.device, dtype=torch.int32)
             total, mx = sum(local), max(local)
+            rng_ = shard.component_range(K)
+            if rng_ is not None and all(c == 0 for i, c in enumerate(local) if not rng_[0] <= i < rng_[1]):
+                own = rng_           # every row of this rank belongs to a component it updates itself
             self.sample_db.count_override = torch.full((K,), float(per), device=self.model.device)
         elif samples.shape[0] == 0:
             n_add = torch.full((K,), max(1, int(num_desired_samples)), device=self.model.device, dtype=torch.int32)
@@ -80,7 +84,8 @@ class VipsSampleSelector(SampleSelector):
             n_add = torch.clamp(num_desired_samples - n_eff, min=1).to(torch.int32)
             total, mx = None, None
         new_samples, mapping = self.model.sample_from_components_no_shuffle(n_add, noise=noise, total=total,
-                                                                            max_per_component=mx, row_offset=row_offset)
+                                                                            max_per_component=mx, row_offset=row_offset,
+                                                                            **({} if own is None else {"component_range": own}))
         new_target_grads, new_target_lnpdfs = self.get_target_grads(new_samples)
         return new_samples, new_target_lnpdfs, new_target_grads, mapping
 
@@ -91,7 +96,8 @@ class VipsSampleSelector(SampleSelector):
         num_reused_samples = samples.shape[0]
         new_samples, new_target_lnpdfs, new_target_grads, mapping = self.sample_where_needed(samples, oldsamples_pdf,
                                                                                              noise=noise)
-        self.sample_db.add_samples(new_samples, self.model.means, self.model.chol_cov, new_target_lnpdfs,
+        chols = self.model.chol_cov if self.model.shard is None else self.model.chol_cov_handle    # stored, not read
+        self.sample_db.add_samples(new_samples, self.model.means, chols, new_target_lnpdfs,
                                    new_target_grads, mapping, prepared=self._prepared())
         num_new_samples = new_samples.shape[0]
         oldsamples_pdf, samples, mapping, target_lnpdfs, target_grads = self.sample_db.get_newest_samples(

@@ -221,6 +221,26 @@ size_t gvi_gauss_kernel_sum_partials(int n1, int n2);
 int gvi_gauss_kernel_sum_f32(const float* X, int n1, const float* Y, int n2, int D, const float* w, double* partial,
                              void* stream);
 
+/* ---- direct / iBLR update for a NON-SYMMETRIC -E[H] (ng_based_component_updater.py:97-141, 160-223) ----------------------
+ * The Stein estimator does not symmetrise its Hessian estimate with standard importance weights (ng_estimator.py:168 vs
+ * :186); the reference then inverts the general matrix P' = P + s R (iBLR: + s^2/2 R Sigma R) with an LU factorisation
+ * (tf.linalg.inv / tf.linalg.solve, :116-117, :199) and factors the LOWER triangle of the inverse (tf.linalg.cholesky, :118,
+ * :200).  Restated literally: Gauss-Jordan with partial pivoting + Cholesky per component.  mode 1 = direct, 2 = iBLR;
+ * prec[K,D,D] = old precisions; success[k] = 0 keeps the old parameters (singular P' or non-positive pivot). */
+size_t gvi_update_full_general_workspace(int K, int D);
+int gvi_update_full_general_f32(int mode, const float* means, const float* chols, const float* prec, const float* Hneg,
+                                const float* gneg, const float* stepsizes, const float* num_updates, int K, int D,
+                                float* out_means, float* out_chols, int32_t* success, void* ws, size_t ws_bytes,
+                                void* stream);
+
+/* ---- planar-robot target (experiments/target_distributions/planar_robot.py:29-66; BASELINE config C2) ----------------
+ * theta[N,D] joint angles (D = number of links <= 64) -> lnpdf[n] = N(theta_n; 0, diag(prior_stds^2)) + max over the G <= 8
+ * goals[G,2] of N(forward_kinematics(theta_n); goal, likelihood_std^2 I)  (:49-53, :57-66), and, when grad != NULL,
+ * grad[N,D] = its gradient through the arg-max goal (replaces the tf.GradientTape of sample_selector.py:73-77).
+ * link_lengths[D] may be NULL (all ones, :35). */
+int gvi_planar_robot_f32(const float* theta, int N, int D, const float* prior_stds, const float* link_lengths,
+                         const float* goals, int G, float likelihood_std, float* lnpdf, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

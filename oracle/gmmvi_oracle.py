@@ -892,6 +892,96 @@ def gmm_target(weights, means, covs, dt=np.float32):
     return f
 
 
+def student_t_mixture_target(weights, means, covs, alpha=2, dt=np.float64):
+    """StudentTMixture_LNPDF (experiments/target_distributions/student_t_mixture.py:34-68): MixtureSameFamily of
+    MultivariateStudentTLinearOperator(df=alpha, loc=means, scale=chol(covs)),
+        log t_j(x) = lgamma((nu+D)/2) - lgamma(nu/2) - D/2 log(nu pi) - sum_i log L_j[i,i] - (nu+D)/2 log1p(m_j(x)/nu),
+        m_j(x) = |L_j^-1 (x - mu_j)|^2,   log p(x) = LSE_j(log w_j + log t_j(x)).
+    The reference differentiates with a GradientTape (use_log_density_and_grad=False, sample_selector.py:73-77); the
+    analytic gradient is  -sum_j r_j(x) (nu+D)/(nu+m_j) Sigma_j^-1 (x - mu_j).  Returns f(X) -> (lnpdf[N], grad[N, D])."""
+    from math import lgamma
+    w = np.asarray(weights, dt)
+    means = np.asarray(means, dt)
+    chols = np.stack([cholesky_or_nan(np.asarray(c, dt)) for c in np.asarray(covs, dt)])
+    D = means.shape[1]
+    nu = float(alpha)
+    norm = lgamma(0.5 * (nu + D)) - lgamma(0.5 * nu) - 0.5 * D * np.log(nu * np.pi)
+    logdet = np.sum(np.log(np.diagonal(chols, axis1=1, axis2=2)), axis=1)
+    import scipy.linalg as sla
+
+    def f(X):
+        X = np.asarray(X, dt)
+        lt = np.empty((means.shape[0], X.shape[0]), dt)
+        pz = np.empty((means.shape[0],) + X.shape, dt)                  # Sigma_j^-1 (x - mu_j)
+        maha = np.empty_like(lt)
+        for j in range(means.shape[0]):
+            diff = (X - means[j]).T
+            z = sla.solve_triangular(chols[j], diff, lower=True)
+            maha[j] = np.sum(z * z, axis=0)
+            pz[j] = sla.solve_triangular(chols[j], z, lower=True, trans="T").T
+            lt[j] = norm - logdet[j] - 0.5 * (nu + D) * np.log1p(maha[j] / nu)
+        lw = lt + np.log(w)[:, None]
+        lp = logsumexp(lw, axis=0)
+        r = np.exp(lw - lp[None, :]) * (nu + D) / (nu + maha)
+        grad = -np.einsum("jn,jnd->nd", r, pz)
+        return lp.astype(dt), grad.astype(dt)
+    return f
+
+
+def student_t_mixture_marginal_log_density(weights, means, covs, X, dim, alpha=2, dt=np.float64):
+    """StudentTMixture_LNPDF.marginal_log_density (student_t_mixture.py:46-64): mixture of scalar Student-t with
+    loc = means[:, dim], scale = sqrt(covs[:, dim, dim])."""
+    from math import lgamma
+    nu = float(alpha)
+    loc = np.asarray(means, dt)[:, dim]
+    scale = np.sqrt(np.asarray(covs, dt)[:, dim, dim])
+    y = (np.asarray(X, dt)[:, dim][None, :] - loc[:, None]) / scale[:, None]
+    lt = (lgamma(0.5 * (nu + 1)) - lgamma(0.5 * nu) - 0.5 * np.log(nu * np.pi) - np.log(scale)[:, None]
+          - 0.5 * (nu + 1) * np.log1p(y * y / nu))
+    return logsumexp(lt + np.log(np.asarray(weights, dt))[:, None], axis=0)
+
+
+def planar_robot_forward_kinematics(theta, link_lengths=None):
+    """PlanarRobot.forward_kinematics (planar_robot.py:57-63): end effector (x, y) of the chain of joint angles."""
+    theta = np.asarray(theta)
+    ll = np.ones(theta.shape[1], theta.dtype) if link_lengths is None else np.asarray(link_lengths, theta.dtype)
+    cs = np.cumsum(theta, axis=1)
+    return np.stack((np.sum(ll * np.cos(cs), axis=1), np.sum(ll * np.sin(cs), axis=1)), axis=1)
+
+
+def planar_robot_target(num_links, num_goals, prior_std=2e-1, likelihood_std=1e-2, dt=np.float64):
+    """PlanarRobot (planar_robot.py:29-66): log p(theta) = N(theta; 0, diag(prior_stds^2)) + max_g N(fk(theta); goal_g,
+    likelihood_std^2 I), prior_stds = [1, prior_std, ...] (:32-33), goals (7,0) | (+-7,0),(0,+-7) (:37-42), `likelihood`
+    takes the MAX over the goals (:49-53).  The gradient (a GradientTape in the reference) follows the arg-max goal:
+    d/dtheta_i = -theta_i / s_i^2 - [(x-gx) dx/dtheta_i + (y-gy) dy/dtheta_i] / likelihood_std^2 with
+    dx/dtheta_i = -sum_{m>=i} l_m sin(c_m), dy/dtheta_i = sum_{m>=i} l_m cos(c_m).  Returns f(X) -> (lnpdf[N], grad[N, D])."""
+    if num_goals == 1:
+        goals = np.array([[7.0, 0.0]], dt)
+    elif num_goals == 4:
+        goals = np.array([[7.0, 0.0], [-7.0, 0.0], [0.0, 7.0], [0.0, -7.0]], dt)
+    else:
+        raise ValueError
+    stds = (prior_std * np.ones(num_links)).astype(np.float32).astype(dt)      # :34 casts the scales to float32
+    stds[0] = 1.0
+    ls = np.asarray(likelihood_std, np.float32).astype(dt)                     # tfd.MultivariateNormalDiag(scale_diag=[..]) is fp32
+
+    def f(X):
+        X = np.asarray(X, dt)
+        D = X.shape[1]
+        prior = -0.5 * np.sum((X / stds) ** 2, axis=1) - np.sum(np.log(stds)) - 0.5 * D * np.log(2 * np.pi)
+        cs = np.cumsum(X, axis=1)
+        pos = np.stack((np.sum(np.cos(cs), axis=1), np.sum(np.sin(cs), axis=1)), axis=1)
+        d = pos[None, :, :] - goals[:, None, :]                                # [G, N, 2]
+        lik = -0.5 * np.sum((d / ls) ** 2, axis=2) - 2 * np.log(ls) - np.log(2 * np.pi)
+        best = np.argmax(lik, axis=0)
+        dbest = d[best, np.arange(X.shape[0])]                                 # [N, 2]
+        dx = -np.cumsum(np.sin(cs)[:, ::-1], axis=1)[:, ::-1]
+        dy = np.cumsum(np.cos(cs)[:, ::-1], axis=1)[:, ::-1]
+        grad = -X / stds ** 2 - (dbest[:, :1] * dx + dbest[:, 1:] * dy) / ls ** 2
+        return (prior + lik[best, np.arange(X.shape[0])]).astype(dt), grad.astype(dt)
+    return f
+
+
 # --------------------------------------------------------------------------------------
 # A16: one full iteration with a fixed number of components (gmmvi.py:146-174)
 # --------------------------------------------------------------------------------------

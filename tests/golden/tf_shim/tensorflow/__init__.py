@@ -438,6 +438,8 @@ class _Math:
     is_inf = staticmethod(lambda x: _torch.isinf(_t(x)))
     is_finite = staticmethod(lambda x: _torch.isfinite(_t(x)))
     pow = staticmethod(lambda x, y: _torch.pow(_t(x), _t(y) if isinstance(y, _torch.Tensor) else y))
+    sin = staticmethod(lambda x: _torch.sin(_t(x)))
+    cos = staticmethod(lambda x: _torch.cos(_t(x)))
     reduce_logsumexp = staticmethod(reduce_logsumexp)
     reduce_sum = staticmethod(reduce_sum)
     reduce_max = staticmethod(reduce_max)
@@ -490,6 +492,13 @@ class _Linalg:
         return _torch.linalg.solve(m.transpose(-1, -2) if adjoint else m, _t(rhs))
 
 
+class _LinearOperatorLowerTriangular:
+    """tf.linalg.LinearOperatorLowerTriangular: only the lower triangle of `tril` is used."""
+    def __init__(self, tril, **_):
+        self.tril = _torch.tril(_t(tril))
+
+
+_Linalg.LinearOperatorLowerTriangular = _LinearOperatorLowerTriangular
 linalg = _Linalg()
 matmul = _Linalg.matmul
 

@@ -47,3 +47,78 @@ class _Distributions:
 
 
 distributions = _Distributions()
+
+
+# ---- the distributions the reference's TARGETS are written with (student_t_mixture.py:40-44, planar_robot.py:34,46) --------
+# Closed forms as documented by TFP, written with differentiable torch ops so that the reference's GradientTape
+# (sample_selector.py:73-77) works through them.
+class _Categorical:
+    def __init__(self, logits=None, probs=None):
+        logits = _tf._t(logits) if logits is not None else _torch.log(_tf._t(probs))
+        self.logits = logits - _torch.logsumexp(logits, dim=-1, keepdim=True)
+
+
+class _MultivariateNormalDiag:
+    def __init__(self, loc=None, scale_diag=None):
+        if isinstance(scale_diag, (list, tuple)):      # Python floats become float32 constants in TF (planar_robot.py:46)
+            scale_diag = _torch.tensor(scale_diag, dtype=_torch.float32).to(_torch.float64)
+        self.scale_diag = _tf._t(scale_diag)
+        self.loc = _tf._t(loc, self.scale_diag.dtype)
+
+    def log_prob(self, x):
+        x = _tf._t(x, self.loc.dtype)
+        z = (x - self.loc) / self.scale_diag
+        d = self.loc.shape[-1]
+        return (-0.5 * _torch.sum(z * z, dim=-1) - _torch.sum(_torch.log(self.scale_diag), dim=-1)
+                - 0.5 * d * _torch.log(_torch.tensor(2 * _torch.pi, dtype=self.loc.dtype)))
+
+
+class _StudentT:
+    """Scalar Student-t, batch of (df, loc, scale)."""
+    def __init__(self, df, loc, scale):
+        self.loc, self.scale = _tf._t(loc), _tf._t(scale)
+        self.df = _tf._t(float(df), self.loc.dtype)
+
+    def log_prob(self, x):
+        x = _tf._t(x, self.loc.dtype)
+        y = (x - self.loc) / self.scale
+        df = self.df
+        return (_torch.lgamma(0.5 * (df + 1)) - _torch.lgamma(0.5 * df) - 0.5 * _torch.log(df * _torch.pi)
+                - _torch.log(self.scale) - 0.5 * (df + 1) * _torch.log1p(y * y / df))
+
+
+class _MultivariateStudentTLinearOperator:
+    """log p(x) = lgamma((df+d)/2) - lgamma(df/2) - d/2 log(df pi) - log|det scale| - (df+d)/2 log1p(|scale^-1 (x-loc)|^2 / df)."""
+    def __init__(self, df, loc, scale):
+        self.loc = _tf._t(loc)
+        self.scale = scale                       # tf.linalg.LinearOperatorLowerTriangular
+        self.df = _tf._t(float(df), self.loc.dtype)
+
+    def log_prob(self, x):
+        x = _tf._t(x, self.loc.dtype)
+        L = self.scale.tril
+        d = self.loc.shape[-1]
+        diff = (x - self.loc).unsqueeze(-1)                                   # [..., K, d, 1] by broadcasting
+        z = _torch.linalg.solve_triangular(L.expand(diff.shape[:-2] + L.shape[-2:]), diff, upper=False).squeeze(-1)
+        maha = _torch.sum(z * z, dim=-1)
+        logdet = _torch.sum(_torch.log(_torch.abs(_torch.diagonal(L, dim1=-2, dim2=-1))), dim=-1)
+        df = self.df
+        return (_torch.lgamma(0.5 * (df + d)) - _torch.lgamma(0.5 * df) - 0.5 * d * _torch.log(df * _torch.pi) - logdet
+                - 0.5 * (df + d) * _torch.log1p(maha / df))
+
+
+class _MixtureSameFamily:
+    def __init__(self, mixture_distribution, components_distribution):
+        self.mix, self.comp = mixture_distribution, components_distribution
+
+    def log_prob(self, x):
+        x = _tf._t(x, self.mix.logits.dtype)
+        lp = self.comp.log_prob(x.unsqueeze(-1) if isinstance(self.comp, _StudentT) else x.unsqueeze(-2))   # [..., K]
+        return _torch.logsumexp(lp + self.mix.logits, dim=-1)
+
+
+_Distributions.Categorical = _Categorical
+_Distributions.MultivariateNormalDiag = _MultivariateNormalDiag
+_Distributions.StudentT = _StudentT
+_Distributions.MultivariateStudentTLinearOperator = _MultivariateStudentTLinearOperator
+_Distributions.MixtureSameFamily = _MixtureSameFamily

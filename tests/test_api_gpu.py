@@ -1,6 +1,7 @@
 """API-level parity: the module mirror (GMMVI / SampleSelector / NgEstimator / updaters) against the oracle's
 `train_iter` on identical injected noise, plus runner smoke runs of the example configurations."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +16,20 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+# north_star tolerances: log-densities 1e-5, NG estimates and updated means / covariances 1e-4 (relative, fp32)
+TOL_LOGDENS, TOL_NG = 1e-5, 1e-4
+REPORT_ONLY = os.environ.get("GMMVI_B200_PARITY_REPORT", "0") == "1"     # print every measured error, assert nothing
+
+
+def close(label, got, want, tol):
+    """Assert rel_err(got, want) < tol; the measured error is printed (pytest -s) so that the bound can be audited."""
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    err = rel_err(got, want)
+    print(f"PARITY {label}: {err:.3e} (tol {tol:.0e})")
+    if not REPORT_ONLY:
+        assert err < tol, f"{label}: {err:.3e} >= {tol:.0e}"
 
 
 def base_config(updater="trust-region", weight_updater="trust-region", diag=False, desired=40, ratio=0.0,
@@ -96,19 +111,19 @@ def test_iterations_match_oracle(updater, weight_updater, diag):
         Ed = torch.as_tensor(E).cuda()
         samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=Ed)
         assert np.array_equal(mapping.cpu().numpy(), out["mapping"])               # bit exact
-        assert rel_err(samples.cpu().numpy(), out["samples"]) < 1e-5
-        assert rel_err(bg.cpu().numpy(), out["bg"]) < 1e-5
-        assert rel_err(lnpdfs.cpu().numpy(), out["lnpdfs"]) < 1e-5
-        assert rel_err(grads.cpu().numpy(), out["grads"]) < 1e-4
+        close("samples", samples, out["samples"], TOL_LOGDENS)
+        close("bg", bg, out["bg"], TOL_LOGDENS)
+        close("lnpdfs", lnpdfs, out["lnpdfs"], TOL_LOGDENS)
+        close("grads", grads, out["grads"], TOL_NG)
         H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
-        assert rel_err(H.cpu().numpy(), out["H_neg"]) < 2e-4, it
-        assert rel_err(g.cpu().numpy(), out["g_neg"]) < 2e-4, it
+        close("H", H, out["H_neg"], TOL_NG)
+        close("g", g, out["g_neg"], TOL_NG)
         gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
         m = gmmvi.model
         assert np.array_equal(gmmvi.ng_based_updater.last_success.cpu().numpy().astype(bool), out["update"]["success"])
-        assert rel_err(m.means.cpu().numpy(), og.means) < 5e-4, it
-        assert rel_err(m.chol_cov.cpu().numpy(), og.chol_cov) < 5e-4, it
-        assert np.allclose(m.weights.cpu().numpy(), og.weights, rtol=2e-3, atol=1e-6), it
+        close("means", m.means, og.means, TOL_NG)
+        close("chol_cov", m.chol_cov, og.chol_cov, TOL_NG)
+        close("weights", m.weights, og.weights, TOL_NG)
         assert np.allclose(m.l2_regularizers.cpu().numpy(), og.l2_regularizers)
         assert np.allclose(m.num_received_updates.cpu().numpy(), og.num_received_updates)
         if updater == "trust-region":
@@ -136,9 +151,9 @@ def test_sample_reuse_counts_are_exact():
         samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=torch.as_tensor(E).cuda())
         assert samples.shape[0] == out["samples"].shape[0], (it, n_add)
         assert np.array_equal(mapping.cpu().numpy(), out["mapping"])
-        assert rel_err(bg.cpu().numpy(), out["bg"]) < 1e-5
+        close("bg", bg, out["bg"], TOL_LOGDENS)
         gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
-        assert rel_err(gmmvi.model.means.cpu().numpy(), og.means) < 5e-4
+        close("means", gmmvi.model.means, og.means, TOL_NG)
 
 
 @pytest.mark.parametrize("experiment,codeword,overrides", [
@@ -199,29 +214,36 @@ def test_cpu_tensor_is_rejected():
         ops.mixture_lse(torch.zeros(2, 3), torch.zeros(2))
 
 
-def test_more_iteration_matches_oracle():
-    """MORE estimator + trust-region updates through the module API (BASELINE config C3's algorithm, small shape)."""
+@pytest.mark.parametrize("self_normalized,l2", [(True, 1e-8), (False, 1e-8), (False, 1e-6)])
+def test_more_iteration_matches_oracle(self_normalized, l2):
+    """MORE estimator + trust-region updates through the module API (BASELINE config C3's algorithm, small shape).
+    Without self-normalisation the regression gets the plain exp(lw) (ng_estimator.py:352-356): the ridge term is not
+    scale free, so weights exp(lw) / N (the Stein convention) would regularise N times harder -- visible at l2 = 1e-6,
+    the value `l2_regularizers` reaches after failed updates."""
     K, D, desired = 3, 6, 400
     cfg = base_config("trust-region", "trust-region", False, desired, stepsize=0.05)
     cfg["ng_estimator_type"] = "MORE"
-    cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": 1e-8,
-                                  "use_self_normalized_importance_weights": True}
+    cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": l2,
+                                  "use_self_normalized_importance_weights": self_normalized}
+    cfg["ng_based_updater_config"] = {}
     gmmvi, og, otarget = build_pair(K, D, cfg, seed=4)
-    og.initial_regularizer = 1e-8
-    og.l2_regularizers = np.full(K, 1e-8)
+    gmmvi.model.initial_regularizer = l2
+    og.initial_regularizer = l2
+    og.l2_regularizers = np.full(K, l2)
     odb = O.OracleSampleDB(D, False, False, None, np.float64)
-    ocfg = O.IterationConfig(desired_samples_per_component=desired, ng_estimator="MORE", weight_stepsize=0.1)
+    ocfg = O.IterationConfig(desired_samples_per_component=desired, ng_estimator="MORE", weight_stepsize=0.1,
+                             ng_self_normalized=self_normalized)
     rng = np.random.default_rng(123)
     for it in range(2):
         E = rng.standard_normal((K * desired, D)).astype(np.float32)
         out = O.train_iter(og, odb, otarget, ocfg, lambda k, D_, n: E[k * desired:(k + 1) * desired].T.astype(np.float64))
         samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=torch.as_tensor(E).cuda())
         H, g = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
-        assert rel_err(H.cpu().numpy(), out["H_neg"]) < 2e-3
-        assert rel_err(g.cpu().numpy(), out["g_neg"]) < 2e-3
+        close("H", H, out["H_neg"], TOL_NG)
+        close("g", g, out["g_neg"], TOL_NG)
         gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
-        assert rel_err(gmmvi.model.means.cpu().numpy(), og.means) < 2e-3
-        assert rel_err(gmmvi.model.chol_cov.cpu().numpy(), og.chol_cov) < 2e-3
+        close("means", gmmvi.model.means, og.means, TOL_NG)
+        close("chol_cov", gmmvi.model.chol_cov, og.chol_cov, TOL_NG)
 
 
 @pytest.mark.parametrize("route", ["h16", "tf32", "simt"])
@@ -265,7 +287,9 @@ def _more_c3_shape():
     assert err < max(1e-3, 5 * floor), (err, floor)     # 5151-feature regression in fp32
 
 
-@pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "diagonal_stein_trust_region", "stein_iblr_improvement"])
+@pytest.mark.parametrize("case", ["samtron_fixed", "samtron_d96", "diagonal_stein_trust_region", "stein_iblr_improvement",
+                                  "own_samples_decaying_temperature", "single_component", "direct_rejected_steps",
+                                  "stein_standard_iw_direct", "samtron_reuse"])
 def test_first_iteration_matches_reference_sources(case):
     """The device path against outputs of the reference's OWN sources (tests/golden/reference_<case>.npz, produced by
     tests/golden/make_reference_golden.py from /root/reference/src/gmmvi in float64): one full iteration from the
@@ -294,21 +318,21 @@ def test_first_iteration_matches_reference_sources(case):
     samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=noise)
     assert np.array_equal(mapping.cpu().numpy(), g["mapping0"])                     # bit exact
     if "samples0" in g.files:
-        assert rel_err(samples.cpu().numpy(), g["samples0"]) < 1e-5
-        assert rel_err(grads.cpu().numpy(), g["grads0"]) < 2e-4
-    assert rel_err(bg.cpu().numpy(), g["bg0"]) < 1e-5
-    assert rel_err(lnpdfs.cpu().numpy(), g["lnpdfs0"]) < 1e-5
+        close("samples", samples, g["samples0"], TOL_LOGDENS)
+        close("grads", grads, g["grads0"], TOL_NG)
+    close("bg", bg, g["bg0"], TOL_LOGDENS)
+    close("lnpdfs", lnpdfs, g["lnpdfs0"], TOL_LOGDENS)
     H, gn = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
-    assert rel_err(H.cpu().numpy(), g["H0"]) < 4e-4
-    assert rel_err(gn.cpu().numpy(), g["g0"]) < 4e-4
+    close("H", H, g["H0"], TOL_NG)
+    close("gn", gn, g["g0"], TOL_NG)
     gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
     m = gmmvi.model
     chol_ref = np.stack([np.diag(c) for c in g["chol0"]]) if (diagonal and g["chol0"].ndim == 3) else g["chol0"]
-    assert rel_err(m.means.cpu().numpy(), g["means0"]) < 1e-3
-    assert rel_err(m.chol_cov.cpu().numpy(), chol_ref) < 1e-3
-    assert np.allclose(m.log_weights.cpu().numpy(), g["log_weights0"], rtol=4e-3, atol=1e-5)
+    close("means", m.means, g["means0"], TOL_NG)
+    close("chol_cov", m.chol_cov, chol_ref, TOL_NG)
+    close("weights", m.weights, np.exp(g["log_weights0"]), TOL_NG)
     assert np.allclose(m.stepsizes.cpu().numpy(), g["stepsizes0"], rtol=1e-5)
     assert np.allclose(m.l2_regularizers.cpu().numpy(), g["l20"])
     assert np.array_equal(m.num_received_updates.cpu().numpy(), g["num_received_updates0"])
     if cfg["ng_based_updater_type"] == "trust-region":
-        assert np.allclose(m.last_log_etas.cpu().numpy(), g["last_log_etas0"], rtol=1e-3)
+        assert np.allclose(m.last_log_etas.cpu().numpy(), g["last_log_etas0"], rtol=1e-4)

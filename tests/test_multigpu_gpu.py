@@ -55,12 +55,17 @@ def _worker(rank, world, port, K, D, desired, iters, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
-def test_sharded_iteration_matches_single_gpu(tmp_path, world):
+@pytest.mark.parametrize("world,K,D,desired", [(2, 8, 32, 64),        # SIMT kernels, components divide evenly
+                                               (2, 8, 96, 160),       # tensor-core kernels (D >= 96), 640 rows / rank
+                                               (2, 7, 96, 128),       # K not divisible: all-reduce + replicated update
+                                               (4, 8, 128, 128),
+                                               (8, 16, 96, 128)])
+def test_sharded_iteration_matches_single_gpu(tmp_path, world, K, D, desired):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from gmmvi_b200 import rng
-    K, D, desired, iters = 8, 32, 64, 3
+    iters = 3
     rng.set_seed(77)
     ref = _build(K, D, desired, torch.device("cuda", 0))
     for _ in range(iters):
@@ -74,6 +79,7 @@ def test_sharded_iteration_matches_single_gpu(tmp_path, world):
         assert np.array_equal(p["logw"], parts[0]["logw"])
     # ... which agrees with the single-GPU run (same counter-based noise; sums are re-associated across ranks)
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
-    assert rel(parts[0]["means"], ref.model.means.cpu().numpy()) < 2e-4
-    assert rel(parts[0]["chol"], ref.model.chol_cov.cpu().numpy()) < 2e-4
-    assert np.allclose(np.exp(parts[0]["logw"]), ref.model.weights.cpu().numpy(), rtol=2e-3, atol=1e-6)
+    e_m, e_c = rel(parts[0]["means"], ref.model.means.cpu().numpy()), rel(parts[0]["chol"], ref.model.chol_cov.cpu().numpy())
+    e_w = rel(np.exp(parts[0]["logw"]), ref.model.weights.cpu().numpy())
+    print(f"PARITY sharded world={world} K={K} D={D}: means {e_m:.2e} chol {e_c:.2e} weights {e_w:.2e}")
+    assert e_m < 1e-4 and e_c < 1e-4 and e_w < 1e-4

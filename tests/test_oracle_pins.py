@@ -410,3 +410,53 @@ def test_oracle_model_surface_matches_reference_sources(diagonal):
     assert rel(gm.log_weights, g["added_log_weights"]) < 1e-13 and rel(gm.chol_cov, g["added_chol"]) < 1e-13
     O.remove_component(gm, 1)
     assert rel(gm.log_weights, g["removed_log_weights"]) < 1e-13 and rel(gm.means, g["removed_means"]) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# targets
+# ---------------------------------------------------------------------------------------------------------------------
+TARGET_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_targets.npz")
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.mark.parametrize("name", ["stm20", "stm_hard64"])
+def test_student_t_mixture_oracle_matches_reference_class_and_scipy(name):
+    """oracle.student_t_mixture_target against (a) the reference's StudentTMixture_LNPDF run over the tfp stand-in
+    (tests/golden/make_reference_targets.py), (b) scipy.stats.multivariate_t, (c) central finite differences."""
+    from scipy.stats import multivariate_t
+    g = np.load(TARGET_GOLD)
+    ch = g[name + "_chols"]
+    K = ch.shape[0]
+    covs = ch @ ch.transpose(0, 2, 1)
+    w = np.ones(K) / K
+    X = g[name + "_X"]
+    f = O.student_t_mixture_target(w, g[name + "_means"], covs)
+    v, gr = f(X)
+    assert np.max(np.abs(v - g[name + "_lnpdf"])) < 1e-10 and rel(gr, g[name + "_grad"]) < 1e-11
+    lp = np.stack([multivariate_t(loc=g[name + "_means"][j], shape=covs[j], df=2).logpdf(X) for j in range(K)])
+    assert np.max(np.abs(O.logsumexp(lp + np.log(w)[:, None], axis=0) - v)) < 1e-9
+    m = O.student_t_mixture_marginal_log_density(w, g[name + "_means"], covs, X, 3)
+    assert np.max(np.abs(m - g[name + "_marg3"])) < 1e-12
+    x0 = X[100:104]
+    h = 1e-6
+    for d in (0, 5):
+        e = np.zeros(X.shape[1]); e[d] = h
+        fd = (f(x0 + e)[0] - f(x0 - e)[0]) / (2 * h)
+        assert np.allclose(fd, f(x0)[1][:, d], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,links,goals", [("planar10_4", 10, 4), ("planar10_1", 10, 1), ("planar3_4", 3, 4)])
+def test_planar_robot_oracle_matches_reference_class(name, links, goals):
+    g = np.load(TARGET_GOLD)
+    X = g[name + "_X"]
+    f = O.planar_robot_target(links, goals)
+    v, gr = f(X)
+    assert rel(v, g[name + "_lnpdf"]) < 1e-13 and rel(gr, g[name + "_grad"]) < 1e-13
+    assert rel(O.planar_robot_forward_kinematics(X), g[name + "_fk"]) < 1e-14
+    h = 1e-7
+    e = np.zeros(links); e[1] = h
+    fd = (f(X[:8] + e)[0] - f(X[:8] - e)[0]) / (2 * h)
+    assert np.allclose(fd, gr[:8, 1], rtol=1e-4)

@@ -1,25 +1,25 @@
-"""Device modules OUTSIDE the round-1 hot path against the reference-source goldens (tests/golden/reference_*.npz):
+"""Device modules next to the hot path against the reference-source goldens (tests/golden/reference_*.npz):
 LinSampleSelector + MORE (the algorithm of BASELINE config C3) and VipsComponentAdaptation (SAMTRON's adaptive number of
-components).  The goldens and the oracle side are validated on CPU (tests/test_oracle_pins.py); these device tests were
-written after the round's GPU budget was spent, so they are OPT-IN until they have run once on a B200:
-    GMMVI_B200_UNVALIDATED_TESTS=1 python -m pytest tests/test_reference_goldens_next_gpu.py -m gpu
-(validate, fix, remove the guard)."""
-import os
-
+components).  The goldens and the oracle side are validated on CPU (tests/test_oracle_pins.py).  First run on a B200 in
+round 2 (profiles/r02_gated_tests.log); the former opt-in guard is gone."""
 import numpy as np
 import pytest
 import torch
 
 import oracle as O
+from test_api_gpu import TOL_LOGDENS, TOL_NG, close
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GMMVI_B200_UNVALIDATED_TESTS", "0") != "1",
-                                 reason="not yet validated on a GPU; set GMMVI_B200_UNVALIDATED_TESTS=1")]
+pytestmark = pytest.mark.gpu
 
 
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+# MORE solves a ridge regression on D (D + 1) / 2 + D + 1 features in fp32 (the reference too): its error is set by the
+# condition number of the normal equations, not by the kernels; on this 28-feature case it still meets the 1e-4 bound.
+MORE_TOL = TOL_NG          # measured 2.8e-5 (H) on the B200 (profiles/r02_parity_report_first.log)
 
 
 def _device_gmmvi(case, g):
@@ -45,15 +45,15 @@ def test_mixture_based_selection_and_more_match_reference_sources():
     u = torch.as_tensor(np.asarray(g["uniform0"], np.float32)).cuda()
     samples, mapping, bg, lnpdfs, grads = gmmvi.sample_selector.select_samples(noise=noise, uniforms=u)
     assert np.array_equal(mapping.cpu().numpy(), g["mapping0"])
-    assert rel_err(samples.cpu().numpy(), g["samples0"]) < 1e-5
-    assert rel_err(bg.cpu().numpy(), g["bg0"]) < 1e-5
-    assert rel_err(lnpdfs.cpu().numpy(), g["lnpdfs0"]) < 1e-5
+    close("samples", samples, g["samples0"], TOL_LOGDENS)
+    close("bg", bg, g["bg0"], TOL_LOGDENS)
+    close("lnpdfs", lnpdfs, g["lnpdfs0"], TOL_LOGDENS)
     H, gn = gmmvi.ng_estimator.get_expected_hessian_and_grad(samples, mapping, bg, lnpdfs, grads)
-    assert rel_err(H.cpu().numpy(), g["H0"]) < 5e-3
-    assert rel_err(gn.cpu().numpy(), g["g0"]) < 5e-3
+    close("H (MORE)", H, g["H0"], MORE_TOL)
+    close("g (MORE)", gn, g["g0"], MORE_TOL)
     gmmvi._run_updates(samples, mapping, bg, lnpdfs, grads)
-    assert rel_err(gmmvi.model.means.cpu().numpy(), g["means0"]) < 5e-3
-    assert rel_err(gmmvi.model.chol_cov.cpu().numpy(), g["chol0"]) < 5e-3
+    close("means", gmmvi.model.means, g["means0"], MORE_TOL)
+    close("chol_cov", gmmvi.model.chol_cov, g["chol0"], MORE_TOL)
 
 
 @pytest.mark.parametrize("iteration", [1, 11, 13, 15])
@@ -110,13 +110,3 @@ def test_component_adaptation_matches_reference_sources(iteration):
     assert np.allclose(wrapper.stepsizes.cpu().numpy(), after.stepsizes)
     assert np.allclose(wrapper.last_log_etas.cpu().numpy(), after.last_log_etas, rtol=1e-6)
     assert np.array_equal(wrapper.num_received_updates.cpu().numpy(), after.num_received_updates)
-
-
-@pytest.mark.parametrize("case", ["own_samples_decaying_temperature", "single_component", "direct_rejected_steps",
-                                  "stein_standard_iw_direct", "samtron_reuse"])
-def test_first_iteration_of_further_cases(case):
-    """The first-iteration check of tests/test_api_gpu.py on the cases that were added after the GPU budget was spent
-    (own samples / decaying stepsizes / temperature, K = 1, rejected direct steps) or left out there (standard
-    importance weights, reuse)."""
-    from test_api_gpu import test_first_iteration_matches_reference_sources as check
-    check(case)
