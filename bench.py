@@ -30,9 +30,26 @@ sys.path.insert(0, ROOT)
 
 K_COMP, DIM, PER_COMP = 512, 256, 128
 TARGET_COMPONENTS = 10
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-# captures (profiles/r01_ncu_*.txt), keyed by (kernel kind, K, D, samples per launch); other shapes report null
-NCU_DRAM_TRAFFIC = {("h16", 512, 256, 65536): 1.712667e9 + 138.592256e6}
+# `roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed from the newest
+# committed `ncu --set full` summary of that kernel (profiles/r*_ncu_h16t_logdens.txt, written by profiles/ncu_summary.py).
+# The captures are of the C5 shape (K=512, D=256, 65536 samples per launch); other shapes report null.
+NCU_TRAFFIC_SHAPE = ("h16", 512, 256, 65536)
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_dram_traffic():
+    """-> (bytes per launch | None, source file | None) from the newest profiles/r*_ncu_h16t_logdens.txt."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_h16t_logdens.txt")))
+    for path in reversed(files):
+        vals = {}
+        for line in open(path):
+            parts = line.split()
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[1] in _UNIT:
+                vals[parts[0]] = float(parts[2].replace(",", "")) * _UNIT[parts[1]]
+        if len(vals) == 2:
+            return sum(vals.values()), os.path.relpath(path, ROOT)
+    return None, None
 PRIOR_SCALE = 31.63          # configs/experiment_configs/gmm100.yml:11 (GMM-target experiments)
 
 
@@ -358,6 +375,7 @@ def run_ours(args):
     peak_note = (f"{how} bf16 burst {bf16} TFLOP/s (kind::f16 MMAs run at the bf16 rate)" if kind == "h16" else
                  f"{how} bf16 burst {bf16} TFLOP/s / 2 (TF32 dense rate is half the bf16 rate)")
     achieved = flop_alg / (ld_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_dram_traffic() if (kind, K, D, int(X.shape[0])) == NCU_TRAFFIC_SHAPE else (None, None)
     # executed tensor work of the split-precision kernel: 3 MMAs per 16-column step with N = Dp - 16 jb (h16)
     if kind == "h16":
         Dp = (D + 63) // 64 * 64
@@ -404,8 +422,7 @@ def run_ours(args):
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": achieved / tc_peak,
-                     "traffic": NCU_DRAM_TRAFFIC.get((kind, K, D, int(X.shape[0]))),
-                     "traffic_source": "profiles/r01_ncu_h16t_logdens.txt (bytes per launch)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": 4.0 * (X.shape[0] * D + 2 * K * D * D // 2 + K * X.shape[0]),
                      "kernel": ops.logdens_kernel_name(D), "launch_ms": ld_ms,
                      "algorithmic_flop_per_pair": D * D + 4 * D,
@@ -425,7 +442,9 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["iters_per_sec"], "unit": "iterations/s", "cores": os.cpu_count(),
                                 "kind": "port", "sample": cpu["sample"], "pairs_per_sec": cpu["pairs_per_sec"],
-                                "stages_s": cpu["stages_s"]}
+                                "stages_s": cpu["stages_s"], "extrapolated": True,
+                                "extrapolation": f"sample-proportional stages timed on 1/{cpu['stages_s']['n_scale']:g} "
+                                                 "of the samples and scaled linearly"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -450,8 +469,12 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C5 stress on host CPU: K={K}, D={D}, {per * K} samples/iteration",
                    "samples_per_iteration": per * K, "components": K, "dim": D},
+        "extrapolated": True,
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": best["sample"]},
+                         "sample": best["sample"], "extrapolated": True,
+                         "extrapolation": f"sample-proportional stages timed on 1/{best['stages_s']['n_scale']:g} of the "
+                                          "samples and scaled linearly (BASELINE.md section 3): a stated estimate, not "
+                                          "a measurement of the full configuration"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

@@ -45,6 +45,11 @@ _SIGNATURES = {
     "gvi_stein_full_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gvi_stein_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_vp, c_f, C.c_int, C.c_int, c_f, c_f,
                                      c_vp, C.c_size_t, c_vp]),
+    "gvi_stein_stats_full_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gvi_stein_stats_full_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_vp, c_f, C.c_int, c_f, c_f, c_vp, C.c_size_t,
+                                           c_vp]),
+    "gvi_stein_finalize_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_stein_finalize_full_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "gvi_stein_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_vp]),
     "gvi_more_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gvi_more_fit_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_i,
@@ -67,6 +72,8 @@ _SIGNATURES = {
                                       c_f, c_f, c_i, c_f, c_f, c_vp]),
     "gvi_weight_update_f32": (C.c_int, [C.c_int, c_f, c_f, C.c_int, c_f, C.c_float, c_f, c_f, c_vp]),
     "gvi_fill_normal_f32": (C.c_int, [c_f, C.c_longlong, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_longlong, c_vp]),
+    "gvi_fill_normal_dev_f32": (C.c_int, [c_f, C.c_longlong, C.c_int, C.c_ulonglong, c_vp, C.c_ulonglong, C.c_longlong,
+                                          c_vp]),
     "gvi_sample_f32": (C.c_int, [C.c_int, c_f, c_i, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_i, c_vp]),
     "gvi_tc_bgemm_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "gvi_tc_bgemm_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -812,8 +812,12 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 }
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// subseq_dev (nullable): the draw counter lives in device memory (CUDA-graph replays must not bake it into the launch);
+// subseq_add is added to it.
 __global__ void fill_normal_kernel(float* __restrict__ out, long long rows, int D, unsigned long long seed,
-                                   unsigned long long subseq, long long row_offset) {
+                                   unsigned long long subseq, long long row_offset,
+                                   const unsigned long long* __restrict__ subseq_dev) {
+  if (subseq_dev != nullptr) subseq += *subseq_dev;
   const int groups = ceil_div(D, 4);
   const long long total = rows * groups;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -1033,6 +1037,12 @@ static bool stein_tc_enabled() {
   }
   return v == 1;
 }
+namespace gvi {
+bool small_dim_supported(int D);
+size_t stein_small_workspace_floats(int N, int K, int D);
+int launch_stein_small(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
+                       const float* G, int K, float* M, float* gneg, float* ws, cudaStream_t st);
+}  // namespace gvi
 static size_t stein_base_floats(int K, int D) {
   return ((size_t)2 * K * D * D + tc_gemm_workspace_floats(K, D, D, D) + 63) / 64 * 64;
 }
@@ -1040,8 +1050,35 @@ extern "C" size_t gvi_stein_full_workspace(int N, int K, int D) {
   if (K <= 0) return 0;
   size_t f = stein_base_floats(K, D);
   if (N > 0 && stein_tc_supported(N, D)) f += stein_tc_workspace_floats(N, K, D);
+  else if (N > 0 && D <= 32) f += stein_small_workspace_floats(N, K, D);
   return f * sizeof(float);
 }
+// raw statistics: M_k = sum_n w_kn (x_n - mu_k) g_n^T and gneg_k = -sum_n w_kn g_n; `tcws` = scratch of the tensor-core kernel
+static int stein_stats(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
+                       const float* G, int K, float* M, float* gneg, float* tcws, cudaStream_t st) {
+  int rc;
+  if (N > 0 && small_dim_supported(D))      // D <= 32: statistics and gradient sums in one pass (small_dim.cu)
+    return launch_stein_small(X, N, D, means, W, active, G, K, M, gneg, tcws, st);
+  if (N > 0 && stein_tc_supported(N, D) && stein_tc_enabled())
+    rc = launch_stein_stats_tc(X, N, D, means, W, active, G, K, M, tcws, st);
+  else
+    rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
+  if (rc) return rc;
+  dim3 gg(ceil_div(D, 256), K);
+  stein_gsum_kernel<<<gg, 256, 0, st>>>(W, active, G, N, D, gneg);
+  return check_launch("stein_gsum_kernel");
+}
+// Hneg_k = -(P_k M_k) (symmetrised when asked); T: K D^2 floats followed by the batched-GEMM scratch
+static int stein_finalize(const float* prec, const float* M, int K, int D, int symmetrize, float* Hneg, float* T,
+                          cudaStream_t st) {
+  int rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, prec, D, (long long)D * D, M, D, (long long)D * D, T, D,
+                            (long long)D * D, T + (size_t)K * D * D, tc_gemm_workspace_floats(K, D, D, D), st);
+  if (rc) return rc;
+  dim3 grid(min(ceil_div(D * D, 256), 1024), K);
+  stein_finalize_kernel<<<grid, 256, 0, st>>>(T, D, symmetrize, Hneg);
+  return check_launch("stein_finalize_kernel");
+}
+
 extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec,
                                   const float* W, const uint8_t* active, const float* G, int K, int symmetrize,
                                   float* Hneg, float* gneg, void* ws, size_t ws_bytes, void* stream) {
@@ -1056,24 +1093,47 @@ extern "C" int gvi_stein_full_f32(const float* X, int N, int D, const float* mea
   cudaStream_t st = (cudaStream_t)stream;
   float* M = (float*)ws;
   float* T = M + (size_t)K * D * D;
-  int rc;
-  if (N > 0 && stein_tc_supported(N, D) && stein_tc_enabled())
-    rc = launch_stein_stats_tc(X, N, D, means, W, active, G, K, M, (float*)ws + stein_base_floats(K, D), st);
-  else
-    rc = launch_stein_stats_full(X, N, D, means, W, active, G, K, M, st);
+  int rc = stein_stats(X, N, D, means, W, active, G, K, M, gneg, (float*)ws + stein_base_floats(K, D), st);
   if (rc) return rc;
-  {
-    dim3 gg(ceil_div(D, 256), K);
-    stein_gsum_kernel<<<gg, 256, 0, st>>>(W, active, G, N, D, gneg);
-    if ((rc = check_launch("stein_gsum_kernel"))) return rc;
+  return stein_finalize(prec, M, K, D, symmetrize, Hneg, T, st);
+}
+
+// The two halves of gvi_stein_full_f32 for sample-sharded runs: the raw statistics are linear in the samples, so the
+// ranks reduce-scatter M / gneg by component and every rank finalises only the components it updates.
+extern "C" size_t gvi_stein_stats_full_workspace(int N, int K, int D) {
+  if (K <= 0 || N <= 0) return 0;
+  if (D <= 32) return stein_small_workspace_floats(N, K, D) * sizeof(float);
+  if (!stein_tc_supported(N, D)) return 0;
+  return stein_tc_workspace_floats(N, K, D) * sizeof(float);
+}
+extern "C" int gvi_stein_stats_full_f32(const float* X, int N, int D, const float* means, const float* W,
+                                        const uint8_t* active, const float* G, int K, float* M, float* gneg, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_stein_stats_full_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(X && means && W && G && M && gneg, "gvi_stein_stats_full_f32: null pointer");
+  GVI_REQUIRE(K <= 65535, "gvi_stein_stats_full_f32: K=%d exceeds 65535", K);
+  if (ws_bytes < gvi_stein_stats_full_workspace(N, K, D) || (ws_bytes > 0 && ws == nullptr)) {
+    set_last_error("gvi_stein_stats_full_f32: workspace %zu < %zu", ws_bytes, gvi_stein_stats_full_workspace(N, K, D));
+    return GVI_ERR_WORKSPACE;
   }
-  // T_k = P_k M_k
-  rc = launch_gemm_auto(0, 0, K, D, D, D, 1.f, prec, D, (long long)D * D, M, D, (long long)D * D, T, D,
-                        (long long)D * D, T + (size_t)K * D * D, tc_gemm_workspace_floats(K, D, D, D), st);
-  if (rc) return rc;
-  dim3 grid(min(ceil_div(D * D, 256), 1024), K);
-  stein_finalize_kernel<<<grid, 256, 0, st>>>(T, D, symmetrize, Hneg);
-  return check_launch("stein_finalize_kernel");
+  return stein_stats(X, N, D, means, W, active, G, K, M, gneg, (float*)ws, (cudaStream_t)stream);
+}
+extern "C" size_t gvi_stein_finalize_full_workspace(int K, int D) {
+  if (K <= 0) return 0;
+  return ((size_t)K * D * D + tc_gemm_workspace_floats(K, D, D, D)) * sizeof(float);
+}
+extern "C" int gvi_stein_finalize_full_f32(const float* prec, const float* M, int K, int D, int symmetrize, float* Hneg,
+                                           void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(D > 0 && K >= 0, "gvi_stein_finalize_full_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(prec && M && Hneg && ws, "gvi_stein_finalize_full_f32: null pointer");
+  GVI_REQUIRE(K <= 65535, "gvi_stein_finalize_full_f32: K=%d exceeds 65535", K);
+  if (ws_bytes < gvi_stein_finalize_full_workspace(K, D)) {
+    set_last_error("gvi_stein_finalize_full_f32: workspace %zu < %zu", ws_bytes, gvi_stein_finalize_full_workspace(K, D));
+    return GVI_ERR_WORKSPACE;
+  }
+  return stein_finalize(prec, M, K, D, symmetrize, Hneg, (float*)ws, (cudaStream_t)stream);
 }
 
 extern "C" int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds,
@@ -1105,7 +1165,20 @@ extern "C" int gvi_fill_normal_f32(float* out, long long rows, int D, unsigned l
   GVI_REQUIRE(out, "gvi_fill_normal_f32: null pointer");
   const long long total = rows * ceil_div(D, 4);
   const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  fill_normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, D, seed, subsequence, row_offset);
+  fill_normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, D, seed, subsequence, row_offset, nullptr);
+  return check_launch("fill_normal_kernel");
+}
+
+extern "C" int gvi_fill_normal_dev_f32(float* out, long long rows, int D, unsigned long long seed,
+                                       const unsigned long long* subsequence_dev, unsigned long long subsequence_add,
+                                       long long row_offset, void* stream) {
+  GVI_REQUIRE(rows >= 0 && D > 0, "gvi_fill_normal_dev_f32: bad sizes");
+  if (rows == 0) return GVI_OK;
+  GVI_REQUIRE(out && subsequence_dev, "gvi_fill_normal_dev_f32: null pointer");
+  const long long total = rows * ceil_div(D, 4);
+  const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  fill_normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, D, seed, subsequence_add, row_offset,
+                                                               subsequence_dev);
   return check_launch("fill_normal_kernel");
 }
 

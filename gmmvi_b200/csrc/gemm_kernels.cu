@@ -488,6 +488,14 @@ int launch_stein_stats_full(const float* X, int N, int D, const float* means, co
 
 }  // namespace gvi
 
+namespace gvi {
+bool small_dim_supported(int D);
+int launch_logdens_small(const float* X, int N, int D, const float* means, const float* linv, const float* cst, int K,
+                         float* lq, cudaStream_t st);
+int launch_mixgrad_small(const float* X, int N, int D, const float* means, const float* prec, const float* lq,
+                         const float* logw, const float* logq, int K, float* grad, cudaStream_t st);
+}  // namespace gvi
+
 using namespace gvi;
 
 extern "C" int gvi_logdens_full_f32(const float* X, int N, int D, const float* means, const float* linv,
@@ -496,6 +504,7 @@ extern "C" int gvi_logdens_full_f32(const float* X, int N, int D, const float* m
   GVI_REQUIRE(K <= 65535, "gvi_logdens_full_f32: K=%d exceeds 65535", K);
   if (N == 0 || K == 0) return GVI_OK;
   GVI_REQUIRE(X && means && linv && cst && lq, "gvi_logdens_full_f32: null pointer");
+  if (small_dim_supported(D)) return launch_logdens_small(X, N, D, means, linv, cst, K, lq, (cudaStream_t)stream);
   return launch_logdens_full(X, N, D, means, linv, cst, K, lq, (cudaStream_t)stream);
 }
 
@@ -522,6 +531,7 @@ extern "C" int gvi_mixture_grad_full_f32(const float* X, int N, int D, const flo
     return GVI_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (small_dim_supported(D)) return launch_mixgrad_small(X, N, D, means, prec, lq, logw, logq, K, grad, st);
   uint32_t* mask = (uint32_t*)ws;
   resp_mask_kernel<<<ceil_div(N, BM), 128, ceil_div(K, 32) * sizeof(uint32_t), st>>>(lq, logw, logq, K, N, mask);
   int rc = check_launch("resp_mask_kernel");

@@ -60,13 +60,32 @@ class GMM:
         self._chol_cov = v
         self._version += 1
 
-    def set_components_sharded(self, new_means, chol_full, chol_work, a, b, chol_local):
-        """Result of a component-sharded update: `chol_full` is still being all-gathered (`chol_work`), the rows
-        [a, b) this rank computed itself are available at once (they feed the sharded `prepared()`)."""
-        self.means = new_means.contiguous()
-        self.chol_cov = chol_full
+    def set_components_sharded(self, a, b, means_local, chol_local, extras_local=()):
+        """Result of a component-sharded update: this rank computed the components [a, b).  Three collectives distribute
+        it: ONE small all-gather of (means | log-normalisers | extras) rows, ONE all-gather of the inverse factors (the
+        next log-density pass of every rank needs all of them at once) and an ASYNCHRONOUS all-gather of the factors
+        themselves, which in steady state nobody waits for: a rank samples from / updates only its own components
+        (`local_chol`), the precisions are formed from the gathered inverses.  `extras_local`: [b - a] vectors
+        (success, eta, KL) that travel with the small gather; returns them gathered, as float32 [K] each."""
+        K = self.num_components
+        shard = self.shard
+        if not self.diagonal_covs:
+            l_loc, _, c_loc = ops.prepare_full(chol_local, want_prec=False)[:3]
+        cols = [means_local] + ([c_loc.unsqueeze(1)] if not self.diagonal_covs else []) \
+            + [e.to(torch.float32).unsqueeze(1) for e in extras_local]
+        packed = shard.all_gather_rows(torch.cat(cols, dim=1).contiguous(), K)
+        D = self.num_dimensions
+        self.means = packed[:, :D].contiguous()
+        chol_full, chol_work = shard.all_gather_rows_async(chol_local, K)
+        self.chol_cov = chol_full               # (the setter waits for a previous in-flight gather)
         self._chol_work = chol_work
         self._local_chol = (self._version, a, b, chol_local)
+        c = D
+        if not self.diagonal_covs:
+            linv = shard.all_gather_rows(l_loc, K)
+            self._prepared = (self._version, linv, None, packed[:, c].contiguous())
+            c += 1
+        return [packed[:, c + i].contiguous() for i in range(len(extras_local))]
 
     @property
     def device(self):
@@ -116,7 +135,7 @@ class GMM:
         n = int(num_samples)
         D = self.num_dimensions
         if noise is None:
-            noise = ops.fill_normal(n, D, rng.seed(), rng.next_subsequence(), 0, self.device)
+            noise = ops.fill_normal(n, D, rng.seed(), rng.device_counter() or rng.next_subsequence(), 0, self.device)
         offsets = torch.tensor([0, n], device=self.device, dtype=torch.int32)
         X, _ = ops.sample_components(self.diagonal_covs, noise, offsets, self._means[index:index + 1].contiguous(),
                                      self.chol_cov[index:index + 1].contiguous(), n)
@@ -234,7 +253,7 @@ class GMM:
             total, max_per_component = int(offsets[-1].item()), int(n.max().item()) if n.numel() else 0
         D = self.num_dimensions
         if noise is None:
-            noise = ops.fill_normal(total, D, rng.seed(), rng.next_subsequence(), row_offset, self.device)
+            noise = ops.fill_normal(total, D, rng.seed(), rng.device_counter() or rng.next_subsequence(), row_offset, self.device)
         if total == 0:
             return torch.zeros((0, D), device=self.device), torch.zeros(0, device=self.device, dtype=torch.int32)
         if component_range is not None:

@@ -194,6 +194,17 @@ def clear_memo():
     del _LOGDENS_MEMO[:]
 
 
+def clear_caches():
+    """Drop the log-density memo and every derived-operand cache.  The caches are keyed on (address, torch version
+    counter, shape); a CUDA-graph replay rewrites its static buffers without touching the version counters, so the
+    graph runner clears them after every replay (optimization/graphed.py)."""
+    del _LOGDENS_MEMO[:]
+    del _H16_CACHE[:]
+    del _SPLIT_CACHE[:]
+    del _P16_CACHE[:]
+    del _ABSMAX_CACHE[:]
+
+
 def logdens_diag(X, means, stds):
     X, means, stds = _chk(X, "X"), _chk(means, "means"), _chk(stds, "stds")
     N, D = X.shape
@@ -351,6 +362,34 @@ def stein_full(X, means, prec, W, active, G, symmetrize=True):
     _call("gvi_stein_full_f32", X.data_ptr(), N, D, means.data_ptr(), prec.data_ptr(), W.data_ptr(), _ptr(active),
           G.data_ptr(), K, int(bool(symmetrize)), Hneg.data_ptr(), gneg.data_ptr(), ws.data_ptr(), nbytes, _stream())
     return Hneg, gneg
+
+
+def stein_stats_full(X, means, W, active, G):
+    """Raw Stein statistics of this rank's samples -> (M[K,D,D] = sum_n w (x - mu) g^T, gneg[K,D] = -sum_n w g)."""
+    X, means, W, G = _chk(X, "X"), _chk(means, "means"), _chk(W, "W"), _chk(G, "G")
+    if active is not None:
+        active = _chk(active, "active", torch.uint8)
+    N, D = X.shape
+    K = means.shape[0]
+    M = torch.empty((K, D, D), device=X.device, dtype=torch.float32)
+    gneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
+    nbytes = _lib.lib().gvi_stein_stats_full_workspace(N, K, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.float32)
+    _call("gvi_stein_stats_full_f32", X.data_ptr(), N, D, means.data_ptr(), W.data_ptr(), _ptr(active), G.data_ptr(), K,
+          M.data_ptr(), gneg.data_ptr(), ws.data_ptr(), nbytes, _stream(), kernels=8)
+    return M, gneg
+
+
+def stein_finalize_full(prec, M, symmetrize=True):
+    """Hneg[k] = -sym(P_k M_k) (or the un-symmetrised form of the standard-IW branch) for the given components."""
+    prec, M = _chk(prec, "prec"), _chk(M, "M")
+    K, D, _ = M.shape
+    Hneg = torch.empty_like(M)
+    nbytes = _lib.lib().gvi_stein_finalize_full_workspace(K, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=M.device, dtype=torch.float32)
+    _call("gvi_stein_finalize_full_f32", prec.data_ptr(), M.data_ptr(), K, D, int(bool(symmetrize)), Hneg.data_ptr(),
+          ws.data_ptr(), nbytes, _stream(), kernels=4)
+    return Hneg
 
 
 def stein_diag(X, means, stds, W, G):
@@ -535,8 +574,13 @@ def fill_normal(rows: int, D: int, seed: int, subsequence: int = 0, row_offset: 
     if not out.is_cuda:
         raise _lib.GmmviLibraryError("fill_normal: needs a CUDA device")
     with torch.cuda.device(out.device):
-        _call("gvi_fill_normal_f32", out.data_ptr(), rows, D, seed & (2 ** 64 - 1), subsequence & (2 ** 64 - 1),
-              row_offset, _stream())
+        if isinstance(subsequence, tuple):          # (device counter, offset): rng device mode (CUDA-graph capture)
+            counter, off = subsequence
+            _call("gvi_fill_normal_dev_f32", out.data_ptr(), rows, D, seed & (2 ** 64 - 1), counter.data_ptr(),
+                  int(off), row_offset, _stream())
+        else:
+            _call("gvi_fill_normal_f32", out.data_ptr(), rows, D, seed & (2 ** 64 - 1), subsequence & (2 ** 64 - 1),
+                  row_offset, _stream())
     return out
 
 

@@ -30,6 +30,9 @@ class GMMVI:
         self.weight_stepsize_adapter = weight_stepsize_adapter
         self.weight_updater = weight_updater
         self.num_updates = 0
+        self._graph = None             # optimization/graphed.GraphedIteration when CUDA-graph iterations are enabled
+        self._graph_enabled = False
+        self._graph_stable = 0
 
     @staticmethod
     def build_from_config(config: dict, target_distribution, model):
@@ -63,13 +66,37 @@ class GMMVI:
         gmm = self.model.model if hasattr(self.model, "model") else self.model
         gmm.shard = shard
 
+    def enable_cuda_graph(self, enabled: bool = True):
+        """Run the iteration as ONE captured CUDA graph (the counterpart of the reference's tf.function around train_iter,
+        optimization/gmmvi.py:99-103): `train_iter()` replays the graph whenever the number of components has not changed
+        since the previous iteration, and runs eagerly (then captures again) when it has.  Needs the component-based
+        selector with ratio_reused_samples_to_desired = 0; results are bit-identical to eager iterations."""
+        from .graphed import GraphedIteration
+        if enabled:
+            GraphedIteration(self)          # raises when the configuration cannot be captured
+        self._graph_enabled, self._graph, self._graph_stable = bool(enabled), None, 0
+
+    def _graphed_step(self):
+        from .graphed import GraphedIteration
+        K = self.model.num_components
+        if self._graph is not None and self._graph.num_components != K:
+            self._graph, self._graph_stable = None, 0
+        if self._graph is None:
+            if self._graph_stable < 1:          # first iteration at this K runs eagerly (also warms every kernel up)
+                self._graph_stable += 1
+                return False
+            self._graph = GraphedIteration(self).capture()
+        self._graph.replay()
+        return True
+
     def train_iter(self, noise=None, adaptation_draws=None):
         """optimization/gmmvi.py:146-161.  `noise` ([N,D] standard-normal draws, optional) replaces the device
         generator for this iteration's samples (used by the parity tests and the end-to-end benchmark);
         `adaptation_draws` = (uniform, permutation) does the same for the two random draws of a component addition."""
-        samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
-            self.sample_selector.select_samples(**({} if noise is None else {"noise": noise}))
-        self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
+        if not (self._graph_enabled and noise is None and self._graphed_step()):
+            samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
+                self.sample_selector.select_samples(**({} if noise is None else {"noise": noise}))
+            self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)
         if adaptation_draws is None:
             self.num_component_adapter.adapt_number_of_components(self.num_updates)
         else:

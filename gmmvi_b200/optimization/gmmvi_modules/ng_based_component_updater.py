@@ -59,13 +59,11 @@ class NgBasedComponentUpdater:
                 self._mode, m.diagonal_covs, sl(m.means), m.local_chol(a, b), sl(expected_hessians_neg),
                 sl(expected_gradients_neg), sl(stepsizes), sl(m.last_log_etas), sl(m.num_received_updates),
                 self.temperature)
-            means, succ, etas, kls = (shard.all_gather_rows(parts[i], K) for i in (0, 2, 3, 4))
-            chols, chol_work = shard.all_gather_rows_async(parts[1], K)
+            succ, etas, kls = m.set_components_sharded(a, b, parts[0], parts[1], (parts[2], parts[3], parts[4]))
+            succ = succ.to(torch.int32)
         self.last_success, self.last_kls, self.last_etas = succ, kls, etas
         if rng_ is None:
             m.replace_components(means, chols)
-        else:
-            m.set_components_sharded(means, chols, chol_work, rng_[0], rng_[1], parts[1])
         m.num_received_updates = m.num_received_updates + 1.0
         l2 = m.l2_regularizers                                            # quirk 11, :135-138
         m.l2_regularizers = torch.where(succ.bool(),

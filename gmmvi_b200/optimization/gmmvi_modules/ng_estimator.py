@@ -65,29 +65,39 @@ class SteinNgEstimator(NgEstimator):
         _, model_densities_grad, lq = model.log_density_and_grad(samples)
         G = (target_lnpdfs_grads - model_densities_grad).contiguous()
         iw = self._importance_weights(lq, mapping, background_densities, want_W=True, want_active=True)
+        shard = model.shard
+        rng_ = shard.component_range(model.num_components) if (shard is not None and shard.world > 1) else None
+        symmetrize = self._use_self_normalized_importance_weights       # quirk 7
+        if not symmetrize:
+            rng_ = None         # the general (non-symmetric) direct / iBLR update is replicated: all rows must be valid
+        self.valid_rows = None
         if model.diagonal_covs:
             H, g = ops.stein_diag(samples, model.means, model.chol_cov, iw["W"], G)
+        elif rng_ is not None:
+            # Sample-sharded run: the RAW statistics (sums over this rank's samples) are reduce-scattered by component
+            # (half the traffic of an all-reduce) and only the K / world components this rank updates are finalised
+            # (H_k = -sym(P_k M_k)).  Rows outside [a, b) of the returned tensors are never read (`valid_rows`).
+            a, b = rng_
+            M, g = ops.stein_stats_full(samples, model.means, iw["W"], iw["active"], G)
+            M_own = shard.reduce_scatter_rows(M)
+            g[a:b] = shard.reduce_scatter_rows(g)
+            _, prec, _ = model.prepared()
+            H = M                                                        # storage reuse: only rows [a, b) are valid
+            H[a:b] = ops.stein_finalize_full(prec[a:b].contiguous(), M_own, symmetrize)
+            self.valid_rows = (a, b)
+            H.gvi_nonsymmetric = not symmetrize
+            return H, g
         else:
             _, prec, _ = model.prepared()
-            symmetrize = self._use_self_normalized_importance_weights       # quirk 7
             H, g = ops.stein_full(samples, model.means, prec, iw["W"], iw["active"], G, symmetrize)
             # the standard-IW estimate is not symmetric: the direct / iBLR updaters must treat it like the reference's
             # LU-based tf.linalg.inv / solve does (ng_based_component_updater.py:116-117, 199)
             H.gvi_nonsymmetric = not symmetrize
-        if model.shard is not None:     # partial sums over this rank's samples -> sums over the whole iteration
-            rng_ = model.shard.component_range(model.num_components)
-            if rng_ is not None and model.shard.world > 1:
-                # The component update is sharded the same way and only reads its own rows: reduce-scatter by
-                # component (half the traffic of an all-reduce).  Rows outside [a, b) of the returned tensors keep
-                # this rank's PARTIAL sums and must not be used; `valid_rows` records the valid range.
-                a, b = rng_
-                H[a:b] = model.shard.reduce_scatter_rows(H)
-                g[a:b] = model.shard.reduce_scatter_rows(g)
-                self.valid_rows = (a, b)
-            else:
-                model.shard.all_reduce_sum_(H)
-                model.shard.all_reduce_sum_(g)
-                self.valid_rows = None
+        if shard is not None and shard.world > 1:     # K not divisible by the world size: plain all-reduce
+            nonsym = getattr(H, "gvi_nonsymmetric", False)
+            shard.all_reduce_sum_(H)
+            shard.all_reduce_sum_(g)
+            H.gvi_nonsymmetric = nonsym
         return H, g
 
 

@@ -69,7 +69,10 @@ class VipsSampleSelector(SampleSelector):
                 raise NotImplementedError("sample reuse is not supported together with multi-GPU sharding")
             per = max(1, int(num_desired_samples))
             local, row_offset = shard.local_counts([per] * K)
-            n_add = torch.tensor(local, device=self.model.device, dtype=torch.int32)
+            key = (tuple(local), str(self.model.device))       # constant across iterations: one upload, graph-safe
+            if getattr(self, "_n_add_key", None) != key:
+                self._n_add_key, self._n_add_dev = key, torch.tensor(local, device=self.model.device, dtype=torch.int32)
+            n_add = self._n_add_dev
             total, mx = sum(local), max(local)
             rng_ = shard.component_range(K)
             if rng_ is not None and all(c == 0 for i, c in enumerate(local) if not rng_[0] <= i < rng_[1]):
@@ -103,6 +106,40 @@ class VipsSampleSelector(SampleSelector):
         oldsamples_pdf, samples, mapping, target_lnpdfs, target_grads = self.sample_db.get_newest_samples(
             num_reused_samples + num_new_samples)
         return samples, mapping, oldsamples_pdf, target_lnpdfs, target_grads
+
+
+    def select_samples_deferred(self, noise=None):
+        """The no-reuse iteration WITHOUT touching the sample database -> ((samples, mapping, bg, target_lnpdfs,
+        target_grads), payload).  With ratio_reused_samples_to_desired = 0 `select_samples` reads back exactly the samples
+        it has just stored, and their background density is the mixture they were drawn from with count-proportional
+        weights (sample_db.py:217-227); computing that directly keeps every shape and address fixed, which is what a
+        captured CUDA graph of the iteration needs (optimization/graphed.py).  `payload` is what `add_samples` has to
+        store afterwards (the parameters the samples were drawn from are copied: the update overwrites them).
+        `mapping` holds component indices of the current model; the database-global offset of sample_db.py:115 cancels
+        in the estimators' relative mapping (ng_estimator.py:244)."""
+        if self.reused_samples_per_component != 0:
+            raise NotImplementedError("select_samples_deferred needs ratio_reused_samples_to_desired = 0")
+        m, db = self.model, self.sample_db
+        dev = m.device
+        empty = torch.zeros((0, m.num_dimensions), device=dev)
+        new_samples, lnpdfs, grads, mapping = self.sample_where_needed(empty, torch.zeros(0, device=dev), noise=noise)
+        K = m.num_components
+        if db.count_override is not None:
+            count = db.count_override.to(torch.float32)
+        else:
+            count = torch.full((K,), float(max(1, self.desired_samples_per_component)), device=dev)
+        weight = count / torch.sum(count)
+        if m.diagonal_covs:
+            chols = m.chol_cov
+            bg, _ = db.evaluate_background(weight, m.means, chols, None, new_samples.contiguous())
+            payload = (new_samples, m.means.clone(), chols.clone(), lnpdfs, grads, mapping, None) if db.keep_samples else None
+        else:
+            linv, _, cst = m.prepared(need_prec=False)
+            chols = m.chol_cov if m.shard is None else m.chol_cov_handle
+            bg, _ = db.evaluate_background(weight, m.means, chols, linv, new_samples.contiguous(), cst)
+            payload = ((new_samples, m.means.clone(), chols.clone(), lnpdfs, grads, mapping,
+                        (linv.clone(), None, cst.clone())) if db.keep_samples else None)
+        return (new_samples, mapping, bg, lnpdfs, grads), payload
 
 
 class LinSampleSelector(SampleSelector):

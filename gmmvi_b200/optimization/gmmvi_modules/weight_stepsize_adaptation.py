@@ -42,12 +42,12 @@ class DecayingWeightStepsizeAdaptation(WeightStepsizeAdaptation):
         super().__init__(initial_stepsize, device)
         self.initial_stepsize = float(initial_stepsize)
         self.annealing_exponent = float(annealing_exponent)
-        self.num_weight_updates = 0.0
+        self.num_weight_updates = torch.zeros(1, device=device, dtype=torch.float32)     # device counter (graph-safe)
 
     def _update_stepsize(self):
         """:96-105."""
-        self.stepsize = torch.full_like(self.stepsize, self.initial_stepsize / (1.0 + self.num_weight_updates ** self.annealing_exponent))
-        self.num_weight_updates += 1.0
+        self.stepsize = self.initial_stepsize / (1.0 + torch.pow(self.num_weight_updates, self.annealing_exponent))
+        self.num_weight_updates = self.num_weight_updates + 1.0
 
 
 class ImprovementBasedWeightStepsizeAdaptation(WeightStepsizeAdaptation):

@@ -77,10 +77,19 @@ class SampleDB:
         self.target_lnpdfs = self.target_lnpdfs[::N].contiguous()
         self.target_grads = self.target_grads[::N].contiguous()
         mapping = self.mapping[::N]
-        # tf.unique: first-occurrence order; mapping is non-decreasing so sorted order is the same
-        used, reduced = torch.unique(mapping, sorted=True, return_inverse=True)
-        self.mapping = reduced.to(torch.int32).contiguous()
-        used = used.long()
+        # tf.unique returns the values in FIRST-OCCURRENCE order (sample_db.py:75).  The mapping of the component-based
+        # selector is non-decreasing (sorted order would do), the mixture-based selector stores draw-order indices
+        # (models/gmm.py:155-163), so the order is rebuilt explicitly: rank the sorted unique values by the position of
+        # their first occurrence.
+        vals, inv = torch.unique(mapping, sorted=True, return_inverse=True)
+        pos = torch.arange(mapping.shape[0], device=mapping.device)
+        first = torch.full((vals.shape[0],), mapping.shape[0], device=mapping.device, dtype=pos.dtype)
+        first.scatter_reduce_(0, inv, pos, reduce="amin")
+        order = torch.argsort(first)                       # unique values in first-occurrence order
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.shape[0], device=order.device)
+        self.mapping = rank[inv].to(torch.int32).contiguous()
+        used = vals[order].long()
         self.means = self.means[used].contiguous()
         self.chols = self.chols[used].contiguous()
         self.inv_chols = self.inv_chols[used].contiguous()

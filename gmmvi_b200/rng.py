@@ -13,6 +13,36 @@ import numpy as np
 import torch
 
 _state = {"seed": 0, "subsequence": 0}
+# While a CUDA graph of the iteration is captured (optimization/graphed.py) the draw counter lives on the device: a draw
+# uses *counter + (draws so far in this capture), and the graph ends with counter += draws, so every replay sees fresh
+# subsequences -- the same ones an eager run would have used.
+_device = {"counter": None, "draws": 0}
+
+
+def begin_device_mode(counter):
+    """counter: int64 device tensor [1] holding the subsequence of the next draw."""
+    _device["counter"], _device["draws"] = counter, 0
+
+
+def end_device_mode() -> int:
+    """-> number of draws issued since begin_device_mode."""
+    n = _device["draws"]
+    _device["counter"], _device["draws"] = None, 0
+    return n
+
+
+def device_counter():
+    """(counter tensor, offset) for the next draw in device mode, or None in host mode; advances the offset."""
+    if _device["counter"] is None:
+        return None
+    off = _device["draws"]
+    _device["draws"] = off + 1
+    return _device["counter"], off
+
+
+def advance(n: int):
+    """Account on the host for `n` draws made by a graph replay."""
+    _state["subsequence"] += int(n)
 
 
 def set_seed(seed: int):

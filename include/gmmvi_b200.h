@@ -113,6 +113,15 @@ size_t gvi_stein_full_workspace(int N, int K, int D);
 int gvi_stein_full_f32(const float* X, int N, int D, const float* means, const float* prec, const float* W,
                        const uint8_t* active, const float* G, int K, int symmetrize, float* Hneg, float* gneg,
                        void* ws, size_t ws_bytes, void* stream);
+/* The two halves of gvi_stein_full_f32 for sample-sharded (multi-GPU) runs: M and gneg are sums over samples, so the ranks
+ * reduce-scatter them by component ("reduce-scatter of (sum e g, sum e z g^T)") and every rank
+ * finalises only the K / world components it updates.  M[K,D,D], gneg[K,D]; ws sizes from the *_workspace() calls. */
+size_t gvi_stein_stats_full_workspace(int N, int K, int D);
+int gvi_stein_stats_full_f32(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
+                             const float* G, int K, float* M, float* gneg, void* ws, size_t ws_bytes, void* stream);
+size_t gvi_stein_finalize_full_workspace(int K, int D);
+int gvi_stein_finalize_full_f32(const float* prec, const float* M, int K, int D, int symmetrize, float* Hneg, void* ws,
+                                size_t ws_bytes, void* stream);
 /* diagonal: Hneg[k,d] = -sum_n W (x-mu)_d / std_d^2 * G[n,d]   (ng_estimator.py:177-180) */
 int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* W,
                        const float* G, int K, float* Hneg, float* gneg, void* stream);
@@ -165,6 +174,11 @@ int gvi_weight_update_f32(int trust_region, const float* logw, const float* elr,
  * so a shard draws exactly the rows it owns regardless of the number of GPUs. */
 int gvi_fill_normal_f32(float* out, long long rows, int D, unsigned long long seed,
                         unsigned long long subsequence, long long row_offset, void* stream);
+/* Same generator with the draw counter in DEVICE memory: subsequence = *subsequence_dev + subsequence_add.  A captured CUDA
+ * graph of the iteration replays with fresh noise by incrementing the counter on the device. */
+int gvi_fill_normal_dev_f32(float* out, long long rows, int D, unsigned long long seed,
+                            const unsigned long long* subsequence_dev, unsigned long long subsequence_add,
+                            long long row_offset, void* stream);
 /* x = mu_k + L_k eps for the rows [offsets[k], offsets[k+1]) of eps/X[N,D]; mapping[n]=k
  * (models/gmm.py:361-386, full_cov_gmm.py:36-39, diagonal_gmm.py:43-45).  offsets[K+1] is a device
  * prefix sum; max_rows_per_component (host) bounds the grid. */

@@ -336,3 +336,47 @@ def test_first_iteration_matches_reference_sources(case):
     assert np.array_equal(m.num_received_updates.cpu().numpy(), g["num_received_updates0"])
     if cfg["ng_based_updater_type"] == "trust-region":
         assert np.allclose(m.last_log_etas.cpu().numpy(), g["last_log_etas0"], rtol=1e-4)
+
+
+def test_runner_dump_schema_and_metrics_match_oracle(tmp_path):
+    """GmmviRunner.log_to_disk / finalize write the reference's .npz schema (gmmvi_runner.py:
+    177-200: weights, means, covs, timestamps, fevals; `gmm_dump_<n>.npz` for n < 100 or n % 50 == 0, `final_gmm_dump.npz`),
+    and the Monte-Carlo ELBO / entropy of get_expensive_metrics (:119-144) agree with the oracle on the same test samples."""
+    import glob
+    from gmmvi_b200.configs import get_default_algorithm_config, get_default_experiment_config, update_config
+    from gmmvi_b200.gmmvi_runner import GmmviRunner
+    algo = update_config(get_default_algorithm_config("SAMTRON"),
+                         {"sample_selector_config": {"desired_samples_per_component": 40, "ratio_reused_samples_to_desired": 0.0},
+                          "model_initialization": {"num_initial_components": 6}})
+    config = update_config(update_config(get_default_experiment_config("gmm20"), {"start_seed": 3}), algo)
+    config["gmmvi_runner_config"] = {"log_metrics_interval": 1}
+    config["dump_gmm_path"] = str(tmp_path)
+    runner = GmmviRunner.build_from_config(config)
+    for n in range(3):
+        out = runner.iterate_and_log(n)
+        runner.log_to_disk(n)
+    runner.log_to_disk(101)                      # neither < 100 nor a multiple of 50: nothing written
+    runner.log_to_disk(150)
+    runner.finalize()
+    files = sorted(os.path.basename(f) for f in glob.glob(os.path.join(runner.dump_gmm_path, "*.npz")))
+    assert files == ["final_gmm_dump.npz", "gmm_dump_0.npz", "gmm_dump_1.npz", "gmm_dump_150.npz", "gmm_dump_2.npz"]
+    m = runner.gmmvi.model
+    K, D = m.num_components, m.num_dimensions
+    d = np.load(os.path.join(runner.dump_gmm_path, "final_gmm_dump.npz"))
+    assert sorted(d.files) == ["covs", "fevals", "means", "timestamps", "weights"]
+    assert d["weights"].shape == (K,) and d["means"].shape == (K, D) and d["covs"].shape == (K, D, D)
+    assert abs(float(d["weights"].sum()) - 1.0) < 1e-5 and int(d["fevals"]) == runner.gmmvi.sample_db.num_samples_written
+    L = m.chol_cov.cpu().numpy().astype(np.float64)
+    close("dumped covs", d["covs"], L @ L.transpose(0, 2, 1), TOL_LOGDENS)
+    assert {"-elbo", "entropy", "target_density", "algo_time", "walltime", "num_samples", "num_components", "max_weight",
+            "num_db_samples", "num_db_components"} <= set(out)
+    # ELBO pieces on fixed test samples against the oracle (fp64) evaluated at the device's parameters
+    test_samples, entropy = runner.get_samples_and_entropy(2000)
+    og = O.OracleGMM(m.log_weights.cpu().numpy().astype(np.float64), m.means.cpu().numpy().astype(np.float64), L, False)
+    X = test_samples.cpu().numpy().astype(np.float64)
+    close("entropy", entropy.reshape(1), np.array([-np.mean(O.log_density(og, X))]), TOL_LOGDENS)
+    tgt = runner.gmmvi.sample_selector.target_distribution
+    tL = tgt.gmm.chol_cov.cpu().numpy().astype(np.float64)
+    ot = O.OracleGMM(tgt.gmm.log_weights.cpu().numpy().astype(np.float64), tgt.gmm.means.cpu().numpy().astype(np.float64), tL, False)
+    mean_reward = torch.mean(runner.gmmvi.sample_selector.target_uld(test_samples))
+    close("target_density", mean_reward.reshape(1), np.array([np.mean(O.log_density(ot, X))]), TOL_LOGDENS)

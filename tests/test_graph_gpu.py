@@ -1,0 +1,98 @@
+"""CUDA-graph iterations (gmmvi_b200/optimization/graphed.py, the counterpart of the reference's tf.function around
+train_iter, optimization/gmmvi.py:99-103) reproduce eager iterations: same seed -> same noise subsequences -> the same
+mixture, including across component additions / deletions (re-capture) and with the growing sample database."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _fixed(K, D, desired, updater="trust-region", diag=False):
+    from gmmvi_b200.experiments.target_distributions.gmm import GMM_LNPDF
+    from gmmvi_b200.models.diagonal_gmm import DiagonalGMM
+    from gmmvi_b200.models.full_cov_gmm import FullCovGMM
+    from gmmvi_b200.models.gmm_wrapper import GmmWrapper
+    from gmmvi_b200.optimization.gmmvi import GMMVI
+    from test_api_gpu import base_config
+    rng = np.random.default_rng(0)
+    means = (rng.standard_normal((K, D)) * 2).astype(np.float32)
+    A = rng.standard_normal((K, D, D))
+    covs = (A @ A.transpose(0, 2, 1) / D + np.eye(D)).astype(np.float32)
+    tm = rng.standard_normal((3, D)) * 2
+    tA = rng.standard_normal((3, D, D))
+    cfg = base_config(updater, "trust-region", diag, desired, stepsize=0.05, comp_adapter="improvement-based")
+    cfg["weight_stepsize_adapter_type"] = "improvement_based"
+    cfg["weight_stepsize_adapter_config"] = {"initial_stepsize": 0.5, "min_stepsize": 0.0001, "max_stepsize": 1.0,
+                                             "stepsize_inc_factor": 1.15, "stepsize_dec_factor": 0.85}
+    w = np.ones(K, np.float32) / K
+    model = DiagonalGMM(w, means, np.stack([np.diag(c) for c in covs])) if diag else FullCovGMM(w, means, covs)
+    target = GMM_LNPDF(np.ones(3) / 3, tm, tA @ tA.transpose(0, 2, 1) / D + np.eye(D))
+    return GMMVI.build_from_config(cfg, target, GmmWrapper.build_from_config(model, cfg))
+
+
+def _state(g):
+    m = g.model
+    return {n: getattr(m, n).detach().cpu().numpy().copy() for n in
+            ("means", "chol_cov", "log_weights", "stepsizes", "last_log_etas", "l2_regularizers", "num_received_updates",
+             "reward_history", "weight_history")}
+
+
+@pytest.mark.parametrize("K,D,desired,updater,diag", [(8, 32, 64, "trust-region", False), (6, 96, 128, "trust-region", False),
+                                                      (5, 12, 50, "iBLR", False), (6, 16, 40, "trust-region", True)])
+def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag):
+    from gmmvi_b200 import rng
+    iters = 6
+    rng.set_seed(11)
+    eager = _fixed(K, D, desired, updater, diag)
+    for _ in range(iters):
+        eager.train_iter()
+    rng.set_seed(11)
+    graphed = _fixed(K, D, desired, updater, diag)
+    graphed.enable_cuda_graph()
+    for _ in range(iters):
+        graphed.train_iter()
+    torch.cuda.synchronize()
+    assert graphed._graph is not None and graphed._graph.graph is not None       # iterations 2.. were replays
+    assert graphed.num_updates == eager.num_updates == iters
+    assert graphed.sample_db.num_samples_written == eager.sample_db.num_samples_written
+    a, b = _state(eager), _state(graphed)
+    for n in a:
+        assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
+    # the database holds the last iteration's samples in both modes
+    assert torch.equal(eager.sample_db.samples, graphed.sample_db.samples)
+
+
+def test_graph_mode_follows_component_adaptation():
+    """SAMTRON with VipsComponentAdaptation and the growing sample database (the runner flow of examples/5): components
+    are added / deleted between replays, the graph is captured again for every new K."""
+    from gmmvi_b200.configs import get_default_algorithm_config, get_default_experiment_config, update_config
+    from gmmvi_b200.gmmvi_runner import GmmviRunner
+
+    def run(graph):
+        algo = update_config(get_default_algorithm_config("SAMTRON"),
+                             {"num_component_adapter_config": {"del_iters": 5, "add_iters": 4},
+                              "sample_selector_config": {"desired_samples_per_component": 50, "ratio_reused_samples_to_desired": 0.0},
+                              "model_initialization": {"num_initial_components": 8}})
+        config = update_config(update_config(get_default_experiment_config("stm20"), {"start_seed": 5}), algo)
+        config["gmmvi_runner_config"] = {"log_metrics_interval": 10 ** 9}
+        runner = GmmviRunner.build_from_config(config)
+        if graph:
+            runner.gmmvi.enable_cuda_graph()
+        ks = []
+        for n in range(18):
+            runner.iterate_and_log(n)
+            ks.append(runner.gmmvi.model.num_components)
+        return runner, ks
+    torch.manual_seed(0)
+    e, ks_e = run(False)
+    torch.manual_seed(0)
+    g, ks_g = run(True)
+    assert ks_e == ks_g and len(set(ks_e)) > 1            # components were added (and the graph re-captured)
+    assert e.gmmvi.sample_db.num_samples_written == g.gmmvi.sample_db.num_samples_written
+    assert e.gmmvi.sample_db.samples.shape == g.gmmvi.sample_db.samples.shape
+    a, b = _state(e.gmmvi), _state(g.gmmvi)
+    for n in a:
+        assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
+    assert torch.equal(e.gmmvi.sample_db.samples, g.gmmvi.sample_db.samples)
+    assert torch.equal(e.gmmvi.sample_db.mapping, g.gmmvi.sample_db.mapping)

@@ -210,3 +210,29 @@ def test_default_configs_equal_the_reference_yml_files():
         upd = C.update_config(C.get_default_algorithm_config("SAMTRON"),
                               {"sample_selector_config": {"desired_samples_per_component": 7}, "temperature": 0.5})
         assert norm(upd) == ref["merged"]["update"]
+
+
+def test_thinning_reindexes_in_first_occurrence_order():
+    """SampleDB.remove_every_nth_sample (sample_db.py:64-79): tf.unique returns first-occurrence order; with the
+    mixture-based selector's draw-order mapping that differs from sorted order.  Pure index logic: runs on CPU tensors."""
+    from gmmvi_b200.optimization.sample_db import SampleDB
+    rng = np.random.default_rng(0)
+    D, M, N = 3, 7, 40
+    mapping = rng.integers(0, M, N).astype(np.int32)            # not monotone
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    means = rng.standard_normal((M, D)).astype(np.float32)
+    chols = np.tile(np.eye(D, dtype=np.float32), (M, 1, 1)) * np.arange(1, M + 1, dtype=np.float32)[:, None, None]
+    db = SampleDB(D, False, True, 1000, device="cpu")
+    t = torch.as_tensor
+    db.samples, db.target_lnpdfs, db.target_grads = t(X), t(X[:, 0].copy()), t(X.copy())
+    db.mapping, db.means, db.chols, db.inv_chols = t(mapping), t(means), t(chols), t(1.0 / np.maximum(chols, 1e-30) * (chols > 0))
+    db.consts = t(np.arange(M, dtype=np.float32))
+    odb = O.OracleSampleDB(D, False, True, 1000, np.float32)
+    odb.samples, odb.target_lnpdfs, odb.target_grads = X, X[:, 0].copy(), X.copy()
+    odb.mapping, odb.means, odb.chols, odb.inv_chols = mapping, means, chols, chols.copy()
+    db.remove_every_nth_sample(2)
+    odb.remove_every_nth_sample(2)
+    assert np.array_equal(db.mapping.numpy(), odb.mapping)
+    assert np.array_equal(db.means.numpy(), odb.means) and np.array_equal(db.chols.numpy(), odb.chols)
+    assert np.array_equal(db.samples.numpy(), odb.samples)
+    assert db.consts.shape[0] == odb.means.shape[0]

@@ -575,3 +575,44 @@ def test_mmd_matches_oracle(n1, n2, D):
     ref = O.mmd(G, S, alpha, np.float64)
     assert np.isclose(float(m.compute_MMD(dev(S))), ref, rtol=1e-3, atol=1e-6)
     assert abs(float(m.compute_MMD(dev(G)))) < 1e-6
+
+
+@pytest.mark.parametrize("K,D,N", [(1, 1, 7), (37, 8, 1000), (19, 9, 515), (45, 20, 9000), (128, 10, 3001), (11, 16, 129),
+                                   (9, 17, 400), (10, 24, 640), (13, 25, 300), (8, 31, 777), (12, 32, 1500)])
+def test_small_dimension_kernels(K, D, N, monkeypatch):
+    """The D <= 32 kernels (csrc/small_dim.cu: the shapes of BASELINE configs C1 / C2 -- D = 20 and D = 10) against the
+    fp64 oracle and against the general tile engines (GMMVI_B200_SMALL_DIM=0) on the same inputs: component log
+    densities, mixture gradient, Stein statistics with weightless blocks skipped."""
+    from gmmvi_b200 import ops
+
+    def run():
+        ops.clear_caches()
+        g, X = make_problem(K, D, N, seed=21, scale=4.0)
+        g32 = gmm32_of(g)
+        rng = np.random.default_rng(22)
+        tgrad = rng.standard_normal((N, D)).astype(np.float32)
+        linv, prec, cst, _ = ops.prepare_full(dev(g32.chol_cov))
+        lq = ops.logdens_full(dev(X), dev(g32.means), linv, cst, memo=False, tensor_cores=False)
+        logq = ops.mixture_lse(lq, dev(g32.log_weights))
+        gq = ops.mixture_grad_full(dev(X), dev(g32.means), prec, lq, dev(g32.log_weights), logq, tensor_cores=False)
+        bg = ops.mixture_lse(lq, dev(np.log(np.ones(K, np.float32) / K)))
+        iw = ops.importance_weights(lq, bg, None, True, None, True, False, False, True)
+        G = (dev(tgrad) - gq).contiguous()
+        H, gn = ops.stein_full(dev(X), dev(g32.means), prec, iw["W"], iw["active"], G, True)
+        return g32, X, tgrad, [t.cpu().numpy() for t in (lq, gq, H, gn, bg)]
+    g32, X, tgrad, small = run()
+    monkeypatch.setenv("GMMVI_B200_SMALL_DIM", "0")
+    _, _, _, general = run()
+    monkeypatch.delenv("GMMVI_B200_SMALL_DIM")
+    g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64), g32.chol_cov.astype(np.float64), False)
+    X64 = X.astype(np.float64)
+    ref_lq = O.component_log_densities(g_in, X64)
+    _, ref_grad, _ = O.log_density_and_grad(g_in, X64)
+    mapping = np.zeros(N, np.int32); mapping[-1] = K - 1
+    Href, gref = O.stein_ng(g_in, X64, mapping, small[4].astype(np.float64), np.zeros(N), tgrad.astype(np.float64), False, True)
+    assert rel_err(small[0], ref_lq) < LOGDENS_RTOL
+    assert np.max(np.abs(small[0] - ref_lq) / np.maximum(np.abs(ref_lq), 1.0)) < LOGDENS_RTOL        # element-wise
+    assert rel_err(small[1], ref_grad) < NG_RTOL
+    assert rel_err(small[2], Href) < NG_RTOL and rel_err(small[3], gref) < NG_RTOL
+    for a, b in zip(small[:4], general[:4]):
+        assert rel_err(a, b) < 2e-5
