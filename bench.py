@@ -230,6 +230,12 @@ def run_ours(args):
 
     rng.set_seed(1234)
     gmmvi = build(PRIOR_SCALE)
+    use_graph = not args.no_graph
+    if use_graph:
+        # one CUDA graph per iteration (the counterpart of the reference's tf.function around train_iter): the same
+        # kernels and collectives, launched with one call instead of ~170 -- at 8 GPUs a rank's kernels take ~4 ms and
+        # the Python between the launches would otherwise set the pace
+        gmmvi.enable_cuda_graph()
 
     def sync_all():
         if world > 1:
@@ -267,8 +273,8 @@ def run_ours(args):
     # ---- end to end: host noise in, updated mixture out -------------------------------------------
     # Every step copies its own noise shard from pinned host memory and (rank 0) reads the updated mixture back;
     # the copies run on two copy streams so that step i+1's upload and step i's read-back overlap the kernels of
-    # their neighbours (double-buffered noise; the update writes NEW parameter tensors, so step i's result stays
-    # valid while step i+1 computes).  All of it is inside the timed region.
+    # their neighbours (double-buffered noise; the result is read back from a per-step snapshot).  All of it is inside
+    # the timed region.
     hostE = [torch.empty((N, D), dtype=torch.float32).pin_memory().normal_() for _ in range(2)]
     devE = [torch.empty((N, D), dtype=torch.float32, device=dev) for _ in range(2)]
     read_back = rank == 0
@@ -294,9 +300,12 @@ def run_ours(args):
                 upload(i + 1)
             cur.wait_event(up[i])
             gmmvi.train_iter(noise=devE[i % 2])
+            if read_back:
+                # a graph replay updates the mixture in place (static buffers): read back from a snapshot taken on the
+                # compute stream (134 MB device copy, ~0.05 ms) so that the next step does not race the D2H copy
+                lw, mu, ch = (t.clone() for t in (gmmvi.model.log_weights, gmmvi.model.means, gmmvi.model.chol_cov))
             done[i].record(cur)
             if read_back:
-                lw, mu, ch = gmmvi.model.log_weights, gmmvi.model.means, gmmvi.model.chol_cov
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(done[i])
                     out_w.copy_(lw, non_blocking=True)
@@ -417,7 +426,7 @@ def run_ours(args):
                                   f"component update sharded + all-gather",
                    "l2": "working set per step (~1.2 GB: [K,N] densities, [K,D,D] factors) exceeds the 126 MB L2",
                    "pairs_per_sec_full_iteration": N_total * K / (ms_per_step * 1e-3),
-                   "dense_variant_iterations_per_sec": dense, "finite": finite,
+                   "dense_variant_iterations_per_sec": dense, "finite": finite, "cuda_graph": use_graph,
                    "kl_evaluations_per_component": kl_evals_stats},
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
@@ -480,6 +489,233 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (C1 - C4) through the reference-facing runner: python bench.py --config C1
+# ------------------------------------------------------------------------------------------------
+CONFIG_DOC = {
+    "C1": "examples/5_samtron_20D_student-T.py: SAMTRON, 20-D Student-t mixture target, 45 initial components (+1 / 60 "
+          "iterations), 200 samples per component, no reuse",
+    "C2": "examples/6_samtron_planar4.py: SAMTRON, 10-link planar robot with 4 goals, 100 initial components (+1 per "
+          "iteration, del_iters 10), 100 samples per component",
+    "C3": "synthetic 100-D 10-mode GMM target, 50 full-covariance components, 4096 samples / iteration (mixture-based "
+          "selector), MORE + trust-region weights; N < F = 5151 features: rank deficient, as SURVEY.md warns",
+    "C3w": "C3 with 12288 samples / iteration (N > 2 F: a well-posed regression)",
+    "C4d": "synthetic 200-D Student-t mixture, 256 DIAGONAL components, 64 samples per component (16384 / iteration), "
+           "Stein + iBLR, fixed stepsize 1e-4",
+    "C4f": "C4 with full covariances",
+}
+
+
+def build_config_runner(name, use_graph=True):
+    from gmmvi_b200.configs import get_default_algorithm_config, get_default_experiment_config, update_config
+    from gmmvi_b200.gmmvi_runner import GmmviRunner
+    rc = {"log_metrics_interval": 10 ** 9, "use_cuda_graph": use_graph}
+    if name in ("C1", "C2"):
+        if name == "C1":
+            exp, over = "stm20", {"sample_selector_config": {"desired_samples_per_component": 200,
+                                                            "ratio_reused_samples_to_desired": 0.0},
+                                  "model_initialization": {"num_initial_components": 45}}
+        else:
+            exp, over = "planar_robot_4", {"num_component_adapter_config": {"del_iters": 10, "add_iters": 1},
+                                           "sample_selector_config": {"desired_samples_per_component": 100,
+                                                                      "ratio_reused_samples_to_desired": 0.0},
+                                           "model_initialization": {"num_initial_components": 100}}
+        algo = update_config(get_default_algorithm_config("SAMTRON"), over)
+        config = update_config(update_config(get_default_experiment_config(exp), {"start_seed": 1}), algo)
+        config["gmmvi_runner_config"] = rc
+        return GmmviRunner.build_from_config(config), config
+    from gmmvi_b200 import rng as grng
+    grng.set_seed(1)
+    if name in ("C3", "C3w"):
+        from gmmvi_b200.experiments.target_distributions.gmm import make_target
+        D, K, target, codeword, diag, prior_scale, initial_cov = 100, 50, make_target(100), "ZEPTFOX", False, 31.63, 1.0
+        over = {"sample_selector_config": {"desired_samples_per_component": 4096 if name == "C3" else 12288,
+                                           "ratio_reused_samples_to_desired": 0.0},
+                "component_stepsize_adapter_config": {"initial_stepsize": 0.01}}
+    else:
+        from gmmvi_b200.experiments.target_distributions.student_t_mixture import make_target
+        D, K, target, codeword, diag, prior_scale, initial_cov = (200, 256, make_target(200, False, device="cuda"), "SEMYFUX",
+                                                                  name == "C4d", 100.0, 300.0)
+        over = {"sample_selector_config": {"desired_samples_per_component": 64, "ratio_reused_samples_to_desired": 0.0},
+                "component_stepsize_adapter_config": {"initial_stepsize": 1e-4}}
+    algo = update_config(get_default_algorithm_config(codeword), over)
+    config = update_config({"start_seed": 1, "use_sample_database": False, "max_database_size": 10000000, "temperature": 1.0,
+                            "model_initialization": {"use_diagonal_covs": diag, "num_initial_components": K,
+                                                     "prior_mean": 0.0, "prior_scale": prior_scale,
+                                                     "initial_cov": initial_cov},
+                            "gmmvi_runner_config": rc}, algo)
+    config["target_fn"] = target
+    return GmmviRunner.build_from_config(config), config
+
+
+def cpu_baseline_config(name, runner, config, iters):
+    """The oracle (restated reference, NumPy fp32) iterating the SAME configuration from the device's current mixture on
+    the host cores: 1 warm-up + `iters` timed iterations, median.  Nothing is extrapolated at these sizes."""
+    import oracle as O
+    dt = np.float32
+    g = runner.gmmvi
+    m = g.model
+    diag = bool(m.diagonal_covs)
+    f = lambda t: t.detach().cpu().numpy().astype(dt)
+    nca = config["num_component_adapter_config"]
+    H = 10000 if "del_iters" not in nca else max(2 * max(2, nca["del_iters"]) + 8, 64)     # runner: 10000 (quirk 17); a
+    # shorter window that still covers del_iters keeps the host copy of the history from dominating the CPU figure
+    og = O.OracleGMM(f(m.log_weights), f(m.means), f(m.chol_cov), diag,
+                     initial_stepsize=float(config["component_stepsize_adapter_config"]["initial_stepsize"]),
+                     initial_regularizer=float(config["ng_estimator_config"].get("initial_l2_regularizer", 1e-12)),
+                     max_reward_history_length=H)
+    og.stepsizes = f(m.stepsizes)
+    tgt = g.sample_selector.target_distribution
+    tname = type(tgt).__name__
+    if tname == "StudentTMixture_LNPDF":
+        target = O.student_t_mixture_target(tgt.target_weights.numpy(), tgt.target_means.numpy(), tgt.target_covs.numpy(),
+                                            tgt.alpha, dt)
+    elif tname == "PlanarRobot":
+        target = O.planar_robot_target(tgt._num_dimensions, tgt._num_goals, dt=dt)
+    else:
+        target = O.gmm_target(tgt.target_weights.numpy(), tgt.target_means.numpy(), tgt.target_covs.numpy(), dt)
+    D = m.num_dimensions
+    keep = bool(config["use_sample_database"])
+    db = O.OracleSampleDB(D, diag, keep, config["max_database_size"] if keep else None, dt)
+    sel = config["sample_selector_config"]
+    cs_type = config["component_stepsize_adapter_type"]
+    cs_cfg = {k: v for k, v in config["component_stepsize_adapter_config"].items() if k != "initial_stepsize"}
+    if cs_type == "decaying":
+        cs_cfg["initial_stepsize"] = config["component_stepsize_adapter_config"]["initial_stepsize"]
+    ws_cfg = config["weight_stepsize_adapter_config"]
+    wad = None
+    if config["weight_stepsize_adapter_type"] == "improvement_based":
+        wad = O.ImprovementBasedWeightStepsize(ws_cfg["initial_stepsize"], ws_cfg["min_stepsize"], ws_cfg["max_stepsize"],
+                                               ws_cfg["stepsize_inc_factor"], ws_cfg["stepsize_dec_factor"], dt=dt)
+    elif config["weight_stepsize_adapter_type"] == "decaying":
+        wad = O.DecayingWeightStepsize(ws_cfg["initial_stepsize"], ws_cfg["annealing_exponent"], dt=dt)
+    cfg = O.IterationConfig(
+        sample_selector=config["sample_selector_type"], desired_samples_per_component=sel["desired_samples_per_component"],
+        ratio_reused_samples_to_desired=sel["ratio_reused_samples_to_desired"], ng_estimator=config["ng_estimator_type"],
+        only_use_own_samples=config["ng_estimator_config"]["only_use_own_samples"],
+        ng_self_normalized=config["ng_estimator_config"]["use_self_normalized_importance_weights"],
+        updater=config["ng_based_updater_type"], component_stepsize=cs_type,
+        component_stepsize_cfg={"min_stepsize": cs_cfg.get("min_stepsize"), "max_stepsize": cs_cfg.get("max_stepsize"),
+                                "inc": cs_cfg.get("stepsize_inc_factor"), "dec": cs_cfg.get("stepsize_dec_factor")}
+        if cs_type == "improvement-based" else cs_cfg,
+        weight_updater=config["weight_updater_type"],
+        weight_self_normalized=config["weight_updater_config"]["use_self_normalized_importance_weights"],
+        weight_stepsize=float(ws_cfg["initial_stepsize"]), temperature=float(config["temperature"]))
+    adapter = None
+    if config["num_component_adapter_type"] == "adaptive":
+        a = {k: nca[k] for k in ("del_iters", "add_iters", "max_components", "thresholds_for_add_heuristic",
+                                 "min_weight_for_del_heuristic", "num_database_samples")}
+        mi = config["model_initialization"]
+        adapter = O.VipsComponentAdaptation(og, db, mi["prior_mean"], mi["initial_cov"], **a)
+    rs = np.random.default_rng(0)
+    noise_fn = lambda k, D_, n: rs.standard_normal((D_, n)).astype(dt)
+    uniform_fn = lambda n: rs.uniform(size=n).astype(dt)
+    times = []
+    for it in range(iters + 1):
+        t0 = time.perf_counter()
+        O.train_iter(og, db, target, cfg, noise_fn, wad, uniform_fn)
+        if adapter is not None:
+            adapter.adapt_number_of_components(g.num_updates + it + 1, lambda: float(rs.uniform()),
+                                               lambda n: rs.permutation(n), target)
+        times.append(time.perf_counter() - t0)
+    sec = float(np.median(times[1:]))
+    return {"value": 1.0 / sec, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port", "extrapolated": False,
+            "sample": f"oracle (restated reference, NumPy/OpenBLAS fp32), the full configuration from the device's current "
+                      f"mixture (K={og.num_components}): 1 warm-up + median of {iters} iteration(s) = {sec * 1e3:.1f} ms",
+            "sec_per_iter": sec}
+
+
+def run_config(args):
+    import torch
+    from gmmvi_b200 import ops
+    name = args.config
+    torch.cuda.set_device(0)
+    runner, config = build_config_runner(name, not args.no_graph)
+    g = runner.gmmvi
+    warm = max(args.warmup, 12)              # past the first component additions / the deletion window of C1 / C2
+    for n in range(warm):
+        g.train_iter()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    l0 = ops.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g.train_iter()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ops.kernel_launches() - l0
+    clk = clocks.stop()
+    # end to end: the reference-facing call of the examples, GmmviRunner.iterate_and_log (a device synchronisation and the
+    # read-back of the cheap metrics every iteration)
+    t0 = time.perf_counter()
+    for n in range(args.steps):
+        out = runner.iterate_and_log(warm + args.steps + n)
+    e2e_s = time.perf_counter() - t0
+    m = g.model
+    K, D = m.num_components, m.num_dimensions
+    N = int(g.sample_db.samples.shape[0]) if not g.sample_db.keep_samples else None
+    sel = config["sample_selector_config"]
+    n_iter = sel["desired_samples_per_component"] * (K if config["sample_selector_type"] == "component-based" else 1)
+    finite = bool(torch.isfinite(m.means).all() and torch.isfinite(m.chol_cov).all())
+    # dominant sample x component kernel alone: one component_log_densities pass over an iteration's worth of samples
+    X = m.sample(n_iter)[0].contiguous()
+    m.component_log_densities(X)
+    torch.cuda.synchronize()
+    ops.clear_caches()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        if m.diagonal_covs:
+            ops.logdens_diag(X, m.means, m.chol_cov)
+        else:
+            linv, _, cst = m.prepared(need_prec=False)
+            ops.logdens_full(X, m.means, linv, cst, memo=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ld_ms = e0.elapsed_time(e1) / reps
+    pairs = float(n_iter) * K
+    hbm, bf16, _, how = measured_peaks()
+    if m.diagonal_covs or D <= 64:
+        # bandwidth-shaped: SURVEY.md section 8(d) bytes model 4 (N D + 2 K D + K + K N) (full: K D^2 / 2 factor entries)
+        par = 2 * K * D if m.diagonal_covs else K * D * (D + 1) // 2 + K * D
+        alg_bytes = 4.0 * (n_iter * D + par + K + K * n_iter)
+        ach = alg_bytes / (ld_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "algorithmic_bytes": alg_bytes, "peak_source": f"{how} HBM copy bandwidth"}
+    else:
+        flop = pairs * (D * D + 4 * D)
+        ach = flop / (ld_ms * 1e-3) / 1e12
+        kind = ops.logdens_kernel_kind(D)
+        peak = bf16 if kind == "h16" else 63.98       # SIMT fp32: measured cuBLAS fp32 (profiles/r02_measured_peaks_tf32_fp64.json)
+        roof = {"bound": "tensor" if kind == "h16" else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "algorithmic_flop_per_pair": D * D + 4 * D,
+                "peak_source": f"{how} bf16 burst" if kind == "h16" else "measured cuBLAS fp32 SIMT GEMM"}
+    roof.update({"kernel": "component log-density: " + ("gvi::logdens_diag_kernel" if m.diagonal_covs else
+                                                         ("gvi::sd::logdens_small_kernel" if D <= 32 else ops.logdens_kernel_name(D))),
+                 "launch_ms": ld_ms, "pairs_per_launch": pairs})
+    cpu = None if args.no_cpu else cpu_baseline_config(name, runner, config, 3 if name in ("C1", "C2") else 1)
+    line = {"metric": "gmmvi_iterations_per_sec", "value": args.steps / (ms * 1e-3), "unit": "iterations/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {CONFIG_DOC[name]}", "components": K, "dim": D,
+                       "samples_per_iteration": n_iter, "finite": finite,
+                       "cuda_graph": bool(g._graph_enabled and g._graph),
+                       "l2": "iteration working set is rewritten every step; no buffer is reused across timed steps"},
+            "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3), "roofline": roof,
+            "e2e": {"value": args.steps / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 8,
+                    "note": "GmmviRunner.iterate_and_log: the call of the reference's examples; the samples are drawn on the "
+                            "device by the algorithm itself (no host input), every iteration ends with a device "
+                            "synchronisation and the read-back of the cheap metrics"},
+            "gpu_launches": launches, "clocks": clk}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,13 +727,18 @@ def main():
     ap.add_argument("--per-comp", type=int, default=PER_COMP)
     ap.add_argument("--cpu-sample-per-comp", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C3w", "C4d", "C4f", "C5"],
+                    help="BASELINE.json configuration; C5 (default) is the headline stress configuration")
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the iteration kernel by kernel instead of as a CUDA graph")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-single-GPU check at N > 1")
     ap.add_argument("--parity-iters", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "C5":
+        run_config(args)
     else:
         run_ours(args)
 

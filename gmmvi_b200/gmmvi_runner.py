@@ -15,8 +15,10 @@ from .optimization.gmmvi import GMMVI
 
 
 class GmmviRunner:
-    def __init__(self, config, log_metrics_interval, device="cuda"):
-        """gmmvi_runner.py:34-61."""
+    def __init__(self, config, log_metrics_interval, device="cuda", use_cuda_graph=True):
+        """gmmvi_runner.py:34-61.  `use_cuda_graph` (gmmvi_runner_config, default on): run the iteration as one captured
+        CUDA graph whenever the configuration allows it -- what the reference's tf.function around train_iter
+        (optimization/gmmvi.py:99-103) does for TensorFlow; results are identical to op-by-op iterations."""
         if "seed" not in config.keys():
             config["seed"] = config["start_seed"]
         rng.set_seed(config["seed"])
@@ -25,6 +27,11 @@ class GmmviRunner:
         self.log_metrics_interval = log_metrics_interval
         target_distribution, initial_model = init_experiment(self.config, device=device)
         self.gmmvi = GMMVI.build_from_config(self.config, target_distribution, initial_model)
+        if use_cuda_graph:
+            try:
+                self.gmmvi.enable_cuda_graph()
+            except NotImplementedError:          # sample reuse / mixture-based selector: op-by-op iterations
+                pass
         if "mmd_evaluation_config" in config.keys():
             # gmmvi_runner.py:45-54; `sample_dir` is looked up next to this file like in the reference, then as given
             from .experiments.evaluation.mmd import MMD

@@ -30,9 +30,10 @@ class GMMVI:
         self.weight_stepsize_adapter = weight_stepsize_adapter
         self.weight_updater = weight_updater
         self.num_updates = 0
-        self._graph = None             # optimization/graphed.GraphedIteration when CUDA-graph iterations are enabled
+        self._graph = None             # {'rng' | 'noise': optimization/graphed.GraphedIteration} when graphs are enabled
         self._graph_enabled = False
-        self._graph_stable = 0
+        self._graph_stable = 0         # eager iterations at the current number of components
+        self._graph_patience = 1       # eager iterations required before a capture (backs off when K keeps changing)
 
     @staticmethod
     def build_from_config(config: dict, target_distribution, model):
@@ -74,26 +75,43 @@ class GMMVI:
         from .graphed import GraphedIteration
         if enabled:
             GraphedIteration(self)          # raises when the configuration cannot be captured
-        self._graph_enabled, self._graph, self._graph_stable = bool(enabled), None, 0
+        self._graph_enabled, self._graph, self._graph_stable, self._graph_K = bool(enabled), None, 0, None
 
-    def _graphed_step(self):
+    def _graphed_step(self, noise=None):
+        """Replay (or capture, then replay) the graph of the current number of components -> True; False when this
+        iteration has to run eagerly (first iteration at a new K).  Two graphs are kept: one that draws its noise from
+        the device generator and one that reads injected noise from a static buffer the caller's tensor is copied to."""
         from .graphed import GraphedIteration
         K = self.model.num_components
-        if self._graph is not None and self._graph.num_components != K:
-            self._graph, self._graph_stable = None, 0
-        if self._graph is None:
-            if self._graph_stable < 1:          # first iteration at this K runs eagerly (also warms every kernel up)
+        slot = "noise" if noise is not None else "rng"
+        graphs = self._graph if isinstance(self._graph, dict) else {}
+        if K != getattr(self, "_graph_K", None):
+            # a capture costs tens of launches' worth of host time: if the number of components changes again before the
+            # graph has paid for itself, wait longer before the next capture (examples/6 adds a component EVERY
+            # iteration and ends up never capturing)
+            if getattr(self, "_graph_K", None) is not None:
+                replays = max((g.replays for g in graphs.values()), default=0)
+                self._graph_patience = 1 if replays >= 16 else min(2 * self._graph_patience + 1, 63)
+            graphs, self._graph_stable, self._graph_K = {}, 0, K
+        if noise is not None and slot in graphs and graphs[slot].noise_buffer.shape != noise.shape:
+            del graphs[slot]
+        self._graph = graphs
+        if slot not in graphs:
+            if self._graph_stable < self._graph_patience:      # first iteration(s) at this K run eagerly (warm-up)
                 self._graph_stable += 1
                 return False
-            self._graph = GraphedIteration(self).capture()
-        self._graph.replay()
+            buf = None if noise is None else torch.empty_like(noise, memory_format=torch.contiguous_format)
+            graphs[slot] = GraphedIteration(self, noise_buffer=buf).capture()
+        if noise is not None:
+            graphs[slot].noise_buffer.copy_(noise)
+        graphs[slot].replay()
         return True
 
     def train_iter(self, noise=None, adaptation_draws=None):
         """optimization/gmmvi.py:146-161.  `noise` ([N,D] standard-normal draws, optional) replaces the device
         generator for this iteration's samples (used by the parity tests and the end-to-end benchmark);
         `adaptation_draws` = (uniform, permutation) does the same for the two random draws of a component addition."""
-        if not (self._graph_enabled and noise is None and self._graphed_step()):
+        if not (self._graph_enabled and self._graphed_step(noise)):
             samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads = \
                 self.sample_selector.select_samples(**({} if noise is None else {"noise": noise}))
             self._run_updates(samples, mapping, sample_dist_densities, target_lnpdfs, target_lnpdf_grads)

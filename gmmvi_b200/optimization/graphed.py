@@ -50,6 +50,7 @@ class GraphedIteration:
         self.noise_buffer = noise_buffer            # static [N, D] buffer the caller fills before each replay (optional)
         self.graph = None
         self.num_components = None
+        self.replays = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def _install(self, gmm, slots, statics, prep):
@@ -80,6 +81,28 @@ class GraphedIteration:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         written0 = g.sample_db.num_samples_written
+        kernels0, calls0 = ops.KERNELS, ops.LAUNCHES
+        # Python's cyclic collector must not run inside the capture: it may destroy an older, unreachable CUDA graph
+        # (GMMVI <-> GraphedIteration is a cycle) and freeing its memory pool invalidates the capture in progress.
+        import gc
+        gc_was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            self._capture(g, gmm, slots, statics, prep, full)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+        ops.clear_caches()
+        # kernels one replay launches (ops.kernel_launches() stays a count of what ran on the device)
+        self.kernels, self.calls = ops.KERNELS - kernels0, ops.LAUNCHES - calls0
+        ops.KERNELS, ops.LAUNCHES = kernels0, calls0
+        self.samples_per_iteration = g.sample_db.num_samples_written - written0
+        # the capture run executed nothing: the first replay performs the iteration that was captured
+        g.sample_db.num_samples_written = written0
+        return self
+
+    def _capture(self, g, gmm, slots, statics, prep, full):
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             rng.begin_device_mode(self.counter)
             try:
@@ -97,11 +120,6 @@ class GraphedIteration:
                 if new is not s:
                     s.copy_(new)
             self._install(gmm, slots, statics, prep)
-        ops.clear_caches()
-        self.samples_per_iteration = g.sample_db.num_samples_written - written0
-        # the capture run executed nothing: the first replay performs the iteration that was captured
-        g.sample_db.num_samples_written = written0
-        return self
 
     def _body(self):
         g = self.gmmvi
@@ -121,7 +139,10 @@ class GraphedIteration:
     def replay(self):
         g = self.gmmvi
         self.graph.replay()
+        self.replays += 1
         ops.clear_caches()                  # the replay rewrote the static buffers behind the caches' keys
+        ops.KERNELS += self.kernels
+        ops.LAUNCHES += self.calls
         rng.advance(self.draws)
         g.num_updates += 1
         if self.payload is not None:

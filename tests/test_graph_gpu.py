@@ -53,7 +53,7 @@ def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag):
     for _ in range(iters):
         graphed.train_iter()
     torch.cuda.synchronize()
-    assert graphed._graph is not None and graphed._graph.graph is not None       # iterations 2.. were replays
+    assert graphed._graph and graphed._graph["rng"].graph is not None           # iterations 2.. were replays
     assert graphed.num_updates == eager.num_updates == iters
     assert graphed.sample_db.num_samples_written == eager.sample_db.num_samples_written
     a, b = _state(eager), _state(graphed)
@@ -61,6 +61,23 @@ def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag):
         assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
     # the database holds the last iteration's samples in both modes
     assert torch.equal(eager.sample_db.samples, graphed.sample_db.samples)
+
+
+def test_graph_with_injected_noise_equals_eager():
+    """train_iter(noise=...) in graph mode: the noise is copied into the graph's static buffer before the replay."""
+    K, D, desired, iters = 8, 32, 64, 5
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    noise = [torch.randn((K * desired, D), device="cuda", generator=gen) for _ in range(iters)]
+    eager, graphed = _fixed(K, D, desired), _fixed(K, D, desired)
+    graphed.enable_cuda_graph()
+    for e in noise:
+        eager.train_iter(noise=e)
+        graphed.train_iter(noise=e.clone())
+    torch.cuda.synchronize()
+    assert "noise" in graphed._graph
+    a, b = _state(eager), _state(graphed)
+    for n in a:
+        assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
 
 
 def test_graph_mode_follows_component_adaptation():
@@ -75,10 +92,9 @@ def test_graph_mode_follows_component_adaptation():
                               "sample_selector_config": {"desired_samples_per_component": 50, "ratio_reused_samples_to_desired": 0.0},
                               "model_initialization": {"num_initial_components": 8}})
         config = update_config(update_config(get_default_experiment_config("stm20"), {"start_seed": 5}), algo)
-        config["gmmvi_runner_config"] = {"log_metrics_interval": 10 ** 9}
+        config["gmmvi_runner_config"] = {"log_metrics_interval": 10 ** 9, "use_cuda_graph": graph}
         runner = GmmviRunner.build_from_config(config)
-        if graph:
-            runner.gmmvi.enable_cuda_graph()
+        assert runner.gmmvi._graph_enabled == graph
         ks = []
         for n in range(18):
             runner.iterate_and_log(n)

@@ -36,7 +36,7 @@ def _build(K, D, desired, dev):
     return GMMVI.build_from_config(cfg, target, GmmWrapper.build_from_config(model, cfg))
 
 
-def _worker(rank, world, port, K, D, desired, iters, out_dir):
+def _worker(rank, world, port, K, D, desired, iters, out_dir, graph=False):
     import torch.distributed as dist
     from gmmvi_b200 import rng
     from gmmvi_b200.distributed import ShardContext
@@ -46,32 +46,39 @@ def _worker(rank, world, port, K, D, desired, iters, out_dir):
     rng.set_seed(77)
     g = _build(K, D, desired, torch.device("cuda", rank))
     g.enable_sharding(ShardContext(rank, world))
+    if graph:
+        g.enable_cuda_graph()          # the NCCL collectives are captured with the kernels
     for _ in range(iters):
         g.train_iter()
     torch.cuda.synchronize()
+    assert not graph or (g._graph and g._graph["rng"].graph is not None)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=g.model.means.cpu().numpy(),
              chol=g.model.chol_cov.cpu().numpy(), logw=g.model.log_weights.cpu().numpy(),
              n_local=g.sample_db.samples.shape[0])
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,K,D,desired", [(2, 8, 32, 64),        # SIMT kernels, components divide evenly
-                                               (2, 8, 96, 160),       # tensor-core kernels (D >= 96), 640 rows / rank
-                                               (2, 7, 96, 128),       # K not divisible: all-reduce + replicated update
-                                               (4, 8, 128, 128),
-                                               (8, 16, 96, 128)])
-def test_sharded_iteration_matches_single_gpu(tmp_path, world, K, D, desired):
+@pytest.mark.parametrize("world,K,D,desired,graph", [
+    (2, 8, 32, 64, False),        # small-dimension kernels, components divide evenly
+    (2, 8, 96, 160, False),       # tensor-core kernels (D >= 96), 640 rows / rank
+    (2, 7, 96, 128, False),       # K not divisible: all-reduce + replicated update
+    (2, 8, 96, 160, True),        # the same iteration as ONE CUDA graph per rank, NCCL collectives captured
+    (2, 7, 96, 128, True),
+    (4, 8, 128, 128, False),
+    (8, 16, 96, 128, False),
+    (8, 16, 96, 128, True)])
+def test_sharded_iteration_matches_single_gpu(tmp_path, world, K, D, desired, graph):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from gmmvi_b200 import rng
-    iters = 3
+    iters = 4 if graph else 3
     rng.set_seed(77)
     ref = _build(K, D, desired, torch.device("cuda", 0))
     for _ in range(iters):
         ref.train_iter()
     torch.cuda.synchronize()
-    mp.spawn(_worker, args=(world, _free_port(), K, D, desired, iters, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), K, D, desired, iters, str(tmp_path), graph), nprocs=world, join=True)
     parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     assert sum(int(p["n_local"]) for p in parts) == K * desired
     for p in parts:          # every rank holds the same replicated model ...
@@ -81,5 +88,5 @@ def test_sharded_iteration_matches_single_gpu(tmp_path, world, K, D, desired):
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     e_m, e_c = rel(parts[0]["means"], ref.model.means.cpu().numpy()), rel(parts[0]["chol"], ref.model.chol_cov.cpu().numpy())
     e_w = rel(np.exp(parts[0]["logw"]), ref.model.weights.cpu().numpy())
-    print(f"PARITY sharded world={world} K={K} D={D}: means {e_m:.2e} chol {e_c:.2e} weights {e_w:.2e}")
+    print(f"PARITY sharded world={world} K={K} D={D} graph={graph}: means {e_m:.2e} chol {e_c:.2e} weights {e_w:.2e}")
     assert e_m < 1e-4 and e_c < 1e-4 and e_w < 1e-4
