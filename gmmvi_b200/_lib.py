@@ -50,7 +50,8 @@ _SIGNATURES = {
                                            c_vp]),
     "gvi_stein_finalize_full_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "gvi_stein_finalize_full_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_vp, C.c_size_t, c_vp]),
-    "gvi_stein_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_vp]),
+    "gvi_stein_diag_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "gvi_stein_diag_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_vp, C.c_size_t, c_vp]),
     "gvi_more_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gvi_more_fit_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_i,
                                    c_vp, C.c_size_t, c_vp]),

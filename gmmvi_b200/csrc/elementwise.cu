@@ -35,6 +35,11 @@ int launch_gemm_auto(int transA, int transB, int batch, int M, int N, int Kd, fl
                      long long strideC, float* ws, size_t ws_floats, cudaStream_t st);
 size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
 bool stein_tc_supported(int N, int D);
+int launch_logdens_diag2(const float* X, int N, int D, const float* means, const float* stds, int K, float* lq,
+                         cudaStream_t st);
+size_t stein_diag_workspace_floats(int N, int K, int D);
+int launch_stein_diag2(const float* X, int N, int D, const float* means, const float* stds, const float* W, const float* G,
+                       int K, float* Hneg, float* gneg, float* ws, cudaStream_t st);
 size_t stein_tc_workspace_floats(int N, int K, int D);
 int launch_stein_stats_tc(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
                           const float* G, int K, float* M, float* ws, cudaStream_t st);
@@ -927,6 +932,10 @@ extern "C" int gvi_logdens_diag_f32(const float* X, int N, int D, const float* m
   GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_logdens_diag_f32: bad sizes");
   if (N == 0 || K == 0) return GVI_OK;
   GVI_REQUIRE(X && means && stds && lq, "gvi_logdens_diag_f32: null pointer");
+  if (!(getenv("GMMVI_B200_DIAG_V1"))) {              // second-generation kernel (diag.cu); 1 = shape not supported
+    const int rc2 = launch_logdens_diag2(X, N, D, means, stds, K, lq, (cudaStream_t)stream);
+    if (rc2 != 1) return rc2;
+  }
   const size_t smem = (size_t)32 * D * sizeof(float);
   if (smem > 200 * 1024) {
     set_last_error("gvi_logdens_diag_f32: D=%d too large for the sample tile", D);
@@ -1136,11 +1145,16 @@ extern "C" int gvi_stein_finalize_full_f32(const float* prec, const float* M, in
   return stein_finalize(prec, M, K, D, symmetrize, Hneg, (float*)ws, (cudaStream_t)stream);
 }
 
+extern "C" size_t gvi_stein_diag_workspace(int N, int K, int D) { return stein_diag_workspace_floats(N, K, D) * sizeof(float); }
 extern "C" int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds,
-                                  const float* W, const float* G, int K, float* Hneg, float* gneg, void* stream) {
+                                  const float* W, const float* G, int K, float* Hneg, float* gneg, void* ws,
+                                  size_t ws_bytes, void* stream) {
   GVI_REQUIRE(N >= 0 && D > 0 && K >= 0, "gvi_stein_diag_f32: bad sizes");
   if (K == 0) return GVI_OK;
   GVI_REQUIRE(X && means && stds && W && G && Hneg && gneg, "gvi_stein_diag_f32: null pointer");
+  // with a workspace: two matrix products W [X o G | G] on the GEMM engines (diag.cu); without: the serial kernel
+  if (ws != nullptr && N > 0 && ws_bytes >= gvi_stein_diag_workspace(N, K, D) && !getenv("GMMVI_B200_DIAG_V1"))
+    return launch_stein_diag2(X, N, D, means, stds, W, G, K, Hneg, gneg, (float*)ws, (cudaStream_t)stream);
   dim3 grid(ceil_div(D, 256), K);
   stein_diag_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, means, stds, W, G, Hneg, gneg);
   return check_launch("stein_diag_kernel");

@@ -398,8 +398,10 @@ def stein_diag(X, means, stds, W, G):
     K = means.shape[0]
     Hneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
     gneg = torch.empty((K, D), device=X.device, dtype=torch.float32)
+    nbytes = _lib.lib().gvi_stein_diag_workspace(N, K, D)
+    ws = torch.empty(max(nbytes, 4) // 4, device=X.device, dtype=torch.float32)
     _call("gvi_stein_diag_f32", X.data_ptr(), N, D, means.data_ptr(), stds.data_ptr(), W.data_ptr(), G.data_ptr(), K,
-          Hneg.data_ptr(), gneg.data_ptr(), _stream())
+          Hneg.data_ptr(), gneg.data_ptr(), ws.data_ptr(), nbytes, _stream(), kernels=4)
     return Hneg, gneg
 
 

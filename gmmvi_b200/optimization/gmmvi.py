@@ -34,6 +34,8 @@ class GMMVI:
         self._graph_enabled = False
         self._graph_stable = 0         # eager iterations at the current number of components
         self._graph_patience = 1       # eager iterations required before a capture (backs off when K keeps changing)
+        self._graph_pool = None        # memory pool shared by this object's graphs (optimization/graphed.py)
+        self.graph_captures = 0
 
     @staticmethod
     def build_from_config(config: dict, target_distribution, model):
@@ -102,6 +104,7 @@ class GMMVI:
                 return False
             buf = None if noise is None else torch.empty_like(noise, memory_format=torch.contiguous_format)
             graphs[slot] = GraphedIteration(self, noise_buffer=buf).capture()
+            self.graph_captures += 1
         if noise is not None:
             graphs[slot].noise_buffer.copy_(noise)
         graphs[slot].replay()

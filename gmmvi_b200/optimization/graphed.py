@@ -103,7 +103,24 @@ class GraphedIteration:
         return self
 
     def _capture(self, g, gmm, slots, statics, prep, full):
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        # capture_begin / capture_end by hand instead of the torch.cuda.graph context: the context empties the caching
+        # allocator (a cudaFree of every cached block, ~0.2 s) on every entry, which an adaptive run that captures again
+        # after each change of the number of components cannot afford.  All graphs of one GMMVI share a memory pool.
+        if getattr(g, "_graph_pool", None) is None:
+            g._graph_pool = torch.cuda.graph_pool_handle()
+            g._graph_stream = torch.cuda.Stream(gmm.device)
+        stream = g._graph_stream
+        stream.wait_stream(torch.cuda.current_stream(gmm.device))
+        with torch.cuda.stream(stream):
+            self.graph.capture_begin(pool=g._graph_pool, capture_error_mode="thread_local")
+            try:
+                self._captured_region(g, gmm, slots, statics, prep, full)
+            finally:
+                self.graph.capture_end()
+        torch.cuda.current_stream(gmm.device).wait_stream(stream)
+
+    def _captured_region(self, g, gmm, slots, statics, prep, full):
+        if True:
             rng.begin_device_mode(self.counter)
             try:
                 self.payload = self._body()

@@ -122,9 +122,12 @@ int gvi_stein_stats_full_f32(const float* X, int N, int D, const float* means, c
 size_t gvi_stein_finalize_full_workspace(int K, int D);
 int gvi_stein_finalize_full_f32(const float* prec, const float* M, int K, int D, int symmetrize, float* Hneg, void* ws,
                                 size_t ws_bytes, void* stream);
-/* diagonal: Hneg[k,d] = -sum_n W (x-mu)_d / std_d^2 * G[n,d]   (ng_estimator.py:177-180) */
+/* diagonal: Hneg[k,d] = -sum_n W (x-mu)_d / std_d^2 * G[n,d]   (ng_estimator.py:177-180).  With a workspace of
+ * gvi_stein_diag_workspace(N, K, D) bytes the sums run as two matrix products W [X o G | G] on the GEMM engines (split over
+ * the samples, partial products added in a fixed order); ws = NULL selects the serial per-(component, dimension) kernel. */
+size_t gvi_stein_diag_workspace(int N, int K, int D);
 int gvi_stein_diag_f32(const float* X, int N, int D, const float* means, const float* stds, const float* W,
-                       const float* G, int K, float* Hneg, float* gneg, void* stream);
+                       const float* G, int K, float* Hneg, float* gneg, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- MORE natural-gradient estimator -----------------------------------------------------------
  * Weighted ridge regression on quadratic features of the whitened samples, per component (ng_estimator.py:296-376,

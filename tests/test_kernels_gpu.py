@@ -85,7 +85,8 @@ def test_prepare_and_logdens_full(K, D, N):
     assert rel_err(grad.cpu().numpy(), ref_grad) < NG_RTOL
 
 
-@pytest.mark.parametrize("K,D,N", [(3, 3, 5), (9, 10, 130), (5, 200, 333), (40, 20, 1000)])
+@pytest.mark.parametrize("K,D,N", [(3, 3, 5), (9, 10, 130), (5, 200, 333), (40, 20, 1000), (70, 200, 2111), (13, 33, 257),
+                                   (256, 200, 1024)])
 def test_logdens_diag(K, D, N):
     from gmmvi_b200 import ops
     g, X = make_problem(K, D, N, diag=True)
@@ -191,9 +192,10 @@ def test_stein_full(K, D, N, self_norm):
     assert rel_err(Hneg.cpu().numpy(), Href) < NG_RTOL
 
 
-def test_stein_diag():
+@pytest.mark.parametrize("K,D,N", [(5, 50, 400), (64, 200, 2111), (256, 200, 4096), (3, 7, 50)])
+def test_stein_diag(K, D, N):
+    """(256, 200, ..) is the shape of BASELINE config C4-diagonal; the sums run as split-K matrix products (csrc/diag.cu)."""
     from gmmvi_b200 import ops
-    K, D, N = 5, 50, 400
     g, X = make_problem(K, D, N, seed=7, diag=True)
     g32 = gmm32_of(g)
     g_in = O.OracleGMM(g32.log_weights.astype(np.float64), g32.means.astype(np.float64),
@@ -214,6 +216,16 @@ def test_stein_diag():
     Hneg, gneg = ops.stein_diag(dev(X), dev(g32.means), dev(g32.chol_cov), iw["W"], G)
     assert rel_err(gneg.cpu().numpy(), gref) < NG_RTOL
     assert rel_err(Hneg.cpu().numpy(), Href) < NG_RTOL
+    # the first-generation kernels (serial per (component, dimension)) agree
+    import os
+    os.environ["GMMVI_B200_DIAG_V1"] = "1"
+    try:
+        H1, g1 = ops.stein_diag(dev(X), dev(g32.means), dev(g32.chol_cov), iw["W"], G)
+        lq1 = ops.logdens_diag(dev(X), dev(g32.means), dev(g32.chol_cov))
+    finally:
+        del os.environ["GMMVI_B200_DIAG_V1"]
+    assert rel_err(Hneg.cpu().numpy(), H1.cpu().numpy()) < 2e-5 and rel_err(gneg.cpu().numpy(), g1.cpu().numpy()) < 2e-5
+    assert rel_err(lq.cpu().numpy(), lq1.cpu().numpy()) < 1e-6
 
 
 def _update_problem(K, D, seed, diag=False, last_eta=None):
