@@ -79,15 +79,15 @@ logdens_diag2_kernel(const float* __restrict__ X, int N, int D, int Dp, const fl
       for (int kk = 0; kk < KC; ++kk) {
         if (kk < nk) {
           const float4* p4 = reinterpret_cast<const float4*>(par + kk * Dp + d0);
-          float a = acc[kk];
+          float a0 = acc[kk], a1 = 0.f;                     // two chains: the FMA latency is exposed otherwise
 #pragma unroll
           for (int j = 0; j < DC; j += 2) {
             const float4 p = p4[j >> 1];                    // (mu_j, isg_j, mu_j+1, isg_j+1)
             const float t0 = (p.x - x[j]) * p.y, t1 = (p.z - x[j + 1]) * p.w;
-            a = fmaf(t0, t0, a);
-            a = fmaf(t1, t1, a);
+            a0 = fmaf(t0, t0, a0);
+            a1 = fmaf(t1, t1, a1);
           }
-          acc[kk] = a;
+          acc[kk] = a0 + a1;
         }
       }
     }
@@ -143,7 +143,7 @@ int launch_logdens_diag2(const float* X, int N, int D, const float* means, const
     attr_set = true;
   }
   const int nb = ceil_div(N, TS), kchunks = ceil_div(K, KC);
-  int ysplit = min(kchunks, max(1, ceil_div(148 * 4, nb)));
+  int ysplit = min(kchunks, max(1, ceil_div(148 * 8, nb)));     // >= 8 CTAs (32 warps) per SM
   const int per = ceil_div(kchunks, ysplit);
   ysplit = ceil_div(kchunks, per);
   logdens_diag2_kernel<<<dim3(nb, ysplit), TS, smem, st>>>(X, N, D, Dp, means, stds, K, per, lq);

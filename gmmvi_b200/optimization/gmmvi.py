@@ -94,6 +94,9 @@ class GMMVI:
             if getattr(self, "_graph_K", None) is not None:
                 replays = max((g.replays for g in graphs.values()), default=0)
                 self._graph_patience = 1 if replays >= 16 else min(2 * self._graph_patience + 1, 63)
+            # the retired graphs stay alive until the next capture has begun: the shared memory pool exists only while a
+            # graph uses it
+            self._graph_retired = list(graphs.values()) or getattr(self, "_graph_retired", None)
             graphs, self._graph_stable, self._graph_K = {}, 0, K
         if noise is not None and slot in graphs and graphs[slot].noise_buffer.shape != noise.shape:
             del graphs[slot]
@@ -105,6 +108,7 @@ class GMMVI:
             buf = None if noise is None else torch.empty_like(noise, memory_format=torch.contiguous_format)
             graphs[slot] = GraphedIteration(self, noise_buffer=buf).capture()
             self.graph_captures += 1
+            self._graph_retired = None
         if noise is not None:
             graphs[slot].noise_buffer.copy_(noise)
         graphs[slot].replay()

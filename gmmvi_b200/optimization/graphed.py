@@ -86,8 +86,7 @@ class GraphedIteration:
         # (GMMVI <-> GraphedIteration is a cycle) and freeing its memory pool invalidates the capture in progress.
         import gc
         gc_was_enabled = gc.isenabled()
-        gc.collect()
-        gc.disable()
+        gc.disable()                    # (no gc.collect() here: a full collection costs tens of ms per capture)
         try:
             self._capture(g, gmm, slots, statics, prep, full)
         finally:
@@ -106,8 +105,11 @@ class GraphedIteration:
         # capture_begin / capture_end by hand instead of the torch.cuda.graph context: the context empties the caching
         # allocator (a cudaFree of every cached block, ~0.2 s) on every entry, which an adaptive run that captures again
         # after each change of the number of components cannot afford.  All graphs of one GMMVI share a memory pool.
-        if getattr(g, "_graph_pool", None) is None:
+        live = [x for x in ((g._graph or {}).values() if isinstance(g._graph, dict) else []) if x.graph is not None]
+        live += [x for x in (getattr(g, "_graph_retired", None) or []) if x.graph is not None]
+        if getattr(g, "_graph_pool", None) is None or not live:      # a pool only exists while some graph uses it
             g._graph_pool = torch.cuda.graph_pool_handle()
+        if getattr(g, "_graph_stream", None) is None:
             g._graph_stream = torch.cuda.Stream(gmm.device)
         stream = g._graph_stream
         stream.wait_stream(torch.cuda.current_stream(gmm.device))
