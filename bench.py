@@ -195,6 +195,28 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def shutdown_distributed(gmmvi_objects=()):
+    """Release captured graphs (they hold NCCL kernels) before the process group goes away; a watchdog ends the process
+    if the communicator teardown does not return (seen with graphs alive: the JSON line is already printed)."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    for g in gmmvi_objects:
+        try:
+            g.enable_cuda_graph(False)
+            g._graph_retired = None
+        except Exception:
+            pass
+    gc.collect()
+    torch.cuda.synchronize()
+    if dist.is_available() and dist.is_initialized():
+        sys.stdout.flush()
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -408,8 +430,7 @@ def run_ours(args):
         del g2
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown_distributed([gmmvi])
         return
     cpu = cpu_baseline(K, D, per, args.cpu_sample_per_comp) if (world == 1 and not args.no_cpu) else None
     line = {
@@ -454,9 +475,8 @@ def run_ours(args):
                                 "stages_s": cpu["stages_s"], "extrapolated": True,
                                 "extrapolation": f"sample-proportional stages timed on 1/{cpu['stages_s']['n_scale']:g} "
                                                  "of the samples and scaled linearly"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown_distributed([gmmvi])
 
 
 def run_reference(args):

@@ -350,7 +350,7 @@ logdens_h16_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
       const float f = 1.0f / (pow2_scale(xi + mi) * pow2_scale(tm));
-      if (n < N) lq[(long long)k * N + n] = c - 0.5f * (((s0 + s1) * f) * f);
+      if (n < N) __stcs(lq + (long long)k * N + n, c - 0.5f * (((s0 + s1) * f) * f));     // streaming store: keep X in L2
     }
   } else {
     reg_inc<88>();
@@ -709,7 +709,7 @@ logdens_h16t_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       }
       const float s0 = s01.x + s23.x, s1 = s01.y + s23.y;
       const float f = 1.0f / (pow2_scale(xi + mi) * pow2_scale(tm));
-      if (n < N) lq[(long long)k * N + n] = c - 0.5f * (((s0 + s1) * f) * f);
+      if (n < N) __stcs(lq + (long long)k * N + n, c - 0.5f * (((s0 + s1) * f) * f));     // streaming store: keep X in L2
     }
   } else {
     reg_inc<88>();

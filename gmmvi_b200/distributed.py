@@ -36,20 +36,27 @@ class ShardContext:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
 
-    def all_gather_rows(self, local: torch.Tensor, total_rows: int) -> torch.Tensor:
-        """Concatenate equally sized row blocks of all ranks (rank order) -> [total_rows, ...]."""
+    @staticmethod
+    def _out(out, local, total_rows):
+        shape = (total_rows,) + tuple(local.shape[1:])
+        if out is not None and tuple(out.shape) == shape and out.dtype == local.dtype and out.is_contiguous():
+            return out
+        return torch.empty(shape, device=local.device, dtype=local.dtype)
+
+    def all_gather_rows(self, local: torch.Tensor, total_rows: int, out=None) -> torch.Tensor:
+        """Concatenate equally sized row blocks of all ranks (rank order) -> [total_rows, ...] (into `out` when it fits)."""
         if self.world == 1:
             return local
-        out = torch.empty((total_rows,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        out = self._out(out, local, total_rows)
         dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
         return out
 
-    def all_gather_rows_async(self, local: torch.Tensor, total_rows: int):
+    def all_gather_rows_async(self, local: torch.Tensor, total_rows: int, out=None):
         """Like all_gather_rows, but returns (out, work): the caller must `work.wait()` (a stream dependency, not a
         host block) before the first use of `out`; `work` is None when nothing is in flight."""
         if self.world == 1:
             return local, None
-        out = torch.empty((total_rows,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        out = self._out(out, local, total_rows)
         work = dist.all_gather_into_tensor(out, local.contiguous(), group=self.group, async_op=True)
         return out, work
 

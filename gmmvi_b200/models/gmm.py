@@ -29,6 +29,7 @@ class GMM:
         self._prepared = None          # (version, linv, prec, cst) for full covariances
         self._chol_work = None         # in-flight all-gather of chol_cov (sharded component update)
         self._local_chol = None        # (version, a, b, chol[a:b]) of the most recent sharded update
+        self._static_out = None        # {"chol" | "linv" | "prec" | "cst": buffer} a graph runner wants results written to
         self.log_weights = log_weights
         self._means = means
         self._chol_cov = chol_covs
@@ -69,6 +70,7 @@ class GMM:
         (success, eta, KL) that travel with the small gather; returns them gathered, as float32 [K] each."""
         K = self.num_components
         shard = self.shard
+        so = self._static_out or {}
         if not self.diagonal_covs:
             l_loc, _, c_loc = ops.prepare_full(chol_local, want_prec=False)[:3]
         cols = [means_local] + ([c_loc.unsqueeze(1)] if not self.diagonal_covs else []) \
@@ -76,13 +78,14 @@ class GMM:
         packed = shard.all_gather_rows(torch.cat(cols, dim=1).contiguous(), K)
         D = self.num_dimensions
         self.means = packed[:, :D].contiguous()
-        chol_full, chol_work = shard.all_gather_rows_async(chol_local, K)
+        chol_full, chol_work = shard.all_gather_rows_async(chol_local, K, out=so.get("chol"))
         self.chol_cov = chol_full               # (the setter waits for a previous in-flight gather)
         self._chol_work = chol_work
         self._local_chol = (self._version, a, b, chol_local)
         c = D
         if not self.diagonal_covs:
-            linv = shard.all_gather_rows(l_loc, K)
+            linv = shard.all_gather_rows(l_loc, K, out=so.get("linv"))
+            ops.invalidate_split(linv)
             self._prepared = (self._version, linv, None, packed[:, c].contiguous())
             c += 1
         return [packed[:, c + i].contiguous() for i in range(len(extras_local))]
@@ -113,19 +116,26 @@ class GMM:
         K D^2 floats) the first time a caller asks for them (`need_prec`)."""
         if self._prepared is None or self._prepared[0] != self._version:
             rng_ = self.shard.component_range(self.num_components) if self.shard is not None else None
+            so = self._static_out or {}
             if rng_ is None:
-                linv, prec, cst, _ = ops.prepare_full(self.chol_cov, want_prec=True)
+                linv, prec, cst, _ = ops.prepare_full(self.chol_cov, want_prec=True,
+                                                      out=(so.get("linv"), so.get("prec"), so.get("cst")))
+                ops.invalidate_split(linv)
+                ops.invalidate_split(prec)
             else:       # components sharded over the ranks
                 a, b = rng_
                 K = self.num_components
                 l_loc, _, c_loc = ops.prepare_full(self.local_chol(a, b), want_prec=False)[:3]
-                linv = self.shard.all_gather_rows(l_loc, K)
+                linv = self.shard.all_gather_rows(l_loc, K, out=so.get("linv"))
+                ops.invalidate_split(linv)
                 cst = self.shard.all_gather_rows(c_loc, K)
                 prec = None
             self._prepared = (self._version, linv, prec, cst)
         if need_prec and self._prepared[2] is None:
             v, linv, _, cst = self._prepared
-            self._prepared = (v, linv, ops.bgemm(linv, linv, transA=True), cst)       # P = L^-T L^-1
+            prec = ops.bgemm(linv, linv, transA=True, out=(self._static_out or {}).get("prec"))       # P = L^-T L^-1
+            ops.invalidate_split(prec)
+            self._prepared = (v, linv, prec, cst)
         return self._prepared[1:]
 
     # ---- abstract per-family pieces ---------------------------------------------------------------

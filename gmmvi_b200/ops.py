@@ -56,8 +56,66 @@ _H16_CACHE = []         # [(key, linv, hi, lo, tmax)]
 _ABSMAX_CACHE = []      # [(key, tensor, out)]
 
 
+# Split operands of STATIC parameter buffers (a CUDA-graph runner's, optimization/graphed.py):
+# {source address: [hi, lo, tmax, valid, C-ABI call]}.  The split of such a buffer is written into its registered operand
+# buffers, and while `valid` is set (the operands were produced from the buffer's current content) it is not recomputed;
+# whoever rewrites the buffer calls invalidate_split().
+_SPLIT_STATIC = {}
+_SPLIT_CALL = {"lower": "gvi_split_h16_f32", "full": "gvi_split_h16_full_f32"}
+
+
+def split_registered(src):
+    return _SPLIT_STATIC.get(src.data_ptr())
+
+
+def register_split_buffers(src, kind="lower", valid=False):
+    """Allocate operand buffers for the static tensor `src` [K, D, D] (kind: "lower" = inverse factors, "full" =
+    precisions); no-op when the tensor-core kernels do not take this dimension."""
+    K, D, _ = src.shape
+    lib = _lib.lib()
+    ok = lib.gvi_logdens_full_h16_supported(int(D)) if kind == "lower" else lib.gvi_mixture_grad_full_h16_supported(int(D))
+    if not (USE_TENSOR_CORES and ok):
+        return None
+    Dp = lib.gvi_h16_padded_dim(D)
+    hi = torch.empty((K, Dp, Dp), device=src.device, dtype=torch.float16)
+    e = [hi, torch.empty_like(hi), torch.empty(K, device=src.device, dtype=torch.float32), bool(valid), _SPLIT_CALL[kind]]
+    _SPLIT_STATIC[src.data_ptr()] = e
+    return e
+
+
+def invalidate_split(src):
+    e = _SPLIT_STATIC.get(src.data_ptr())
+    if e is not None:
+        e[3] = False
+
+
+def clear_split_registry():
+    _SPLIT_STATIC.clear()
+
+
+def _split_static(src):
+    e = _SPLIT_STATIC.get(src.data_ptr())
+    if e is None:
+        return None
+    K, D, _ = src.shape
+    if e[0].shape[0] != K:
+        return None
+    if not e[3]:
+        _call(e[4], src.data_ptr(), K, D, e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(), _stream())
+        e[3] = True
+    return e[0], e[1], e[2]
+
+
+def split_static_now(src):
+    """Compute the registered operands of `src` if they are not valid (eagerly, before a capture)."""
+    _split_static(src)
+
+
 def split_h16(linv):
     """Zero-padded, power-of-two scaled fp16 (hi, lo) copies of the inverse Cholesky factors + tmax[K]."""
+    st = _split_static(linv)
+    if st is not None:
+        return st
     key = (linv.data_ptr(), linv._version, tuple(linv.shape))
     for k_, _, hi, lo, tmax in _H16_CACHE:
         if k_ == key:
@@ -125,13 +183,19 @@ def _call(name, *args, kernels=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def prepare_full(chol: torch.Tensor, want_prec: bool = True):
-    """chol[K,D,D] -> (linv[K,D,D], prec[K,D,D] | None, cst[K], ok[K] int32)."""
+def _fits(t, shape):
+    return t is not None and tuple(t.shape) == tuple(shape) and t.dtype == torch.float32 and t.is_contiguous()
+
+
+def prepare_full(chol: torch.Tensor, want_prec: bool = True, out=None):
+    """chol[K,D,D] -> (linv[K,D,D], prec[K,D,D] | None, cst[K], ok[K] int32).  `out` = (linv, prec, cst) buffers to
+    write into (used when their shapes fit; a graph runner passes its static buffers)."""
     chol = _chk(chol, "chol")
     K, D, _ = chol.shape
-    linv = torch.empty_like(chol)
-    prec = torch.empty_like(chol) if want_prec else None
-    cst = torch.empty(K, device=chol.device, dtype=torch.float32)
+    o = out if out is not None else (None, None, None)
+    linv = o[0] if _fits(o[0], chol.shape) else torch.empty_like(chol)
+    prec = (o[1] if _fits(o[1], chol.shape) else torch.empty_like(chol)) if want_prec else None
+    cst = o[2] if _fits(o[2], (K,)) else torch.empty(K, device=chol.device, dtype=torch.float32)
     ok = torch.empty(K, device=chol.device, dtype=torch.int32)
     nbytes = _lib.lib().gvi_prepare_full_workspace(K, D)
     ws = torch.empty(max(nbytes, 8) // 8, device=chol.device, dtype=torch.float64)
@@ -228,6 +292,9 @@ TC_MIXGRAD = os.environ.get("GMMVI_B200_TC_MIXGRAD", "1") != "0"
 
 def split_h16_full(prec):
     """Zero-padded, power-of-two scaled fp16 (hi, lo) copies of full matrices [K, D, D] (the precisions) + tmax[K]."""
+    st = _split_static(prec)
+    if st is not None:
+        return st
     key = (prec.data_ptr(), prec._version, tuple(prec.shape))
     for k_, _, hi, lo, tmax in _P16_CACHE:
         if k_ == key:
@@ -599,7 +666,7 @@ def sample_components(diagonal: bool, eps, offsets, means, chols, max_rows_per_c
     return X, mapping
 
 
-def bgemm(A, B, transA=False, transB=False, alpha=1.0, tensor_cores=None):
+def bgemm(A, B, transA=False, transB=False, alpha=1.0, tensor_cores=None, out=None):
     """Batched C[b] = alpha * op(A[b]) op(B[b]) for 3-D tensors (or 2-D, batch 1).  tensor_cores=True forces the
     tcgen05 3xTF32 kernel, False the SIMT engine, None picks the tensor cores when the shape allows."""
     A, B = _chk(A, "A"), _chk(B, "B")
@@ -609,7 +676,7 @@ def bgemm(A, B, transA=False, transB=False, alpha=1.0, tensor_cores=None):
     batch = A.shape[0]
     M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
     N = B.shape[1] if transB else B.shape[2]
-    Cc = torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
+    Cc = out if (_fits(out, (batch, M, N)) and not squeeze) else torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
     use_tc = tensor_cores
     if use_tc is None:
         use_tc = USE_TENSOR_CORES and M >= 64 and N >= 32 and bool(_lib.lib().gvi_tc_bgemm_supported(M, N, Kd))

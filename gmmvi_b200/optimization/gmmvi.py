@@ -78,6 +78,9 @@ class GMMVI:
         if enabled:
             GraphedIteration(self)          # raises when the configuration cannot be captured
         self._graph_enabled, self._graph, self._graph_stable, self._graph_K = bool(enabled), None, 0, None
+        if getattr(self, "_graph_state", None) is not None:
+            self._graph_state.release()
+        self._graph_state = None
 
     def _graphed_step(self, noise=None):
         """Replay (or capture, then replay) the graph of the current number of components -> True; False when this
@@ -98,6 +101,9 @@ class GMMVI:
             # graph uses it
             self._graph_retired = list(graphs.values()) or getattr(self, "_graph_retired", None)
             graphs, self._graph_stable, self._graph_K = {}, 0, K
+            if getattr(self, "_graph_state", None) is not None:
+                self._graph_state.release()
+                self._graph_state = None
         if noise is not None and slot in graphs and graphs[slot].noise_buffer.shape != noise.shape:
             del graphs[slot]
         self._graph = graphs

@@ -9,16 +9,20 @@ deleting components, metrics, the growing sample database) stay outside and run 
 
 What makes an iteration replayable:
   * every tensor that lives across iterations (mixture parameters, per-component learner state, stepsizes, reward /
-    weight histories, the inverse factors derived from the parameters) sits in a STATIC buffer: the captured body reads
-    the static buffers, computes new values into graph-private memory, and ends by copying them back;
+    weight histories, the inverse factors / precisions derived from the parameters and their fp16 split operands) sits
+    in a STATIC buffer (`GraphState`, shared by all graphs of one number of components): the captured body reads the
+    static buffers and ends by writing the new values back -- the big ones (inverse factors, precisions, gathered
+    Cholesky factors, split operands) are produced directly in place, the rest is copied;
   * the noise generator's draw counter is a device scalar the graph increments (gvi_fill_normal_dev_f32), so replays
     draw the subsequences an eager run would have drawn -- results are bit-identical to eager iterations;
   * no host synchronisation inside: the body is the no-reuse iteration (`select_samples_deferred`), whose shapes depend
     only on the number of components; the sample database is appended to after the replay;
   * NCCL collectives of a sharded run are captured like any other kernel.
 Supported: component-based selector with ratio_reused_samples_to_desired = 0, any estimator / updater / stepsize rule.
-A change of the number of components drops the graph; it is captured again once K has been stable for an iteration."""
+A change of the number of components drops the graphs; they are captured again once K has been stable for a while."""
 from __future__ import annotations
+
+import gc
 
 import torch
 
@@ -40,6 +44,81 @@ def _slots(gmmvi):
     return gmm, out
 
 
+class GraphState:
+    """Static buffers of one number of components, shared by the graphs captured for it."""
+
+    def __init__(self, gmmvi):
+        self.gmm, self.slots = _slots(gmmvi)
+        gmm = self.gmm
+        self.num_components = gmm.num_components
+        self.full = not gmm.diagonal_covs
+        if gmm._chol_work is not None:
+            _ = gmm.chol_cov                        # finish an in-flight all-gather before cloning
+        self.statics = [getattr(o, n).detach().clone().contiguous() for o, n in self.slots]
+        self.prep = [t.detach().clone().contiguous() for t in gmm.prepared(need_prec=True)] if self.full else None
+        self.counter = torch.zeros(1, device=gmm.device, dtype=torch.int64)
+        self.host_subsequence = None                # value of the device counter, tracked on the host
+        ops.clear_split_registry()
+        self.install()
+
+    def chol_static(self):
+        return self.statics[2]
+
+    def sync_from_model(self):
+        """Bring the static buffers up to date with whatever eager code did to the model since the last replay."""
+        gmm = self.gmm
+        dirty = False
+        for (obj, name), s in zip(self.slots, self.statics):
+            cur = getattr(obj, name) if name != "_chol_cov" else gmm.chol_cov
+            if cur is not s:
+                s.copy_(cur)
+                dirty = True
+        if self.full:
+            p = gmm._prepared
+            if dirty or p is None or p[0] != gmm._version or p[1] is not self.prep[0]:
+                gmm._prepared = None if dirty else gmm._prepared
+                for s, new in zip(self.prep, gmm.prepared(need_prec=True)):
+                    if new is not s:
+                        s.copy_(new)
+                for t in self.prep[:2]:
+                    ops.invalidate_split(t)
+        self.install()
+
+    def install(self):
+        """Point the model / learner attributes at the static buffers and declare the derived operands valid for them."""
+        gmm = self.gmm
+        for (obj, name), s in zip(self.slots, self.statics):
+            setattr(obj, name, s)
+        gmm._version += 1
+        if gmm._chol_work is not None:
+            gmm._chol_work.wait()
+            gmm._chol_work = None
+        gmm._local_chol = None
+        if gmm.shard is not None:
+            r = gmm.shard.component_range(gmm.num_components)
+            if r is not None:
+                gmm._local_chol = (gmm._version, r[0], r[1], gmm._chol_cov[r[0]:r[1]])
+        if self.full:
+            gmm._prepared = (gmm._version, self.prep[0], self.prep[1], self.prep[2])
+            # results that can be produced in place: the next update gathers / prepares straight into the static buffers
+            gmm._static_out = {"chol": self.chol_static(), "linv": self.prep[0], "prec": self.prep[1], "cst": self.prep[2]}
+            for t, kind in zip(self.prep[:2], ("lower", "full")):
+                if ops.split_registered(t) is None:
+                    ops.register_split_buffers(t, kind, valid=False)
+        else:
+            gmm._prepared = None
+            gmm._static_out = None
+
+    def set_counter(self):
+        if self.host_subsequence != rng._state["subsequence"]:      # eager draws advanced the host counter
+            self.host_subsequence = rng._state["subsequence"]
+            self.counter.fill_(self.host_subsequence)
+
+    def release(self):
+        self.gmm._static_out = None
+        ops.clear_split_registry()
+
+
 class GraphedIteration:
     def __init__(self, gmmvi, noise_buffer=None):
         from .gmmvi_modules.sample_selector import VipsSampleSelector
@@ -52,31 +131,21 @@ class GraphedIteration:
         self.num_components = None
         self.replays = 0
 
-    # ------------------------------------------------------------------------------------------------------------
-    def _install(self, gmm, slots, statics, prep):
-        for (obj, name), s in zip(slots, statics):
-            setattr(obj, name, s)
-        gmm._version += 1
-        if gmm._chol_work is not None:
-            gmm._chol_work.wait()
-            gmm._chol_work = None
-        gmm._local_chol = None
-        if gmm.shard is not None:
-            r = gmm.shard.component_range(gmm.num_components)
-            if r is not None:
-                gmm._local_chol = (gmm._version, r[0], r[1], gmm._chol_cov[r[0]:r[1]])
-        gmm._prepared = None if prep is None else (gmm._version, prep[0], prep[1], prep[2])
-
     def capture(self):
         g = self.gmmvi
-        gmm, slots = _slots(g)
-        self.num_components = gmm.num_components
-        dev = gmm.device
-        full = not gmm.diagonal_covs
-        statics = [getattr(o, n).detach().clone().contiguous() for o, n in slots]
-        prep = [t.detach().clone().contiguous() for t in gmm.prepared(need_prec=True)] if full else None
-        self.counter = torch.tensor([rng._state["subsequence"]], device=dev, dtype=torch.int64)
-        self._install(gmm, slots, statics, prep)
+        st = getattr(g, "_graph_state", None)
+        K = (g.model.model if hasattr(g.model, "model") else g.model).num_components
+        if st is None or st.num_components != K:
+            st = g._graph_state = GraphState(g)
+        else:
+            st.sync_from_model()
+        self.state = st
+        gmm = st.gmm
+        self.num_components = K
+        if st.full:                                  # the split operands of the current factors, computed once, eagerly
+            for t in st.prep[:2]:
+                ops.split_static_now(t)
+        st.set_counter()
         ops.clear_caches()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -84,11 +153,10 @@ class GraphedIteration:
         kernels0, calls0 = ops.KERNELS, ops.LAUNCHES
         # Python's cyclic collector must not run inside the capture: it may destroy an older, unreachable CUDA graph
         # (GMMVI <-> GraphedIteration is a cycle) and freeing its memory pool invalidates the capture in progress.
-        import gc
         gc_was_enabled = gc.isenabled()
         gc.disable()                    # (no gc.collect() here: a full collection costs tens of ms per capture)
         try:
-            self._capture(g, gmm, slots, statics, prep, full)
+            self._capture(g, st)
         finally:
             if gc_was_enabled:
                 gc.enable()
@@ -101,10 +169,11 @@ class GraphedIteration:
         g.sample_db.num_samples_written = written0
         return self
 
-    def _capture(self, g, gmm, slots, statics, prep, full):
+    def _capture(self, g, st):
         # capture_begin / capture_end by hand instead of the torch.cuda.graph context: the context empties the caching
         # allocator (a cudaFree of every cached block, ~0.2 s) on every entry, which an adaptive run that captures again
         # after each change of the number of components cannot afford.  All graphs of one GMMVI share a memory pool.
+        gmm = st.gmm
         live = [x for x in ((g._graph or {}).values() if isinstance(g._graph, dict) else []) if x.graph is not None]
         live += [x for x in (getattr(g, "_graph_retired", None) or []) if x.graph is not None]
         if getattr(g, "_graph_pool", None) is None or not live:      # a pool only exists while some graph uses it
@@ -116,29 +185,35 @@ class GraphedIteration:
         with torch.cuda.stream(stream):
             self.graph.capture_begin(pool=g._graph_pool, capture_error_mode="thread_local")
             try:
-                self._captured_region(g, gmm, slots, statics, prep, full)
+                self._captured_region(g, st)
             finally:
                 self.graph.capture_end()
         torch.cuda.current_stream(gmm.device).wait_stream(stream)
 
-    def _captured_region(self, g, gmm, slots, statics, prep, full):
-        if True:
-            rng.begin_device_mode(self.counter)
-            try:
-                self.payload = self._body()
-            finally:
-                self.draws = rng.end_device_mode()
-            self.counter.add_(self.draws)
-            if full:
-                for s, new in zip(prep, gmm.prepared(need_prec=True)):
-                    if new is not s:
-                        s.copy_(new)
-            _ = gmm.chol_cov                          # waits for an in-flight all-gather of a sharded update
-            for (obj, name), s in zip(slots, statics):
-                new = getattr(obj, name)
-                if new is not s:
+    def _captured_region(self, g, st):
+        gmm = st.gmm
+        rng.begin_device_mode(st.counter)
+        try:
+            self.payload = self._body()
+        finally:
+            self.draws = rng.end_device_mode()
+        st.counter.add_(self.draws)
+        if st.full:
+            for s, new in zip(st.prep, gmm.prepared(need_prec=True)):
+                if new is not s:                          # produced elsewhere (shape did not fit the in-place path)
                     s.copy_(new)
-            self._install(gmm, slots, statics, prep)
+                    ops.invalidate_split(s)
+            # The next replay starts from these buffers WITHOUT splitting them again (no split kernel is captured at the
+            # start of the body: the operands were valid then), so every operand rewritten during this iteration must be
+            # brought up to date here; the inverse factors already were, for the weight-update pass.
+            for s in st.prep[:2]:
+                ops.split_static_now(s)
+        _ = gmm.chol_cov                                  # waits for an in-flight all-gather of a sharded update
+        for (obj, name), s in zip(st.slots, st.statics):
+            new = getattr(obj, name)
+            if new is not s:
+                s.copy_(new)
+        st.install()
 
     def _body(self):
         g = self.gmmvi
@@ -157,7 +232,12 @@ class GraphedIteration:
 
     def replay(self):
         g = self.gmmvi
+        st = self.state
+        if getattr(st.gmm, "_means") is not st.statics[1] or getattr(st.gmm, "_chol_cov") is not st.statics[2]:
+            st.sync_from_model()            # eager code replaced the parameters since the last replay
+        st.set_counter()
         self.graph.replay()
+        st.host_subsequence += self.draws
         self.replays += 1
         ops.clear_caches()                  # the replay rewrote the static buffers behind the caches' keys
         ops.KERNELS += self.kernels

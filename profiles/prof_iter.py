@@ -23,7 +23,8 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 K, D, per = bench.K_COMP, bench.DIM, bench.PER_COMP
-means, chols, tmeans, tchols = bench.workload_arrays(K, D, 0, bench.PRIOR_SCALE)
+# --dense: overlapping components (mean scale 0.05): no (component, sample block) can be skipped
+means, chols, tmeans, tchols = bench.workload_arrays(K, D, 0, 0.05 if "--dense" in sys.argv else bench.PRIOR_SCALE)
 model = FullCovGMM.from_cholesky(np.ones(K, np.float32) / K, means, chols, device=dev)
 tgt = GMM_LNPDF.from_cholesky(np.ones(10) / 10, tmeans, tchols, device=dev)
 cfg = bench.samtron_config(per)
@@ -31,7 +32,9 @@ g = GMMVI.build_from_config(cfg, tgt, GmmWrapper.build_from_config(model, cfg))
 if world > 1:
     g.enable_sharding(ShardContext(rank, world))
 rng.set_seed(1234)
-for _ in range(3):
+if "--graph" in sys.argv:
+    g.enable_cuda_graph()
+for _ in range(4):
     g.train_iter()
 torch.cuda.synchronize()
 steps = 5
@@ -49,5 +52,4 @@ if rank == 0:
     print(f"sum of device time per iteration: {tot / steps / 1e3:.3f} ms")
     for e in sorted(ev, key=lambda e: -e.self_device_time_total)[:70]:
         print(f"{e.self_device_time_total / steps / 1e3:8.3f} ms  n={e.count / steps:5.1f}  {e.key[:90]}")
-if world > 1:
-    dist.destroy_process_group()
+bench.shutdown_distributed([g])

@@ -112,3 +112,29 @@ def test_graph_mode_follows_component_adaptation():
         assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
     assert torch.equal(e.gmmvi.sample_db.samples, g.gmmvi.sample_db.samples)
     assert torch.equal(e.gmmvi.sample_db.mapping, g.gmmvi.sample_db.mapping)
+
+
+def test_rng_and_noise_graphs_share_their_state():
+    """Alternating train_iter() and train_iter(noise=...) replays two different graphs over ONE set of static buffers."""
+    from gmmvi_b200 import rng
+    K, D, desired, iters = 6, 96, 128, 6
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    noise = [torch.randn((K * desired, D), device="cuda", generator=gen) for _ in range(iters)]
+    runs = []
+    for graph in (False, True):
+        rng.set_seed(21)
+        g = _fixed(K, D, desired)
+        if graph:
+            g.enable_cuda_graph()
+        for i in range(iters):
+            g.train_iter()
+            g.train_iter(noise=noise[i])
+            if i == 2:                                  # eager code in between: an extra draw and a density evaluation
+                X, _ = g.model.sample(100)
+                g.model.log_density(X)
+        torch.cuda.synchronize()
+        runs.append(_state(g))
+        if graph:
+            assert set(g._graph) == {"rng", "noise"} and g._graph["rng"].replays >= iters - 2
+    for n in runs[0]:
+        assert np.array_equal(runs[0][n], runs[1][n]), (n, float(np.max(np.abs(runs[0][n] - runs[1][n]))))

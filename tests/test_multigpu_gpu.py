@@ -55,6 +55,19 @@ def _worker(rank, world, port, K, D, desired, iters, out_dir, graph=False):
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=g.model.means.cpu().numpy(),
              chol=g.model.chol_cov.cpu().numpy(), logw=g.model.log_weights.cpu().numpy(),
              n_local=g.sample_db.samples.shape[0])
+    if graph:
+        # captured graphs hold NCCL kernels: release them before the communicator; a watchdog ends the worker if the
+        # teardown still does not return (the results are on disk)
+        import gc
+        import threading
+        g.enable_cuda_graph(False)
+        g._graph_retired = None
+        del g
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Timer(15.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
     dist.destroy_process_group()
 
 
