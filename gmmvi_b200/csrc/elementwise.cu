@@ -1116,8 +1116,12 @@ size_t stein_small_workspace_floats(int N, int K, int D);
 int launch_stein_small(const float* X, int N, int D, const float* means, const float* W, const uint8_t* active,
                        const float* G, int K, float* M, float* gneg, float* ws, cudaStream_t st);
 }  // namespace gvi
+// splits of 16 blocks (2048 samples): with well separated components the blocks that carry weight for a tile of 32
+// components are few and contiguous, so coarse splits would leave all of a tile's work to one CTA (measured: 0.82 ms at C5
+// with 18 splits against 0.10 ms for the per-component kernel)
 static int stein_gsum_splits(int N, int K) {
-  return max(1, min(ceil_div(N, 128), ceil_div(148 * 2, ceil_div(max(K, 1), GS_KT))));
+  (void)K;
+  return max(1, min(64, ceil_div(ceil_div(N, 128), 16)));
 }
 static size_t stein_gsum_floats(int N, int K, int D) {
   return (N > 0 && K > 0 && D > 32) ? (size_t)stein_gsum_splits(N, K) * K * D : 0;
