@@ -62,6 +62,8 @@ _SIGNATURES = {
                                                 C.c_int, c_f, c_vp, C.c_size_t, c_vp]),
     "gvi_gauss_kernel_sum_partials": (C.c_size_t, [C.c_int, C.c_int]),
     "gvi_gauss_kernel_sum_f32": (C.c_int, [c_f, C.c_int, c_f, C.c_int, C.c_int, c_f, c_vp, c_vp]),
+    "gvi_cholesky_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "gvi_cholesky_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_i, c_vp, C.c_size_t, c_vp]),
     "gvi_planar_robot_f32": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_float, c_f, c_f, c_vp]),
     "gvi_tridiag_f32": (C.c_int, [c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_vp]),
     "gvi_update_full_f32": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float,

@@ -251,3 +251,59 @@ extern "C" int gvi_update_full_general_f32(int mode, const float* means, const f
                                                      stepsizes, num_updates, D, work, out_means, out_chols, success);
   return check_launch("update_general_kernel");
 }
+
+// ---- construction-time Cholesky (models/full_cov_gmm.py:23, :67: tf.linalg.cholesky of user-supplied covariances) --------
+// One CTA per matrix, fp64 arithmetic on a global (L2-resident) scratch copy, left-looking, result rounded to fp32 -- the
+// same factor a host LAPACK dpotrf would give, without the device -> host -> device round trip the adaptive runs paid on
+// every component addition.  ok[k] = 0 and a NaN-filled factor (TensorFlow's behaviour) when a pivot is not positive.
+namespace gvi {
+__global__ void __launch_bounds__(256)
+cholesky_f64_kernel(const float* __restrict__ A, int D, double* __restrict__ work, float* __restrict__ L,
+                    int32_t* __restrict__ ok) {
+  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const long long DD = (long long)D * D;
+  double* W = work + k * DD;
+  const float* Ak = A + k * DD;
+  for (long long e = tid; e < DD; e += nt) W[e] = (double)Ak[e];
+  __syncthreads();
+  __shared__ double s_diag;
+  bool good = true;
+  for (int j = 0; j < D && good; ++j) {
+    const double* rj = W + (long long)j * D;
+    for (int i = j + tid; i < D; i += nt) {
+      double* ri = W + (long long)i * D;
+      double s = ri[j];
+      for (int m = 0; m < j; ++m) s -= ri[m] * rj[m];
+      ri[j] = s;
+    }
+    __syncthreads();
+    if (tid == 0) s_diag = W[(long long)j * D + j];
+    __syncthreads();
+    const double d = s_diag;
+    if (!(d > 0.0) || !isfinite(d)) { good = false; break; }
+    const double r = sqrt(d), ir = 1.0 / r;
+    for (int i = j + tid; i < D; i += nt) W[(long long)i * D + j] = (i == j) ? r : W[(long long)i * D + j] * ir;
+    __syncthreads();
+  }
+  float* Lk = L + k * DD;
+  for (long long e = tid; e < DD; e += nt) {
+    const int i = (int)(e / D), j = (int)(e % D);
+    Lk[e] = good ? (j <= i ? (float)W[e] : 0.f) : __int_as_float(0x7fc00000);
+  }
+  if (tid == 0 && ok != nullptr) ok[k] = good ? 1 : 0;
+}
+}  // namespace gvi
+
+extern "C" size_t gvi_cholesky_workspace(int K, int D) { return K > 0 ? (size_t)K * D * D * sizeof(double) : 0; }
+extern "C" int gvi_cholesky_f32(const float* A, int K, int D, float* L, int32_t* ok, void* ws, size_t ws_bytes, void* stream) {
+  GVI_REQUIRE(K >= 0 && D > 0, "gvi_cholesky_f32: bad sizes");
+  if (K == 0) return GVI_OK;
+  GVI_REQUIRE(A && L && ws, "gvi_cholesky_f32: null pointer");
+  GVI_REQUIRE(K <= 65535, "gvi_cholesky_f32: K=%d exceeds 65535", K);
+  if (ws_bytes < gvi_cholesky_workspace(K, D)) {
+    set_last_error("gvi_cholesky_f32: workspace %zu < %zu", ws_bytes, gvi_cholesky_workspace(K, D));
+    return GVI_ERR_WORKSPACE;
+  }
+  cholesky_f64_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(A, D, (double*)ws, L, ok);
+  return check_launch("cholesky_f64_kernel");
+}

@@ -9,19 +9,19 @@ from .. import ops
 from .gmm import GMM, _as_param
 
 
-def _batched_cholesky(covs: torch.Tensor) -> torch.Tensor:
-    """Construction-time factorisation of user-supplied covariances (models/full_cov_gmm.py:23,67).
-    Only used when a model is built or a component is added (never inside an iteration): a host fp64
-    factorisation keeps construction exact; the hot path only ever produces Cholesky factors on device."""
-    return torch.linalg.cholesky(covs.detach().to("cpu", torch.float64)).to(torch.float32)
+def _batched_cholesky(covs: torch.Tensor, device) -> torch.Tensor:
+    """Factorisation of user-supplied covariances (models/full_cov_gmm.py:23, :67: the constructor and add_component,
+    which SAMTRON calls every `add_iters` iterations): `gvi_cholesky_f32`, fp64 arithmetic on the device rounded to fp32,
+    NaN factor for a matrix that is not positive definite like tf.linalg.cholesky.  No host round trip."""
+    covs = torch.as_tensor(covs, dtype=torch.float32).to(device).contiguous()
+    return ops.cholesky(covs)[0]
 
 
 class FullCovGMM(GMM):
     def __init__(self, weights, means, covs, device="cuda"):
         self.diagonal_covs = False
         means = _as_param(means, device)
-        covs = torch.as_tensor(covs, dtype=torch.float32)
-        chol = _batched_cholesky(covs).to(device).contiguous()
+        chol = _batched_cholesky(covs, device)
         log_weights = torch.log(_as_param(weights, device))
         super().__init__(log_weights, means, chol)
 
@@ -72,7 +72,7 @@ class FullCovGMM(GMM):
     def add_component(self, initial_weight, initial_mean, initial_cov):
         """models/full_cov_gmm.py:64-67."""
         dev = self.device
-        new_chol = _batched_cholesky(torch.as_tensor(initial_cov, dtype=torch.float32).reshape(1, self.num_dimensions, -1)).to(dev)
+        new_chol = _batched_cholesky(torch.as_tensor(initial_cov, dtype=torch.float32).reshape(1, self.num_dimensions, -1), dev)
         self.means = torch.cat((self.means, torch.as_tensor(initial_mean, dtype=torch.float32, device=dev).reshape(1, -1)), 0)
         self.chol_cov = torch.cat((self.chol_cov, new_chol), 0).contiguous()
         w = torch.log(torch.as_tensor(initial_weight, dtype=torch.float32, device=dev).reshape(1))

@@ -602,6 +602,19 @@ def gauss_kernel_sum(X, Y, w):
     return partial.sum().to(torch.float32)
 
 
+def cholesky(covs):
+    """Lower Cholesky factors of covs[K,D,D] (fp64 arithmetic on the device, fp32 result; NaN factor when not positive
+    definite) -> (L[K,D,D], ok[K] int32).  Construction-time only: models/full_cov_gmm.py:23, :67."""
+    covs = _chk(covs, "covs")
+    K, D, _ = covs.shape
+    L = torch.empty_like(covs)
+    ok = torch.empty(K, device=covs.device, dtype=torch.int32)
+    nbytes = _lib.lib().gvi_cholesky_workspace(K, D)
+    ws = torch.empty(max(nbytes, 8) // 8, device=covs.device, dtype=torch.float64)
+    _call("gvi_cholesky_f32", covs.data_ptr(), K, D, L.data_ptr(), ok.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return L, ok
+
+
 def planar_robot(theta, prior_stds, goals, likelihood_std: float, want_grad: bool = True):
     """PlanarRobot.log_density (planar_robot.py:49-66) and its gradient -> (lnpdf[N], grad[N,D] | None)."""
     theta, prior_stds, goals = _chk(theta, "theta"), _chk(prior_stds, "prior_stds"), _chk(goals, "goals")

@@ -63,6 +63,7 @@ class SampleDB:
         self.target_grads = z(0, dim)
         self.mapping = torch.zeros(0, device=self.device, dtype=torch.int32)
         self.num_samples_written = 0
+        self._last_batch = None                  # (#samples, #components) of the most recent add_samples call
         self.count_override = None               # global per-component counts when samples are sharded over GPUs
 
     @staticmethod
@@ -73,6 +74,7 @@ class SampleDB:
 
     def remove_every_nth_sample(self, N: int):
         """optimization/sample_db.py:64-79."""
+        self._last_batch = None
         self.samples = self.samples[::N].contiguous()
         self.target_lnpdfs = self.target_lnpdfs[::N].contiguous()
         self.target_grads = self.target_grads[::N].contiguous()
@@ -110,6 +112,7 @@ class SampleDB:
         if self.max_samples is not None and samples.shape[0] + self.samples.shape[0] > self.max_samples:
             self.remove_every_nth_sample(2)
         self.num_samples_written += int(samples.shape[0])
+        self._last_batch = (int(samples.shape[0]), int(means.shape[0]))
         inv, cst = self._invert(chols, prepared)
         mapping = mapping.to(torch.int32)
         if self.keep_samples:
@@ -170,7 +173,11 @@ class SampleDB:
         X = self.samples[start:]
         amap = self.mapping[start:]
         M = int(self.means.shape[0])
-        if self.keep_samples and M > 0:
+        if self.keep_samples and M > 0 and self._last_batch is not None and S - start == self._last_batch[0]:
+            # exactly the batch stored last (every no-reuse iteration): its components are the last ones stored -- known
+            # on the host, no device read.  (The reference derives them from unique(mapping), sample_db.py:221.)
+            lo, hi = M - self._last_batch[1], M - 1
+        elif self.keep_samples and M > 0:
             lo, hi = int(amap.min().item()), int(amap.max().item())      # mapping is non-decreasing
         else:
             lo, hi = 0, M - 1

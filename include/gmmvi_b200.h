@@ -250,6 +250,12 @@ int gvi_update_full_general_f32(int mode, const float* means, const float* chols
                                 float* out_means, float* out_chols, int32_t* success, void* ws, size_t ws_bytes,
                                 void* stream);
 
+/* ---- construction-time Cholesky (models/full_cov_gmm.py:23, :67: tf.linalg.cholesky(covs) in the constructor and in
+ * add_component) -- A[K,D,D] symmetric (lower triangle read) -> L[K,D,D] lower, fp64 arithmetic rounded to fp32; a matrix
+ * that is not positive definite gives a NaN-filled factor (TensorFlow's behaviour) and ok[k] = 0 (ok nullable). */
+size_t gvi_cholesky_workspace(int K, int D);
+int gvi_cholesky_f32(const float* A, int K, int D, float* L, int32_t* ok, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- planar-robot target (experiments/target_distributions/planar_robot.py:29-66; BASELINE config C2) ----------------
  * theta[N,D] joint angles (D = number of links <= 64) -> lnpdf[n] = N(theta_n; 0, diag(prior_stds^2)) + max over the G <= 8
  * goals[G,2] of N(forward_kinematics(theta_n); goal, likelihood_std^2 I)  (:49-53, :57-66), and, when grad != NULL,

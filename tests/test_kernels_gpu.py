@@ -628,3 +628,21 @@ def test_small_dimension_kernels(K, D, N, monkeypatch):
     assert rel_err(small[2], Href) < NG_RTOL and rel_err(small[3], gref) < NG_RTOL
     for a, b in zip(small[:4], general[:4]):
         assert rel_err(a, b) < 2e-5
+
+
+def test_construction_time_cholesky():
+    """gvi_cholesky_f32 (models/full_cov_gmm.py:23, :67): fp64 arithmetic on the device, NaN factor + ok = 0 for a matrix
+    that is not positive definite (tf.linalg.cholesky's behaviour)."""
+    from gmmvi_b200 import ops
+    rng = np.random.default_rng(3)
+    for K, D in ((5, 3), (7, 20), (3, 256), (1, 1)):
+        A = rng.standard_normal((K, D, D))
+        cov = (A @ A.transpose(0, 2, 1) / D + np.eye(D)).astype(np.float32)
+        L, ok = ops.cholesky(dev(cov))
+        ref = np.linalg.cholesky(cov.astype(np.float64))
+        assert ok.cpu().numpy().all()
+        assert rel_err(L.cpu().numpy(), ref) < 2e-7
+        assert np.all(np.triu(L.cpu().numpy(), 1) == 0)
+    bad = np.stack([np.eye(4, dtype=np.float32), -np.eye(4, dtype=np.float32)])
+    L, ok = ops.cholesky(dev(bad))
+    assert ok.cpu().numpy().tolist() == [1, 0] and np.isnan(L[1].cpu().numpy()).all() and np.isfinite(L[0].cpu().numpy()).all()
