@@ -21,6 +21,19 @@ int  check_launch(const char* what);          // cudaGetLastError -> GVI_ERR_CUD
     }                                                           \
   } while (0)
 
+// One-time-per-DEVICE initialisation (cudaFuncSetAttribute, SM count): `mask` is a function-local static; returns true the
+// first time it is called on the current device.  (One process normally drives one GPU; a process that drives several
+// must not inherit the first device's setup.)
+inline bool first_call_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 constexpr float kLog2Pi = 1.8378770664093454835606594728112f;
 constexpr double kLog2PiD = 1.8378770664093454835606594728112;
 

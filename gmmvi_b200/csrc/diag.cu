@@ -137,10 +137,9 @@ int launch_logdens_diag2(const float* X, int N, int D, const float* means, const
   const int Dp = ceil_div(D, DC) * DC;
   const size_t smem = (size_t)(2 * KC * Dp + KC) * sizeof(float);
   if (smem > 200 * 1024) return 1;                    // D > ~3000: the caller keeps the first-generation kernel
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (smem > 48 * 1024 && first_call_on_device(attr_set_mask)) {
     cudaFuncSetAttribute(logdens_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   const int nb = ceil_div(N, TS), kchunks = ceil_div(K, KC);
   int ysplit = min(kchunks, max(1, ceil_div(148 * 8, nb)));     // >= 8 CTAs (32 warps) per SM

@@ -967,25 +967,23 @@ extern "C" int gvi_prepare_full_f32(const float* chol, int K, int D, float* linv
   }
   const int nb = ceil_div(D, PB);
   const size_t smem = (size_t)(nb + 3) * PB * PP * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (first_call_on_device(attr_set_mask)) {
     cudaError_t e = cudaFuncSetAttribute(prepare_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)((size_t)(8 + 3) * PB * PP * sizeof(double)));
     if (e != cudaSuccess) {
       set_last_error("gvi_prepare_full_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GVI_ERR_CUDA;
     }
-    attr_set = true;
   }
-  static bool attr2_set = false;
+  static unsigned long long attr2_set_mask = 0;
   const size_t smem_diag = (size_t)PD_WARPS * 2 * PB * PP * sizeof(double);
-  if (!attr2_set) {
+  if (first_call_on_device(attr2_set_mask)) {
     cudaError_t e = cudaFuncSetAttribute(prepare_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag);
     if (e != cudaSuccess) {
       set_last_error("gvi_prepare_full_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GVI_ERR_CUDA;
     }
-    attr2_set = true;
   }
   double* dinv = (double*)ws;
   prepare_diag_kernel<<<ceil_div(K * nb, PD_WARPS), 32 * PD_WARPS, smem_diag, (cudaStream_t)stream>>>(chol, D, nb, K * nb, dinv);
@@ -1021,10 +1019,9 @@ extern "C" int gvi_logdens_diag_f32(const float* X, int N, int D, const float* m
     set_last_error("gvi_logdens_diag_f32: D=%d too large for the sample tile", D);
     return GVI_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (smem > 48 * 1024 && first_call_on_device(attr_set_mask)) {
     cudaFuncSetAttribute(logdens_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   dim3 grid(ceil_div(N, 32), min(ceil_div(K, 8), 8));
   logdens_diag_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(X, N, D, means, stds, K, lq);

@@ -676,15 +676,14 @@ extern "C" int gvi_more_fit_f32(const float* X, int N, int D, const float* means
   unsigned* dmax = smax + chunk;
   float *alphaS = (float*)(dmax + chunk), *sT = alphaS + chunk, *alphaT = sT + chunk;
   const long long DD = (long long)D * D, ND = (long long)N * D;
-  static bool attr_done = false;
+  static unsigned long long attr_done_mask = 0;
   const size_t potrf_smem = (size_t)2 * more::NB * (more::NB + 1) * sizeof(float);
-  if (!attr_done) {
+  if (first_call_on_device(attr_done_mask)) {
     cudaFuncSetAttribute(more::potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
     cudaFuncSetAttribute(more::potrf_inv_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
     cudaFuncSetAttribute(more::backsolve_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(more::features_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(more::features_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   if ((size_t)F * sizeof(float) > 200 * 1024) {
     set_last_error("gvi_more_fit_f32: D=%d gives F=%d features, too many for the back-substitution kernel", D, F);

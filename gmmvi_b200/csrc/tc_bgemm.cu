@@ -539,8 +539,8 @@ static int launch_tc_bgemm_any(bool h16, int batch, int M, int N, int Kd, float 
     if ((rc = tcx::make_map_3d(&mBh, (const float*)Bh, Kd, N, batch, Kd, sOb, 32))) return rc;
     if ((rc = tcx::make_map_3d(&mBl, (const float*)Bl, Kd, N, batch, Kd, sOb, 32))) return rc;
   }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (first_call_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(tcg::tc_bgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tcg::SMEM_BYTES);
     if (e == cudaSuccess)
@@ -549,7 +549,6 @@ static int launch_tc_bgemm_any(bool h16, int batch, int M, int N, int Kd, float 
       set_last_error("tc_bgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GVI_ERR_CUDA;
     }
-    attr = true;
   }
   const int mt_n = ceil_div(M, tcg::TILE_M), nt_n = ceil_div(N, tcg::ACC_COLS);
   const int tpb = lower_only ? tiles_lower(mt_n, nt_n) : mt_n * nt_n;

@@ -409,7 +409,8 @@ extern "C" int gvi_logdens_full_tc_f32(const float* X, int N, int D, const float
   rc = tc::make_map(&map_lo, linv_lo, K, D);
   if (rc) return rc;
   static int num_sms = 0;
-  if (num_sms == 0) {
+  static unsigned long long dev_mask = 0;       // per device: the attributes below are per device
+  if (first_call_on_device(dev_mask)) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);

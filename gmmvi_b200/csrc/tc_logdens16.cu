@@ -1318,7 +1318,8 @@ extern "C" int gvi_mixture_grad_full_h16_f32(const float* X, const float* tilein
   if ((rc = h16::make_map_h16(&map_hi, p_hi, K, Dp))) return rc;
   if ((rc = h16::make_map_h16(&map_lo, p_lo, K, Dp))) return rc;
   static int num_sms = 0;
-  if (num_sms == 0) {
+  static unsigned long long dev_mask = 0;       // per device: the attributes below are per device
+  if (first_call_on_device(dev_mask)) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1377,7 +1378,8 @@ extern "C" int gvi_logdens_full_h16_f32(const float* X, const float* tileinf, in
   if (rc) return rc;
   static int num_sms = 0;
   static int a_in_tmem = 1;      // GMMVI_B200_H16_A=smem selects the shared-memory A operand for every size
-  if (num_sms == 0) {
+  static unsigned long long dev_mask = 0;       // per device: the attributes below are per device
+  if (first_call_on_device(dev_mask)) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);

@@ -500,7 +500,8 @@ int launch_stein_stats_tc(const float* X, int N, int D, const float* means, cons
   if ((rc = make_map(&map_hi, Ghi, Dn, Np))) return rc;
   if ((rc = make_map(&map_lo, Glo, Dn, Np))) return rc;
   static int num_sms = 0;
-  if (num_sms == 0) {
+  static unsigned long long dev_mask = 0;       // per device: the attributes below are per device
+  if (first_call_on_device(dev_mask)) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);

@@ -516,6 +516,10 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
     else { lower = fmaxf(0.f, logf(last) - 3.f); upper = logf(last) + 3.f; }
     float leta = 0.5f * (upper + lower);
     bool feasible = false;
+    float last_e = -1.f;                           // eta of the most recent Cholesky evaluation (its results are in smem)
+    KlTerms last_t;
+    last_t.ok = false;
+    last_t.kl = FLT_MAX;
     if (tdiag != nullptr) {
       // ---- the same search with KL(eta) evaluated from the tridiagonal form: warp 0 evaluates the 31 candidate etas
       // of the next five bisection levels at once (lane = node of the decision tree, heap numbering: left child =
@@ -575,6 +579,8 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
       const float e = expf(leta);
       const KlTerms t = eval_whitened(s, B, nullptr, 1.f / e, 0.f, D, nbk, 1.f / e);
       ++n_evals;
+      last_e = e;
+      last_t = t;
       if (fabsf(step - t.kl) < 1e-1f * step) { lower = upper = leta; break; }
       if (step > t.kl) { upper = leta; feasible = true; }
       else lower = leta;
@@ -585,8 +591,11 @@ update_full_blocked_kernel(int mode, const float* __restrict__ means, const floa
     eta = fmaxf(new_lower, temperature);
     ok = (new_lower == new_upper);
     if (ok) {
-      const KlTerms t = eval_whitened(s, B, nullptr, 1.f / eta, 0.f, D, nbk, 1.f / eta);
-      ++n_evals;
+      // The reference evaluates kl() once more at the eta it settled on (:478-497).  When that is the eta of the search's
+      // last evaluation (the usual exit: |eps - KL| < 0.1 eps, or the bracket closing right after a feasible step), the
+      // factor, its inverse and M^-1 h are still in shared memory and the second, bit-identical evaluation is skipped.
+      const KlTerms t = (eta == last_e) ? last_t : eval_whitened(s, B, nullptr, 1.f / eta, 0.f, D, nbk, 1.f / eta);
+      ++n_evals;                                   // counted like the reference does
       ok = t.ok && (t.kl < FLT_MAX) && isfinite(t.kl);
       kl = t.kl;
     }
@@ -744,15 +753,14 @@ int launch_update_full_blocked(int mode, const float* means, const float* chols,
                                float* out_chols, int32_t* success, float* etas, float* kls, int32_t* evals,
                                const float* tdiag, const float* toff, const float* thp, cudaStream_t st) {
   const size_t smem = ub::blocked_smem_bytes(D);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (first_call_on_device(attr_set_mask)) {
     cudaError_t e = cudaFuncSetAttribute(ub::update_full_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ub::blocked_smem_bytes(ub::MAXBLK * ub::NB));
     if (e != cudaSuccess) {
       set_last_error("update_full_blocked: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return GVI_ERR_CUDA;
     }
-    attr_set = true;
   }
   ub::update_full_blocked_kernel<<<K, ub::THREADS, smem, st>>>(mode, means, chols, Bm, B2, hv, stepsizes, last_etas,
                                                                num_updates, D, temperature, out_means, out_chols,

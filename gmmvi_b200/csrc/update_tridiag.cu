@@ -187,15 +187,14 @@ bool tridiag_supported(int D) { return D >= 1 && D <= td::MAXD; }
 // d[K, D], e[K, D] (e[k][D-1] = 0), hp[K, D] = P^T h
 int launch_tridiag(const float* Bm, const float* hv, int K, int D, float* d, float* e, float* hp, cudaStream_t st) {
   if (K <= 0) return GVI_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set_mask = 0;
+  if (first_call_on_device(attr_set_mask)) {
     cudaError_t err = cudaFuncSetAttribute(td::tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)td::tridiag_smem_bytes(td::MAXD));
     if (err != cudaSuccess) {
       set_last_error("tridiag: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
       return GVI_ERR_CUDA;
     }
-    attr_set = true;
   }
   td::tridiag_kernel<<<K, td::THREADS, td::tridiag_smem_bytes(D), st>>>(Bm, hv, D, d, e, hp);
   return check_launch("tridiag_kernel");

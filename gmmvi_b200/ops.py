@@ -472,9 +472,13 @@ def stein_diag(X, means, stds, W, G):
     return Hneg, gneg
 
 
-def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=32 << 30):
+def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=None):
     """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32).
-    Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.2 GB per component)."""
+    Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.2 GB per component); the
+    default is half of the device memory that is free right now, at most 32 GiB."""
+    if memory_budget_bytes is None:
+        free, _ = torch.cuda.mem_get_info(samples.device)
+        memory_budget_bytes = min(32 << 30, free // 2)
     X, y, W = _chk(samples, "samples"), _chk(rewards, "rewards"), _chk(weights, "weights")
     means, linv, l2 = _chk(means, "means"), _chk(linv, "linv"), _chk(regularizers, "regularizers")
     N, D = X.shape
