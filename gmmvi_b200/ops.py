@@ -472,13 +472,19 @@ def stein_diag(X, means, stds, W, G):
     return Hneg, gneg
 
 
+_MORE_BUDGET = None     # last default workspace budget (not queried again while a CUDA graph is being captured)
+
+
 def more_fit(regularizers, samples, rewards, weights, means, linv, memory_budget_bytes=None):
     """MORE: per-component weighted quadratic regression -> (reward_quad[K,D,D], reward_lin[K,D], ok[K] int32).
     Components are processed in chunks that fit `memory_budget_bytes` of workspace (C3: 0.2 GB per component); the
     default is half of the device memory that is free right now, at most 32 GiB."""
+    global _MORE_BUDGET
     if memory_budget_bytes is None:
-        free, _ = torch.cuda.mem_get_info(samples.device)
-        memory_budget_bytes = min(32 << 30, free // 2)
+        if _MORE_BUDGET is None or not torch.cuda.is_current_stream_capturing():
+            free, _ = torch.cuda.mem_get_info(samples.device)
+            _MORE_BUDGET = min(32 << 30, free // 2)
+        memory_budget_bytes = _MORE_BUDGET
     X, y, W = _chk(samples, "samples"), _chk(rewards, "rewards"), _chk(weights, "weights")
     means, linv, l2 = _chk(means, "means"), _chk(linv, "linv"), _chk(regularizers, "regularizers")
     N, D = X.shape
