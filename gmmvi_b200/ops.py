@@ -84,9 +84,12 @@ def register_split_buffers(src, kind="lower", valid=False):
 
 
 def invalidate_split(src):
+    """`src` was rewritten in place (raw-pointer kernel / collective: torch's version counter does not see it): its
+    registered split operands are stale, and so is anything memoised on its address."""
     e = _SPLIT_STATIC.get(src.data_ptr())
     if e is not None:
         e[3] = False
+        clear_memo()
 
 
 def clear_split_registry():
@@ -193,6 +196,8 @@ def prepare_full(chol: torch.Tensor, want_prec: bool = True, out=None):
     chol = _chk(chol, "chol")
     K, D, _ = chol.shape
     o = out if out is not None else (None, None, None)
+    if out is not None:
+        clear_memo()        # results written into caller-owned buffers: the address / version keys of the memo do not see it
     linv = o[0] if _fits(o[0], chol.shape) else torch.empty_like(chol)
     prec = (o[1] if _fits(o[1], chol.shape) else torch.empty_like(chol)) if want_prec else None
     cst = o[2] if _fits(o[2], (K,)) else torch.empty(K, device=chol.device, dtype=torch.float32)
@@ -699,6 +704,8 @@ def bgemm(A, B, transA=False, transB=False, alpha=1.0, tensor_cores=None, out=No
     batch = A.shape[0]
     M, Kd = (A.shape[2], A.shape[1]) if transA else (A.shape[1], A.shape[2])
     N = B.shape[1] if transB else B.shape[2]
+    if out is not None:
+        clear_memo()
     Cc = out if (_fits(out, (batch, M, N)) and not squeeze) else torch.empty((batch, M, N), device=A.device, dtype=torch.float32)
     use_tc = tensor_cores
     if use_tc is None:
