@@ -18,6 +18,7 @@
 // several splits write partial sums that a small kernel adds in a fixed order (deterministic).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace gvi {
 namespace st16 {
@@ -30,7 +31,8 @@ constexpr int A_TILE = 128 * 64;        // 8 KB: 128 rows x 32 fp16
 constexpr int B_TILE = 256 * 64;        // 16 KB: up to 256 rows x 32 fp16
 constexpr int STAGE_BYTES = 4 * A_TILE + 2 * B_TILE;     // A_hi[0], A_hi[1], A_lo[0], A_lo[1], B_hi, B_lo = 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr int FLUSH_BLOCKS = 16;        // 128-sample blocks between drains of the accumulator
+constexpr int FLUSH_BLOCKS = 32;        // 128-sample blocks between drains of the accumulator (measured, dense C5 size:
+                                        // 16 -> 15.5 ms, error 0.9e-5; 32 -> 13.3 ms, 1.4e-5; 64 -> 12.2 ms, 2.5e-5 of the 1e-4 budget)
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 stein_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                 const float* __restrict__ Xt, int N, int Np, int D, int Dn, const float* __restrict__ means,
                 const float* __restrict__ W, const uint8_t* __restrict__ active, const float* __restrict__ wmax,
-                const float* __restrict__ minf, const float* __restrict__ scal, int K, int S,
+                const float* __restrict__ minf, const float* __restrict__ scal, int K, int S, int flush_blocks,
                 float* __restrict__ out /* [S][K][D][D] */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -202,7 +204,7 @@ stein_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         fresh = false;
-        if (++since == FLUSH_BLOCKS || seen == nact) {
+        if (++since == flush_blocks || seen == nact) {
           if (elect_one()) umma_commit(&bars->acc_full);
           __syncwarp();
           ++nflush;
@@ -224,7 +226,7 @@ stein_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const float inv = 1.0f / (pow2_scale(wmax[k] * (scal[0] + minf[k])) * sg);
       int nact = 0;
       for (int b = b0; b < b1; ++b) nact += is_active(k, b) ? 1 : 0;
-      const int ndrain = ceil_div(nact, FLUSH_BLOCKS);
+      const int ndrain = ceil_div(nact, flush_blocks);
       if (ndrain == 0) {         // nothing carries weight: the sum is zero
         for (int e = (q * 32 + lane); e < D * D; e += 128) Mk[e] = 0.f;
         continue;
@@ -449,6 +451,12 @@ static int make_map(CUtensorMap* map, const void* base, int Dn, int Np) {
   return GVI_OK;
 }
 
+// 128-sample blocks between two drains of the accumulator (GMMVI_B200_STEIN_FLUSH overrides, read per call)
+static int flush_blocks() {
+  const char* e = getenv("GMMVI_B200_STEIN_FLUSH");
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : FLUSH_BLOCKS;
+}
 static int num_splits(int K, int nblk) {
   int S = 1;
   if (K < 148) S = (148 + K - 1) / K;
@@ -516,7 +524,7 @@ int launch_stein_stats_tc(const float* X, int N, int D, const float* means, cons
   const int grid = units < num_sms ? units : num_sms;
   float* outp = (S > 1) ? part : M;
   stein_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, Xt, N, Np, D, Dn, means, W, active, wmaxp, minf,
-                                                    scal, K, S, outp);
+                                                    scal, K, S, flush_blocks(), outp);
   if ((rc = check_launch("stein_tc_kernel"))) return rc;
   if (S > 1) {
     const long long per = (long long)K * D * D;
