@@ -77,6 +77,9 @@ class GMM:
             + [e.to(torch.float32).unsqueeze(1) for e in extras_local]
         packed = shard.all_gather_rows(torch.cat(cols, dim=1).contiguous(), K)
         D = self.num_dimensions
+        # the inverse factors FIRST: NCCL runs a communicator's collectives in issue order, and the weight-update pass
+        # waits for this gather, not for the factors' (which nobody waits for in steady state)
+        linv = None if self.diagonal_covs else shard.all_gather_rows(l_loc, K, out=so.get("linv"))
         self.means = packed[:, :D].contiguous()
         chol_full, chol_work = shard.all_gather_rows_async(chol_local, K, out=so.get("chol"))
         self.chol_cov = chol_full               # (the setter waits for a previous in-flight gather)
@@ -84,7 +87,6 @@ class GMM:
         self._local_chol = (self._version, a, b, chol_local)
         c = D
         if not self.diagonal_covs:
-            linv = shard.all_gather_rows(l_loc, K, out=so.get("linv"))
             ops.invalidate_split(linv)
             self._prepared = (self._version, linv, None, packed[:, c].contiguous())
             c += 1
