@@ -112,7 +112,15 @@ class GMMVI:
                 self._graph_stable += 1
                 return False
             buf = None if noise is None else torch.empty_like(noise, memory_format=torch.contiguous_format)
-            graphs[slot] = GraphedIteration(self, noise_buffer=buf).capture()
+            from .graphed import GraphCaptureError
+            try:
+                graphs[slot] = GraphedIteration(self, noise_buffer=buf).capture()
+            except GraphCaptureError as e:
+                # e.g. a user target that synchronises with the host: keep working, op by op
+                import warnings
+                warnings.warn(f"{e}; continuing with op-by-op iterations")
+                self.enable_cuda_graph(False)
+                return False
             self.graph_captures += 1
             self._graph_retired = None
         if noise is not None:

@@ -44,6 +44,11 @@ def _slots(gmmvi):
     return gmm, out
 
 
+class GraphCaptureError(RuntimeError):
+    """The iteration could not be captured (e.g. a user-supplied target synchronises with the host inside
+    `log_density`); the caller falls back to op-by-op iterations."""
+
+
 class GraphState:
     """Static buffers of one number of components, shared by the graphs captured for it."""
 
@@ -155,8 +160,20 @@ class GraphedIteration:
         # (GMMVI <-> GraphedIteration is a cycle) and freeing its memory pool invalidates the capture in progress.
         gc_was_enabled = gc.isenabled()
         gc.disable()                    # (no gc.collect() here: a full collection costs tens of ms per capture)
+        updates0 = g.num_updates
         try:
             self._capture(g, st)
+        except Exception as e:
+            # nothing was executed: put the host-side counters back, leave the model on the (valid) static buffers
+            g.sample_db.num_samples_written, g.num_updates = written0, updates0
+            ops.KERNELS, ops.LAUNCHES = kernels0, calls0
+            self.graph = None
+            st.install()
+            ops.clear_caches()
+            for t in (st.prep[:2] if st.full else ()):
+                ops.invalidate_split(t)
+            torch.cuda.synchronize()
+            raise GraphCaptureError(f"CUDA-graph capture of the iteration failed: {type(e).__name__}: {e}") from e
         finally:
             if gc_was_enabled:
                 gc.enable()
@@ -186,8 +203,13 @@ class GraphedIteration:
             self.graph.capture_begin(pool=g._graph_pool, capture_error_mode="thread_local")
             try:
                 self._captured_region(g, st)
-            finally:
-                self.graph.capture_end()
+            except BaseException:
+                try:
+                    self.graph.capture_end()          # leave capture mode; an invalidated capture raises again here
+                except Exception:
+                    pass
+                raise
+            self.graph.capture_end()
         torch.cuda.current_stream(gmm.device).wait_stream(stream)
 
     def _captured_region(self, g, st):

@@ -138,3 +138,43 @@ def test_rng_and_noise_graphs_share_their_state():
             assert set(g._graph) == {"rng", "noise"} and g._graph["rng"].replays >= iters - 2
     for n in runs[0]:
         assert np.array_equal(runs[0][n], runs[1][n]), (n, float(np.max(np.abs(runs[0][n] - runs[1][n]))))
+
+
+def test_capture_failure_falls_back_to_eager_iterations():
+    """A target that synchronises with the host inside log_density cannot be captured: graph mode must turn itself off,
+    warn, and the run must continue op by op with the same results as a run that never tried."""
+    from gmmvi_b200 import rng
+    from gmmvi_b200.experiments.target_distributions.lnpdf import LNPDF
+
+    class SyncingTarget(LNPDF):
+        def __init__(self, inner):
+            super().__init__(use_log_density_and_grad=True)
+            self.inner = inner
+
+        def get_num_dimensions(self):
+            return self.inner.get_num_dimensions()
+
+        def log_density_and_grad(self, x):
+            v, g = self.inner.log_density_and_grad(x)
+            float(v[0].item())                      # device -> host read: illegal while a stream is capturing
+            return v, g
+
+    results = []
+    for graph in (False, True):
+        rng.set_seed(5)
+        g = _fixed(6, 32, 64)
+        g.sample_selector.target_distribution = SyncingTarget(g.sample_selector.target_distribution)
+        if graph:
+            g.enable_cuda_graph()
+            with pytest.warns(UserWarning, match="capture of the iteration failed"):
+                for _ in range(4):
+                    g.train_iter()
+            assert not g._graph_enabled
+        else:
+            for _ in range(4):
+                g.train_iter()
+        torch.cuda.synchronize()
+        assert g.num_updates == 4
+        results.append(_state(g))
+    for n in results[0]:
+        assert np.array_equal(results[0][n], results[1][n]), n
