@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _fixed(K, D, desired, updater="trust-region", diag=False):
+def _fixed(K, D, desired, updater="trust-region", diag=False, variant=None):
     from gmmvi_b200.experiments.target_distributions.gmm import GMM_LNPDF
     from gmmvi_b200.models.diagonal_gmm import DiagonalGMM
     from gmmvi_b200.models.full_cov_gmm import FullCovGMM
@@ -25,6 +25,17 @@ def _fixed(K, D, desired, updater="trust-region", diag=False):
     cfg["weight_stepsize_adapter_type"] = "improvement_based"
     cfg["weight_stepsize_adapter_config"] = {"initial_stepsize": 0.5, "min_stepsize": 0.0001, "max_stepsize": 1.0,
                                              "stepsize_inc_factor": 1.15, "stepsize_dec_factor": 0.85}
+    if variant == "more":            # MORE estimator (ng_estimator.py:296-376) inside the graph
+        cfg["ng_estimator_type"] = "MORE"
+        cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": 1e-8,
+                                      "use_self_normalized_importance_weights": True}
+    elif variant == "decaying":      # decaying stepsizes (device counters), temperature != 1, own samples only
+        cfg["temperature"] = 0.7
+        cfg["ng_estimator_config"]["only_use_own_samples"] = True
+        cfg["component_stepsize_adapter_type"] = "decaying"
+        cfg["component_stepsize_adapter_config"] = {"initial_stepsize": 0.05, "annealing_exponent": 0.6}
+        cfg["weight_stepsize_adapter_type"] = "decaying"
+        cfg["weight_stepsize_adapter_config"] = {"initial_stepsize": 0.5, "annealing_exponent": 0.4}
     w = np.ones(K, np.float32) / K
     model = DiagonalGMM(w, means, np.stack([np.diag(c) for c in covs])) if diag else FullCovGMM(w, means, covs)
     target = GMM_LNPDF(np.ones(3) / 3, tm, tA @ tA.transpose(0, 2, 1) / D + np.eye(D))
@@ -38,17 +49,19 @@ def _state(g):
              "reward_history", "weight_history")}
 
 
-@pytest.mark.parametrize("K,D,desired,updater,diag", [(8, 32, 64, "trust-region", False), (6, 96, 128, "trust-region", False),
-                                                      (5, 12, 50, "iBLR", False), (6, 16, 40, "trust-region", True)])
-def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag):
+@pytest.mark.parametrize("K,D,desired,updater,diag,variant", [
+    (8, 32, 64, "trust-region", False, None), (6, 96, 128, "trust-region", False, None), (5, 12, 50, "iBLR", False, None),
+    (6, 16, 40, "trust-region", True, None), (3, 6, 400, "trust-region", False, "more"),
+    (5, 20, 80, "trust-region", False, "decaying"), (4, 24, 60, "direct", False, "decaying")])
+def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag, variant):
     from gmmvi_b200 import rng
     iters = 6
     rng.set_seed(11)
-    eager = _fixed(K, D, desired, updater, diag)
+    eager = _fixed(K, D, desired, updater, diag, variant)
     for _ in range(iters):
         eager.train_iter()
     rng.set_seed(11)
-    graphed = _fixed(K, D, desired, updater, diag)
+    graphed = _fixed(K, D, desired, updater, diag, variant)
     graphed.enable_cuda_graph()
     for _ in range(iters):
         graphed.train_iter()
