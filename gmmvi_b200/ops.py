@@ -8,6 +8,7 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import os
+import weakref
 
 import torch
 
@@ -57,7 +58,7 @@ _ABSMAX_CACHE = []      # [(key, tensor, out)]
 
 
 # Split operands of STATIC parameter buffers (a CUDA-graph runner's, optimization/graphed.py):
-# {source address: [hi, lo, tmax, valid, C-ABI call]}.  The split of such a buffer is written into its registered operand
+# {source address: [hi, lo, tmax, valid, C-ABI call, weak reference to the source tensor]}.  The split of such a buffer is written into its registered operand
 # buffers, and while `valid` is set (the operands were produced from the buffer's current content) it is not recomputed;
 # whoever rewrites the buffer calls invalidate_split().
 _SPLIT_STATIC = {}
@@ -65,7 +66,13 @@ _SPLIT_CALL = {"lower": "gvi_split_h16_f32", "full": "gvi_split_h16_full_f32"}
 
 
 def split_registered(src):
-    return _SPLIT_STATIC.get(src.data_ptr())
+    """The registry entry of exactly this tensor object (an address can be recycled by the allocator once a graph runner
+    and its buffers are gone: a stale entry must never be served to the new owner of the address)."""
+    e = _SPLIT_STATIC.get(src.data_ptr())
+    if e is not None and e[5]() is not src:
+        del _SPLIT_STATIC[src.data_ptr()]
+        return None
+    return e
 
 
 def register_split_buffers(src, kind="lower", valid=False):
@@ -76,9 +83,12 @@ def register_split_buffers(src, kind="lower", valid=False):
     ok = lib.gvi_logdens_full_h16_supported(int(D)) if kind == "lower" else lib.gvi_mixture_grad_full_h16_supported(int(D))
     if not (USE_TENSOR_CORES and ok):
         return None
+    for ptr in [ptr for ptr, old in _SPLIT_STATIC.items() if old[5]() is None]:      # buffers of runners that are gone
+        del _SPLIT_STATIC[ptr]
     Dp = lib.gvi_h16_padded_dim(D)
     hi = torch.empty((K, Dp, Dp), device=src.device, dtype=torch.float16)
-    e = [hi, torch.empty_like(hi), torch.empty(K, device=src.device, dtype=torch.float32), bool(valid), _SPLIT_CALL[kind]]
+    e = [hi, torch.empty_like(hi), torch.empty(K, device=src.device, dtype=torch.float32), bool(valid), _SPLIT_CALL[kind],
+         weakref.ref(src)]
     _SPLIT_STATIC[src.data_ptr()] = e
     return e
 
@@ -86,7 +96,7 @@ def register_split_buffers(src, kind="lower", valid=False):
 def invalidate_split(src):
     """`src` was rewritten in place (raw-pointer kernel / collective: torch's version counter does not see it): its
     registered split operands are stale, and so is anything memoised on its address."""
-    e = _SPLIT_STATIC.get(src.data_ptr())
+    e = split_registered(src)
     if e is not None:
         e[3] = False
         clear_memo()
@@ -97,7 +107,7 @@ def clear_split_registry():
 
 
 def _split_static(src):
-    e = _SPLIT_STATIC.get(src.data_ptr())
+    e = split_registered(src)
     if e is None:
         return None
     K, D, _ = src.shape
