@@ -208,6 +208,16 @@ class GraphedIteration:
                     self.graph.capture_end()          # leave capture mode; an invalidated capture raises again here
                 except Exception:
                     pass
+                # torch's CUDA generator stays in "capturing" state when capture_end fails (every later torch.randn would
+                # raise "Offset increment outside graph capture"): a trivial capture that succeeds puts it back
+                try:
+                    dummy = torch.cuda.CUDAGraph()
+                    dummy.capture_begin(capture_error_mode="thread_local")
+                    st.counter.add_(0)
+                    dummy.capture_end()
+                    del dummy
+                except Exception:
+                    pass
                 raise
             self.graph.capture_end()
         torch.cuda.current_stream(gmm.device).wait_stream(stream)

@@ -183,6 +183,7 @@ def test_capture_failure_falls_back_to_eager_iterations():
                 for _ in range(4):
                     g.train_iter()
             assert not g._graph_enabled
+            torch.randn(4, device="cuda")           # torch's CUDA generator was put back into its normal state
         else:
             for _ in range(4):
                 g.train_iter()
