@@ -5,9 +5,13 @@ One "step" = one full SAMTRON iteration (sample -> log-density / background -> S
 component update -> trust-region weight update) of a K=512-component, D=256 full-covariance GMM on 65,536
 samples per iteration (128 per component), GMM target, no sample reuse.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C3w|C4d|C4f|C5]
+                    [--no-graph] [--no-parity] [--no-cpu] [--no-dense]
 
-Prints ONE JSON line (rank 0).  `value` = iterations/s with all inputs resident in HBM; `e2e` = the same through
+Prints ONE JSON line (rank 0).  The iteration runs as one CUDA graph per rank unless --no-graph (same kernels and NCCL
+collectives, one launch).  At N > 1 the line carries `parity_vs_1gpu`: the sharded iteration against the single-GPU iteration
+on identical samples, measured after the timed regions.  `--config` selects one of the other BASELINE.json configurations
+(single GPU, through GmmviRunner, with an un-extrapolated CPU figure of the oracle beside it).  `value` = iterations/s with all inputs resident in HBM; `e2e` = the same through
 GMMVI.train_iter with the step's noise coming from pinned host memory and the updated mixture read back;
 `roofline` describes the dominant kernel (component log-density); `cpu_baseline` times the oracle (restated
 reference, NumPy/OpenBLAS fp32) on a bounded sample of the same workload on this box's host cores.
