@@ -97,9 +97,10 @@ class GMMVI:
             if getattr(self, "_graph_K", None) is not None:
                 replays = max((g.replays for g in graphs.values()), default=0)
                 self._graph_patience = 1 if replays >= 16 else min(2 * self._graph_patience + 1, 63)
-            # the retired graphs stay alive until the next capture has begun: the shared memory pool exists only while a
-            # graph uses it
-            self._graph_retired = list(graphs.values()) or getattr(self, "_graph_retired", None)
+            # the retired graphs stay alive until the next capture has begun (the shared memory pool exists only while a
+            # graph uses it) -- unless K keeps changing and the next capture is far away: then their memory is released
+            self._graph_retired = ((list(graphs.values()) or getattr(self, "_graph_retired", None))
+                                   if self._graph_patience <= 1 else None)
             graphs, self._graph_stable, self._graph_K = {}, 0, K
             if getattr(self, "_graph_state", None) is not None:
                 self._graph_state.release()
