@@ -164,8 +164,18 @@ def _sharded_worker(rank, world, port, K, N, lq, bg, rho, out_dir):
     a, b = sc.component_range(K)
     mine = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64) + 0.5
     gathered = sc.all_gather_rows(mine, K)
+    # round 2: gathers into a caller-owned (static) buffer when it fits, into a fresh one when it does not; the
+    # asynchronous variant; and the reduce-scatter of raw statistics by component
+    static = torch.full((K, 3), -1.0, dtype=torch.float64)
+    into = sc.all_gather_rows(mine, K, out=static)
+    wrong = sc.all_gather_rows(mine, K, out=torch.zeros((K + 1, 3), dtype=torch.float64))
+    async_out, work = sc.all_gather_rows_async(mine, K, out=torch.empty((K, 3), dtype=torch.float64))
+    work.wait()
+    stats = torch.arange(K * 2, dtype=torch.float64).reshape(K, 2) * (rank + 1)
+    full = sc.all_reduce_sum_(stats.clone())     # (gloo has no reduce_scatter_tensor: the all-reduce fallback + own rows)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), W=W.numpy(), dot=dot.numpy(), gathered=gathered.numpy(),
-             lo=lo, hi=hi)
+             lo=lo, hi=hi, into_is_static=into.data_ptr() == static.data_ptr(), into=into.numpy(), wrong=wrong.numpy(),
+             async_out=async_out.numpy(), own_stats=full[a:b].numpy())
     dist.destroy_process_group()
 
 
@@ -188,6 +198,27 @@ def test_sharded_importance_weights_match_unsharded_gloo(tmp_path):
     for p in parts:
         assert np.allclose(p["dot"], w @ rho, rtol=1e-12)
         assert np.allclose(p["gathered"][:, 0], np.arange(K) + 0.5)
+        assert bool(p["into_is_static"]) and np.array_equal(p["into"], p["gathered"])
+        assert p["wrong"].shape == (K, 3) and np.array_equal(p["wrong"], p["gathered"])
+        assert np.array_equal(p["async_out"], p["gathered"])
+    c = K // world
+    for r, p in enumerate(parts):            # sum over ranks of stats * (rank + 1) = 3 * stats for two ranks
+        assert np.array_equal(p["own_stats"], 3.0 * np.arange(K * 2, dtype=np.float64).reshape(K, 2)[r * c:(r + 1) * c])
+
+
+def test_rng_device_mode_bookkeeping():
+    """gmmvi_b200/rng.py: draws inside a graph capture use (device counter, offset); replays advance the host counter."""
+    from gmmvi_b200 import rng
+    rng.set_seed(3)
+    assert rng.next_subsequence() == 0 and rng.next_subsequence() == 1
+    assert rng.device_counter() is None
+    counter = object()
+    rng.begin_device_mode(counter)
+    assert rng.device_counter() == (counter, 0) and rng.device_counter() == (counter, 1)
+    assert rng.end_device_mode() == 2 and rng.device_counter() is None
+    assert rng.next_subsequence() == 2          # the capture itself did not consume host subsequences
+    rng.advance(2)                              # one replay
+    assert rng.next_subsequence() == 5
 
 
 def test_default_configs_equal_the_reference_yml_files():
