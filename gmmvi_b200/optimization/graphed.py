@@ -88,6 +88,10 @@ class GraphState:
                 for t in self.prep[:2]:
                     ops.invalidate_split(t)
         self.install()
+        if self.full:
+            # a replay starts from VALID split operands (no split kernel is captured at the start of the body)
+            for t in self.prep[:2]:
+                ops.split_static_now(t)
 
     def install(self):
         """Point the model / learner attributes at the static buffers and declare the derived operands valid for them."""

@@ -192,3 +192,26 @@ def test_capture_failure_falls_back_to_eager_iterations():
         results.append(_state(g))
     for n in results[0]:
         assert np.array_equal(results[0][n], results[1][n]), n
+
+
+def test_eager_parameter_change_between_replays_is_picked_up():
+    """User code that replaces the components between two graph replays (here: GMM.replace_components, models/gmm.py:
+    401-418) must see the next replay start from the new parameters, their inverse factors and their split operands."""
+    from gmmvi_b200 import rng
+    K, D, desired = 6, 96, 128
+    runs = []
+    for graph in (False, True):
+        rng.set_seed(31)
+        g = _fixed(K, D, desired)
+        if graph:
+            g.enable_cuda_graph()
+        for i in range(6):
+            g.train_iter()
+            if i == 3:
+                m = g.model
+                m.replace_components(m.means * 1.01 + 0.05, m.chol_cov * 1.1)
+                m.log_density(torch.zeros((4, D), device="cuda"))        # forces the derived operands, eagerly
+        torch.cuda.synchronize()
+        runs.append(_state(g))
+    for n in runs[0]:
+        assert np.array_equal(runs[0][n], runs[1][n]), (n, float(np.max(np.abs(runs[0][n] - runs[1][n]))))
