@@ -269,8 +269,8 @@ class GraphedIteration:
     def replay(self):
         g = self.gmmvi
         st = self.state
-        if getattr(st.gmm, "_means") is not st.statics[1] or getattr(st.gmm, "_chol_cov") is not st.statics[2]:
-            st.sync_from_model()            # eager code replaced the parameters since the last replay
+        if any(getattr(o, n) is not s for (o, n), s in zip(st.slots, st.statics)):
+            st.sync_from_model()            # eager code replaced parameters / learner state since the last replay
         st.set_counter()
         self.graph.replay()
         st.host_subsequence += self.draws

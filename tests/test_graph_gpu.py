@@ -211,6 +211,9 @@ def test_eager_parameter_change_between_replays_is_picked_up():
                 m = g.model
                 m.replace_components(m.means * 1.01 + 0.05, m.chol_cov * 1.1)
                 m.log_density(torch.zeros((4, D), device="cuda"))        # forces the derived operands, eagerly
+            if i == 4:                                                    # only O(K) state replaced
+                g.model.replace_weights(g.model.log_weights + torch.linspace(0, 0.3, K, device="cuda"))
+                g.model.update_stepsizes(g.model.stepsizes * 0.9)
         torch.cuda.synchronize()
         runs.append(_state(g))
     for n in runs[0]:
