@@ -21,80 +21,79 @@ size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
 namespace dg {
 
 constexpr int TS = 128;      // samples per CTA
-constexpr int KC = 8;        // components per staged chunk
+constexpr int CPC = 32;      // components per CTA (their accumulators live in registers across the coordinate chunks)
 constexpr int DC = 32;       // coordinates held in registers at a time
 
 // lq[k, n] = -D/2 log 2 pi - sum_d log sigma_kd - 1/2 sum_d ((mu_kd - x_nd) / sigma_kd)^2       (diagonal_gmm.py:31-34, 47-53)
+// Loop order: coordinate chunk outside, component inside, so that a thread reads its 32 coordinates ONCE per chunk (a row
+// per thread is an uncoalesced access: 32 L1 wavefronts per warp-wide load, and with the component chunk outside the kernel
+// was bound by exactly those: ncu l1tex 85 %, profiles/r02_ncu_logdens_diag2.txt) and the 32 accumulators stay in registers.
 __global__ void __launch_bounds__(TS)
 logdens_diag2_kernel(const float* __restrict__ X, int N, int D, int Dp, const float* __restrict__ means,
-                     const float* __restrict__ stds, int K, int kchunks_per_cta, float* __restrict__ lq) {
+                     const float* __restrict__ stds, int K, float* __restrict__ lq) {
   extern __shared__ __align__(16) float smem[];
-  float2* par = reinterpret_cast<float2*>(smem);            // [KC][Dp] (mu, 1 / sigma); (0, 0) past D
-  float* cst = smem + 2 * KC * Dp;                          // [KC]
+  float2* par = reinterpret_cast<float2*>(smem);            // [CPC][Dp] (mu, 1 / sigma); (0, 0) past D
+  float* cst = smem + 2 * CPC * Dp;                         // [CPC]
   const int n = blockIdx.x * TS + threadIdx.x;
   const bool live = n < N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0);
-  const int k_begin = blockIdx.y * kchunks_per_cta * KC;
-  const int k_end = min(K, k_begin + kchunks_per_cta * KC);
-  for (int k0 = k_begin; k0 < k_end; k0 += KC) {
-    const int nk = min(KC, k_end - k0);
-    __syncthreads();
-    for (int kk = warp; kk < nk; kk += TS / 32) {
-      const float* mu = means + (long long)(k0 + kk) * D;
-      const float* sg = stds + (long long)(k0 + kk) * D;
-      float ls = 0.f;
-      for (int d = lane; d < Dp; d += 32) {
-        float2 p = make_float2(0.f, 0.f);
-        if (d < D) {
-          const float s = __ldg(sg + d);
-          p = make_float2(__ldg(mu + d), 1.f / s);
-          ls += logf(s);
-        }
-        par[kk * Dp + d] = p;
+  const int k0 = blockIdx.y * CPC;
+  const int nk = min(CPC, K - k0);
+  for (int kk = warp; kk < nk; kk += TS / 32) {
+    const float* mu = means + (long long)(k0 + kk) * D;
+    const float* sg = stds + (long long)(k0 + kk) * D;
+    float ls = 0.f;
+    for (int d = lane; d < Dp; d += 32) {
+      float2 p = make_float2(0.f, 0.f);
+      if (d < D) {
+        const float s = __ldg(sg + d);
+        p = make_float2(__ldg(mu + d), 1.f / s);
+        ls += logf(s);
       }
-      ls = warp_sum(ls);
-      if (lane == 0) cst[kk] = -0.5f * (float)D * kLog2Pi - ls;
+      par[kk * Dp + d] = p;
     }
-    __syncthreads();
-    if (!live) continue;
-    float acc[KC];
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk) acc[kk] = 0.f;
-    for (int d0 = 0; d0 < Dp; d0 += DC) {
-      float x[DC];
-      const float* xr = X + (long long)n * D + d0;
-      if (vec) {
-#pragma unroll
-        for (int j = 0; j < DC; j += 4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (d0 + j < D) v = __ldg(reinterpret_cast<const float4*>(xr + j));
-          x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < DC; ++j) x[j] = (d0 + j < D) ? __ldg(xr + j) : 0.f;
-      }
-#pragma unroll
-      for (int kk = 0; kk < KC; ++kk) {
-        if (kk < nk) {
-          const float4* p4 = reinterpret_cast<const float4*>(par + kk * Dp + d0);
-          float a0 = acc[kk], a1 = 0.f;                     // two chains: the FMA latency is exposed otherwise
-#pragma unroll
-          for (int j = 0; j < DC; j += 2) {
-            const float4 p = p4[j >> 1];                    // (mu_j, isg_j, mu_j+1, isg_j+1)
-            const float t0 = (p.x - x[j]) * p.y, t1 = (p.z - x[j + 1]) * p.w;
-            a0 = fmaf(t0, t0, a0);
-            a1 = fmaf(t1, t1, a1);
-          }
-          acc[kk] = a0 + a1;
-        }
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk)
-      if (kk < nk) lq[(long long)(k0 + kk) * N + n] = cst[kk] - 0.5f * acc[kk];
+    ls = warp_sum(ls);
+    if (lane == 0) cst[kk] = -0.5f * (float)D * kLog2Pi - ls;
   }
+  __syncthreads();
+  if (!live) return;
+  float acc[CPC];
+#pragma unroll
+  for (int kk = 0; kk < CPC; ++kk) acc[kk] = 0.f;
+  for (int d0 = 0; d0 < Dp; d0 += DC) {
+    float x[DC];
+    const float* xr = X + (long long)n * D + d0;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < DC; j += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d0 + j < D) v = __ldg(reinterpret_cast<const float4*>(xr + j));
+        x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DC; ++j) x[j] = (d0 + j < D) ? __ldg(xr + j) : 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < CPC; ++kk) {
+      if (kk < nk) {
+        const float4* p4 = reinterpret_cast<const float4*>(par + kk * Dp + d0);
+        float a0 = acc[kk], a1 = 0.f;                     // two chains: the FMA latency is exposed otherwise
+#pragma unroll
+        for (int j = 0; j < DC; j += 2) {
+          const float4 p = p4[j >> 1];                    // (mu_j, isg_j, mu_j+1, isg_j+1)
+          const float t0 = (p.x - x[j]) * p.y, t1 = (p.z - x[j + 1]) * p.w;
+          a0 = fmaf(t0, t0, a0);
+          a1 = fmaf(t1, t1, a1);
+        }
+        acc[kk] = a0 + a1;
+      }
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < CPC; ++kk)
+    if (kk < nk) lq[(long long)(k0 + kk) * N + n] = cst[kk] - 0.5f * acc[kk];
 }
 
 // B[n] = [x_n o g_n | g_n]  (N x 2D)
@@ -135,17 +134,12 @@ int launch_logdens_diag2(const float* X, int N, int D, const float* means, const
                          cudaStream_t st) {
   using namespace dg;
   const int Dp = ceil_div(D, DC) * DC;
-  const size_t smem = (size_t)(2 * KC * Dp + KC) * sizeof(float);
-  if (smem > 200 * 1024) return 1;                    // D > ~3000: the caller keeps the first-generation kernel
+  const size_t smem = (size_t)(2 * CPC * Dp + CPC) * sizeof(float);
+  if (smem > 200 * 1024) return 1;                    // D > ~780: the caller keeps the first-generation kernel
   static unsigned long long attr_set_mask = 0;
-  if (smem > 48 * 1024 && first_call_on_device(attr_set_mask)) {
+  if (smem > 48 * 1024 && first_call_on_device(attr_set_mask))
     cudaFuncSetAttribute(logdens_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  }
-  const int nb = ceil_div(N, TS), kchunks = ceil_div(K, KC);
-  int ysplit = min(kchunks, max(1, ceil_div(148 * 8, nb)));     // >= 8 CTAs (32 warps) per SM
-  const int per = ceil_div(kchunks, ysplit);
-  ysplit = ceil_div(kchunks, per);
-  logdens_diag2_kernel<<<dim3(nb, ysplit), TS, smem, st>>>(X, N, D, Dp, means, stds, K, per, lq);
+  logdens_diag2_kernel<<<dim3(ceil_div(N, TS), ceil_div(K, CPC)), TS, smem, st>>>(X, N, D, Dp, means, stds, K, lq);
   return check_launch("logdens_diag2_kernel");
 }
 
