@@ -21,7 +21,7 @@ size_t tc_gemm_workspace_floats(int batch, int M, int N, int Kd);
 namespace dg {
 
 constexpr int TS = 128;      // samples per CTA
-constexpr int CPC = 32;      // components per CTA (their accumulators live in registers across the coordinate chunks)
+constexpr int CPC = 16;      // components per CTA (their accumulators live in registers across the coordinate chunks)
 constexpr int DC = 32;       // coordinates held in registers at a time
 
 // lq[k, n] = -D/2 log 2 pi - sum_d log sigma_kd - 1/2 sum_d ((mu_kd - x_nd) / sigma_kd)^2       (diagonal_gmm.py:31-34, 47-53)
