@@ -166,6 +166,36 @@ class LinSampleSelector(SampleSelector):
         new_samples, mapping = self.model.sample(n_add, uniforms=uniforms, noise=noise)
         return new_samples, mapping, num_reused_samples
 
+    def select_samples_deferred(self, noise=None):
+        """The no-reuse iteration of the mixture-based selector WITHOUT touching the sample database (see
+        VipsSampleSelector.select_samples_deferred): n_eff = 0 without old samples, so n_add = desired
+        (sample_selector.py:300-312); the component of every draw comes from the device generator, the per-component
+        counts stay on the device (the sampling kernel is launched for the worst case of one component drawing everything);
+        the background density weights every component by its share of the draws (sample_db.py:217-227; a component
+        that drew nothing has weight 0)."""
+        if self.reused_samples_per_component != 0:
+            raise NotImplementedError("select_samples_deferred needs ratio_reused_samples_to_desired = 0")
+        m, db = self.model, self.sample_db
+        n_add = max(1, self.desired_samples_per_component)
+        K = m.num_components
+        comps = m.sample_categorical(n_add)
+        counts = torch.zeros(K, device=m.device, dtype=torch.int32)
+        counts.scatter_add_(0, comps.long(), torch.ones_like(comps))
+        new_samples, _ = m.sample_from_components_no_shuffle(counts, noise=noise, total=n_add, max_per_component=n_add)
+        grads, lnpdfs = self.get_target_grads(new_samples)
+        weight = counts.to(torch.float32) / float(n_add)
+        if m.diagonal_covs:
+            chols = m.chol_cov
+            bg, _ = db.evaluate_background(weight, m.means, chols, None, new_samples.contiguous())
+            payload = (new_samples, m.means.clone(), chols.clone(), lnpdfs, grads, comps, None) if db.keep_samples else None
+        else:
+            linv, _, cst = m.prepared(need_prec=False)
+            chols = m.chol_cov
+            bg, _ = db.evaluate_background(weight, m.means, chols, linv, new_samples.contiguous(), cst)
+            payload = ((new_samples, m.means.clone(), chols.clone(), lnpdfs, grads, comps,
+                        (linv.clone(), None, cst.clone())) if db.keep_samples else None)
+        return (new_samples, comps, bg, lnpdfs, grads), payload
+
     def select_samples(self, noise=None, uniforms=None):
         """sample_selector.py:327-339.  `noise` / `uniforms` inject the draws of GMM.sample (parity tests)."""
         new_samples, mapping, num_reused_samples = self.sample_where_needed(noise, uniforms)

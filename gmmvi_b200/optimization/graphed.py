@@ -18,7 +18,7 @@ What makes an iteration replayable:
   * no host synchronisation inside: the body is the no-reuse iteration (`select_samples_deferred`), whose shapes depend
     only on the number of components; the sample database is appended to after the replay;
   * NCCL collectives of a sharded run are captured like any other kernel.
-Supported: component-based selector with ratio_reused_samples_to_desired = 0, any estimator / updater / stepsize rule.
+Supported: both selectors with ratio_reused_samples_to_desired = 0, any estimator / updater / stepsize rule.
 A change of the number of components drops the graphs; they are captured again once K has been stable for a while."""
 from __future__ import annotations
 
@@ -130,10 +130,10 @@ class GraphState:
 
 class GraphedIteration:
     def __init__(self, gmmvi, noise_buffer=None):
-        from .gmmvi_modules.sample_selector import VipsSampleSelector
         sel = gmmvi.sample_selector
-        if not isinstance(sel, VipsSampleSelector) or sel.reused_samples_per_component != 0:
-            raise NotImplementedError("CUDA-graph iterations need the component-based selector without sample reuse")
+        if not hasattr(sel, "select_samples_deferred") or sel.reused_samples_per_component != 0:
+            raise NotImplementedError("CUDA-graph iterations need a selector without sample reuse "
+                                      "(ratio_reused_samples_to_desired = 0)")
         self.gmmvi = gmmvi
         self.noise_buffer = noise_buffer            # static [N, D] buffer the caller fills before each replay (optional)
         self.graph = None

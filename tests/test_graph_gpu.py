@@ -29,6 +29,13 @@ def _fixed(K, D, desired, updater="trust-region", diag=False, variant=None):
         cfg["ng_estimator_type"] = "MORE"
         cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": 1e-8,
                                       "use_self_normalized_importance_weights": True}
+    elif variant == "lin-stein":
+        cfg["sample_selector_type"] = "mixture-based"
+    elif variant == "lin-more":      # BASELINE C3's algorithm: mixture-based selector (desired = TOTAL samples) + MORE
+        cfg["sample_selector_type"] = "mixture-based"
+        cfg["ng_estimator_type"] = "MORE"
+        cfg["ng_estimator_config"] = {"only_use_own_samples": False, "initial_l2_regularizer": 1e-8,
+                                      "use_self_normalized_importance_weights": True}
     elif variant == "decaying":      # decaying stepsizes (device counters), temperature != 1, own samples only
         cfg["temperature"] = 0.7
         cfg["ng_estimator_config"]["only_use_own_samples"] = True
@@ -52,15 +59,18 @@ def _state(g):
 @pytest.mark.parametrize("K,D,desired,updater,diag,variant", [
     (8, 32, 64, "trust-region", False, None), (6, 96, 128, "trust-region", False, None), (5, 12, 50, "iBLR", False, None),
     (6, 16, 40, "trust-region", True, None), (3, 6, 400, "trust-region", False, "more"),
-    (5, 20, 80, "trust-region", False, "decaying"), (4, 24, 60, "direct", False, "decaying")])
+    (5, 20, 80, "trust-region", False, "decaying"), (4, 24, 60, "direct", False, "decaying"),
+    (3, 6, 900, "trust-region", False, "lin-more"), (4, 40, 512, "trust-region", False, "lin-stein")])
 def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag, variant):
     from gmmvi_b200 import rng
     iters = 6
     rng.set_seed(11)
+    torch.manual_seed(123)           # the mixture-based selector draws its components from torch's generator
     eager = _fixed(K, D, desired, updater, diag, variant)
     for _ in range(iters):
         eager.train_iter()
     rng.set_seed(11)
+    torch.manual_seed(123)
     graphed = _fixed(K, D, desired, updater, diag, variant)
     graphed.enable_cuda_graph()
     for _ in range(iters):
@@ -74,6 +84,7 @@ def test_graph_replays_equal_eager_iterations(K, D, desired, updater, diag, vari
         assert np.array_equal(a[n], b[n]), (n, float(np.max(np.abs(a[n] - b[n]))))
     # the database holds the last iteration's samples in both modes
     assert torch.equal(eager.sample_db.samples, graphed.sample_db.samples)
+    assert torch.equal(eager.sample_db.mapping, graphed.sample_db.mapping)
 
 
 def test_graph_with_injected_noise_equals_eager():
