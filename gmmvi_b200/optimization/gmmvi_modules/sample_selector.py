@@ -183,7 +183,11 @@ class LinSampleSelector(SampleSelector):
         counts.scatter_add_(0, comps.long(), torch.ones_like(comps))
         new_samples, _ = m.sample_from_components_no_shuffle(counts, noise=noise, total=n_add, max_per_component=n_add)
         grads, lnpdfs = self.get_target_grads(new_samples)
-        weight = counts.to(torch.float32) / float(n_add)
+        # count / sum(count) with a DEVICE divisor, exactly like get_newest_samples (sample_db.py:226): dividing by a Python
+        # scalar is a multiplication by its rounded reciprocal in torch, one ulp off for some counts -- MORE amplifies that
+        # to 1e-4 in the updated means (found by the eager-vs-graph comparison, profiles/debug/deferred_vs_eager_probe.py)
+        cf = counts.to(torch.float32)
+        weight = cf / torch.sum(cf)
         if m.diagonal_covs:
             chols = m.chol_cov
             bg, _ = db.evaluate_background(weight, m.means, chols, None, new_samples.contiguous())
