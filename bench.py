@@ -654,7 +654,9 @@ def run_config(args):
     from gmmvi_b200 import ops
     name = args.config
     torch.cuda.set_device(0)
-    runner, config = build_config_runner(name, not args.no_graph)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # the config helpers print like the reference's; stdout = ONE JSON line
+        runner, config = build_config_runner(name, not args.no_graph)
     g = runner.gmmvi
     warm = max(args.warmup, 12)              # past the first component additions / the deletion window of C1 / C2
     if name in ("C1", "C2") and args.steps < 120:
