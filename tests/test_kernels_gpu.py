@@ -646,3 +646,33 @@ def test_construction_time_cholesky():
     bad = np.stack([np.eye(4, dtype=np.float32), -np.eye(4, dtype=np.float32)])
     L, ok = ops.cholesky(dev(bad))
     assert ok.cpu().numpy().tolist() == [1, 0] and np.isnan(L[1].cpu().numpy()).all() and np.isfinite(L[0].cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("K,D,mode", [(5, 12, "direct"), (4, 64, "direct"), (3, 130, "direct"), (2, 256, "direct"),
+                                      (5, 12, "iBLR"), (3, 96, "iBLR")])
+def test_update_with_nonsymmetric_hessian_matches_oracle(K, D, mode):
+    """gvi_update_full_general_f32: the direct / iBLR update for a NON-symmetric -E[H] (what Stein with standard
+    importance weights hands over, ng_estimator.py:168): general inverse + Cholesky of its lower triangle, restated
+    literally (ng_based_component_updater.py:116-118, 199-200); one component is made to fail (not positive definite)."""
+    from gmmvi_b200 import ops
+    g32, H, gn = _update_problem(K, D, seed=40 + D)
+    rng = np.random.default_rng(41 + D)
+    H = H + 0.15 * rng.standard_normal(H.shape).astype(np.float32) / np.sqrt(D)        # asymmetric part
+    steps = np.full(K, 0.05 if mode == "direct" else 0.02, np.float32)
+    if mode == "direct":          # (the iBLR precision P + s R + s^2/2 R Sigma R is positive definite for any symmetric R)
+        H[-1] = -40.0 * np.eye(D, dtype=np.float32)                                     # P + s R not positive definite
+        steps[-1] = 1.0
+    g32.stepsizes = steps
+    g32.num_received_updates = np.array([0.0] + [1.0] * (K - 1), np.float32)           # iBLR: first update keeps the mean
+    g64 = _as64(g32)
+    info = (O.direct_update if mode == "direct" else O.iblr_update)(g64, H.astype(np.float64), gn.astype(np.float64),
+                                                                    steps.astype(np.float64))
+    _, prec, _, _ = ops.prepare_full(dev(g32.chol_cov))
+    om, oc, succ = ops.update_components_general(mode, dev(g32.means), dev(g32.chol_cov), prec, dev(H), dev(gn), dev(steps),
+                                                 dev(g32.num_received_updates))
+    assert np.array_equal(succ.cpu().numpy().astype(bool), info["success"])
+    assert rel_err(om.cpu().numpy(), g64.means) < NG_RTOL
+    assert rel_err(oc.cpu().numpy(), g64.chol_cov) < NG_RTOL
+    if mode == "direct":          # the rejected component keeps its parameters bit for bit
+        assert not info["success"][-1]
+        assert np.array_equal(om.cpu().numpy()[-1], g32.means[-1]) and np.array_equal(oc.cpu().numpy()[-1], g32.chol_cov[-1])
