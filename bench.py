@@ -432,6 +432,23 @@ def run_ours(args):
         torch.cuda.synchronize()
         dense = max(2, args.steps // 2) / (e0.elapsed_time(e1) * 1e-3)
         del g2
+    dense_block = None
+    if dense is not None:
+        # algorithmic flops of the full iteration with nothing skipped,
+        # P [(D^2 + 4D) 3 + (D^2 + 3D) + 2 D^2] + N (D^2 + D) + K n_kl 3 D^3 + K D^3  (~ 6 P D^2 = 13.3 TFLOP at C5)
+        P_pairs = float(N_total) * K
+        n_kl = float(kl_evals.mean()) if kl_evals is not None else 10.0
+        dense_flop = (P_pairs * ((D * D + 4 * D) * 3 + (D * D + 3 * D) + 2 * D * D) + N_total * (D * D + D)
+                      + K * n_kl * 3.0 * D ** 3 + K * float(D) ** 3)
+        hbm_, bf16_, _, how_ = measured_peaks()
+        dense_block = {"iterations_per_sec": dense, "ms_per_step": 1e3 / dense,
+                       "algorithmic_tflop_per_iteration": dense_flop / 1e12,
+                       "achieved_tflops": dense_flop * dense / 1e12, "peak_tflops": bf16_,
+                       "frac": dense_flop * dense / 1e12 / bf16_,
+                       "note": "components overlap (mean scale 0.05): no (component, sample block) is skipped anywhere; "
+                               "whole-iteration algorithmic flops over the whole-iteration time against the " + how_ +
+                               " bf16 burst; per-kernel ncu figures: profiles/r02_ncu_stein_tc_full_flush32.txt, "
+                               "r02_ncu_mixgrad_h16_dense.txt, r02_ncu_gsum2.txt"}
 
     if rank != 0:
         shutdown_distributed([gmmvi])
@@ -451,7 +468,8 @@ def run_ours(args):
                                   f"component update sharded + all-gather",
                    "l2": "working set per step (~1.2 GB: [K,N] densities, [K,D,D] factors) exceeds the 126 MB L2",
                    "pairs_per_sec_full_iteration": N_total * K / (ms_per_step * 1e-3),
-                   "dense_variant_iterations_per_sec": dense, "finite": finite, "cuda_graph": use_graph,
+                   "dense_variant_iterations_per_sec": dense, "dense_variant": dense_block, "finite": finite,
+                   "cuda_graph": use_graph,
                    "kl_evaluations_per_component": kl_evals_stats},
         "logdens_pairs_per_sec": pairs / (ld_ms * 1e-3),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
