@@ -267,3 +267,18 @@ def test_thinning_reindexes_in_first_occurrence_order():
     assert np.array_equal(db.means.numpy(), odb.means) and np.array_equal(db.chols.numpy(), odb.chols)
     assert np.array_equal(db.samples.numpy(), odb.samples)
     assert db.consts.shape[0] == odb.means.shape[0]
+
+
+def test_bench_traffic_parser_reads_the_committed_ncu_summary():
+    """bench.py's `roofline.traffic` comes from the newest committed ncu summary of the log-density kernel, not a literal."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, src = bench.ncu_dram_traffic()
+    assert src is not None and src.startswith("profiles/r") and src.endswith("_ncu_h16t_logdens.txt")
+    text = open(os.path.join(ROOT, src)).read()
+    rd = float(re.search(r"dram__bytes_read\.sum\s+(\w+)\s+([\d.]+)", text).group(2))
+    assert 1e8 < traffic < 1e10 and traffic > rd      # read + write, in bytes
+    # every BASELINE configuration has a documented --config entry
+    assert set(bench.CONFIG_DOC) == {"C1", "C2", "C3", "C3w", "C4d", "C4f"}
